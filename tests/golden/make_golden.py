@@ -1,0 +1,164 @@
+"""tests/golden/make_golden.py -- regenerates the committed golden vectors.
+
+Runs ONLY in the build container (needs /root/reference compiled into oracle/_ref by
+`make -C oracle ref`).  Inputs are produced by the seeded synthetic generator in
+oracle/gvamp_oracle.c, outputs come from the UNMODIFIED reference (harness library and the
+main_real executable).  The .npz files written here are what `-m "not gpu"` and `-m gpu` tests
+compare against on machines where the reference does not exist.
+
+    python tests/golden/make_golden.py
+"""
+import math
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+from oracle import ref as R  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+PROBS = [0.9, 0.06, 0.04]
+VARS = [0, 1e-4, 1e-3]
+
+
+def case_matvec(tmp):
+    """N % 4 != 0, 2 % missing genotypes, two phenotype NAs: stats / Ax / ATx incl. byte sub-ranges."""
+    N, M, seed = 1003, 400, 11
+    bed = O.synth_bed(seed, 0, M, N, miss_rate=0.02)
+    bedp = os.path.join(tmp, "mv.bed")
+    O.write_bed(bedp, bed)
+    rng = np.random.default_rng(seed)
+    y = rng.normal(size=N)
+    phenp = os.path.join(tmp, "mv.phen")
+    na_idx = [5, 700]
+    O.write_phen(phenp, y, na_idx=na_idx)
+    rd = R.RefData(bedp, N, M, phen_path=phenp)
+    v = rng.normal(size=M)
+    u = rng.normal(size=4 * rd.mbytes)
+    u[N:] = 0.0
+    mave, msig = rd.stats()
+    np.savez_compressed(
+        os.path.join(OUT, "matvec_n1003.npz"), N=N, M=M, seed=seed, miss_rate=0.02, y=y, na_idx=na_idx,
+        mask4=rd.mask4(), nonas=rd.nonas(), phen=rd.filter_pheno(), intercept_scale=np.array(rd.intercept_scale()),
+        mave=mave, msig=msig, v=v, u=u, Ax=rd.Ax(v), ATx=rd.ATx(u), SB=10, LB=100, Ax_sub=rd.Ax(v, 10, 100),
+        ATx_sub=rd.ATx(u[:400], 10, 100), bed_sha=np.frombuffer(__import__("hashlib").sha256(bed.tobytes()).digest(), dtype=np.uint8))
+    # alpha_scale != 1 and a shard with S != 0 of a larger marker set
+    rd2 = R.RefData(bedp, N, 150, Mt=M, S=100, phen_path=phenp, alpha_scale=0.3)
+    mave2, msig2 = rd2.stats()
+    np.savez_compressed(os.path.join(OUT, "matvec_shard.npz"), N=N, M=150, Mt=M, S=100, alpha_scale=0.3, mave=mave2, msig=msig2,
+                        Ax=rd2.Ax(v[100:250]), ATx=rd2.ATx(u))
+
+
+def case_denoiser():
+    N, M = 1000, 5000
+    rng = np.random.default_rng(5)
+    r1 = rng.normal(size=M) * np.where(rng.random(M) < 0.1, 2.0, 0.3)
+    rv = R.RefVamp(N, M, M, PROBS, [v * N for v in VARS])
+    out = {}
+    for tag, gam1 in (("a", 3.0), ("b", 1e-6), ("c", 250.0)):
+        g, gd = rv.g1(r1, gam1)
+        out["g1_" + tag], out["g1d_" + tag], out["gam1_" + tag] = g, gd, gam1
+    # EM update: plain, and one where two variances end within 50 % and merge (vamp.cpp:1054-1071)
+    rv.set_prior(PROBS, [v * N for v in VARS])
+    p, v = rv.update_prior(r1, 3.0)
+    out["em_probs"], out["em_vars"] = p, v
+    p23 = [0.8, 0.05, 0.05, 0.05, 0.05]
+    v23 = [0, 0.1, 0.12, 1.0, 5.0]
+    rv2 = R.RefVamp(N, M, M, p23, v23, EM_max_iter=5, EM_err_thr=1e-4)
+    p, v = rv2.update_prior(r1, 3.0)
+    out["em5_probs_in"], out["em5_vars_in"], out["em5_probs"], out["em5_vars"] = p23, v23, p, v
+    rv3 = R.RefVamp(N, M, M, p23, v23, EM_max_iter=3, EM_err_thr=1e-4, learn_vars=0)
+    p, v = rv3.update_prior(r1, 0.7)
+    out["em5nl_probs"], out["em5nl_vars"] = p, v
+    np.savez_compressed(os.path.join(OUT, "denoiser.npz"), r1=r1, N=N, probs=PROBS, vars=[v * N for v in VARS], **out)
+
+
+def case_probit_pieces():
+    rng = np.random.default_rng(9)
+    x = np.concatenate([np.linspace(-30, 30, 241), rng.normal(size=100) * 5])
+    rv = R.RefVamp(1000, 10, 10, PROBS, VARS)
+    p = rng.normal(size=500) * 2
+    y = (rng.random(500) < 0.5).astype(float)
+    mc = rng.normal(size=500) * 0.3
+    rv.set_state(1e-6, 0.0, 2.0, probit_var=1.0)
+    g, gd = rv.g1_bin_class(p, 0.8, y, mc)
+    eta = np.array([1.0])
+    sim = np.empty(64)
+    R.lib().ref_simulate(64, eta.ctypes.data_as(R.c_f64p), eta.ctypes.data_as(R.c_f64p), 1, 1, sim.ctypes.data_as(R.c_f64p))
+    np.savez_compressed(os.path.join(OUT, "probit_pieces.npz"), x=x, erfcx=R.erfcx(x), p=p, y=y, mcov=mc, tau1=0.8, g=g, gd=gd,
+                        simulate_unit=sim)
+
+
+def case_cg(tmp):
+    N, M, seed = 1000, 1500, 21
+    bed = O.synth_bed(seed, 0, M, N)
+    bedp = os.path.join(tmp, "cg.bed")
+    O.write_bed(bedp, bed)
+    rd = R.RefData(bedp, N, M)
+    rv = R.RefVamp(N, M, M, PROBS, VARS, CG_max_iter=25, seed=4)
+    rng = np.random.default_rng(seed)
+    rhs = rng.normal(size=M)
+    rv.set_state(1e-6, 0.7, 2.0)
+    lm = rv.lmmse_mult(rd, rhs, 2.0)
+    mu = rv.cg(rd, rhs, np.zeros(M), 2.0, 1)
+    mu_warm = rv.cg(rd, rhs, mu * 0.9, 2.0, 1)
+    a2, bern, invq = rv.onsager(rd, 0.7, 2.0)
+    np.savez_compressed(os.path.join(OUT, "cg.npz"), N=N, M=M, seed=seed, rhs=rhs, gam2=0.7, tau=2.0, lmmse=lm, mu=mu,
+                        mu_warm=mu_warm, alpha2=a2, bern=bern, invq=invq, vamp_seed=4, CG_max_iter=25)
+
+
+def case_vamp_linear(tmp):
+    """main_real.exe --run-mode infere --model linear, end to end (scalar build = the semantic spec)."""
+    N, M, seed, h2, CV, iters = 1000, 2000, 3, 0.5, 200, 6
+    bed = O.synth_bed(seed, 0, M, N)
+    bedp = os.path.join(tmp, "v.bed")
+    O.write_bed(bedp, bed)
+    ds0 = O.Dataset(bed, N)
+    beta = O.synth_beta(seed, M, CV, h2)
+    y = ds0.Ax(beta * math.sqrt(N))[:N] + O.synth_noise(seed, N, h2)
+    phenp = os.path.join(tmp, "v.phen")
+    O.write_phen(phenp, y)
+    outd = os.path.join(tmp, "out") + "/"
+    args = ["--run-mode", "infere", "--model", "linear", "--bed-file", bedp, "--phen-files", phenp, "--N", str(N), "--Mt", str(M),
+            "--out-dir", outd, "--out-name", "g", "--iterations", str(iters), "--CG-max-iter", "20", "--rho", "0.5",
+            "--probs", ",".join(map(str, PROBS)), "--vars", ",".join(map(str, VARS)), "--h2", str(h2), "--seed", "1"]
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    log = subprocess.run([R.exe("main_real_scalar.exe")] + args, check=True, capture_output=True, text=True, env=env).stdout
+    out = dict(N=N, M=M, seed=seed, h2=h2, CV=CV, iterations=iters, args=np.array(args[8:]), y=y, beta=beta)
+    for it in range(1, iters + 1):
+        out[f"x1_{it}"] = np.fromfile(f"{outd}g_it_{it}.bin")
+        out[f"r1_{it}"] = np.fromfile(f"{outd}g_r1_it_{it}.bin")
+        out[f"r2_{it}"] = np.fromfile(f"{outd}g_r2_it_{it}.bin")
+        out[f"x2_{it}"] = np.fromfile(f"{outd}g_it_{it}_x2_hat.bin")
+    for nm in ("gam1s", "gam2s", "R2trains"):
+        out[nm] = np.loadtxt(f"{outd}g_{nm}.csv")
+    out["z1_text_last"] = np.loadtxt(f"{outd}g_z1_it_{iters}.csv")
+    gamw = [float(l.split("=")[1]) for l in log.splitlines() if l.startswith("gamw = ")]
+    alpha2 = [float(l.split("=")[1]) for l in log.splitlines() if l.startswith("alpha2 = ")]
+    pv = [np.array(l.split("=")[1].split(), dtype=float) for l in log.splitlines() if l.startswith("prior variances")]
+    pp = [np.array(l.split("=")[1].split(), dtype=float) for l in log.splitlines() if l.startswith("prior probabilities")]
+    out.update(gamw_log=np.array(gamw), alpha2_log=np.array(alpha2), prior_vars_last=pv[-1], prior_probs_last=pp[-1])
+    # MANVECT build of the same run: must agree (N % 4 == 0, no NAs) -- BASELINE.md section 3
+    outd2 = os.path.join(tmp, "out2") + "/"
+    args2 = [a if a != outd else outd2 for a in args]
+    subprocess.run([R.exe("main_real_manvect.exe")] + args2, check=True, capture_output=True, text=True, env=env)
+    out["x1_last_manvect"] = np.fromfile(f"{outd2}g_it_{iters}.bin")
+    np.savez_compressed(os.path.join(OUT, "vamp_linear.npz"), **out)
+    with open(os.path.join(OUT, "vamp_linear.log"), "w") as fh:
+        fh.write("\n".join(l for l in log.splitlines() if not l.startswith("[CG")) + "\n")
+
+
+if __name__ == "__main__":
+    assert R.available(), "build oracle/_ref first: make -C oracle ref"
+    with tempfile.TemporaryDirectory() as tmp:
+        case_matvec(tmp)
+        case_denoiser()
+        case_probit_pieces()
+        case_cg(tmp)
+        case_vamp_linear(tmp)
+    print("golden vectors written to", OUT)

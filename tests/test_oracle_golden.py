@@ -1,0 +1,147 @@
+"""The oracle (oracle/oracle.py + gvamp_oracle.c) against the golden vectors produced by the
+UNMODIFIED reference (tests/golden/make_golden.py).  CPU only; this is what pins the oracle on
+machines where /root/reference does not exist."""
+import hashlib
+import math
+
+import numpy as np
+
+from conftest import golden, relerr
+
+
+def _matvec_dataset(O, g):
+    N, M = int(g["N"]), int(g["M"])
+    bed = O.synth_bed(int(g["seed"]), 0, M, N, miss_rate=float(g["miss_rate"]))
+    assert hashlib.sha256(bed.tobytes()).digest() == g["bed_sha"].tobytes(), "synthetic generator drifted"
+    present = np.ones(N, bool)
+    present[g["na_idx"]] = False
+    mask4 = O.make_mask4(N, present)
+    return bed, mask4, N, M
+
+
+def test_mask_and_phen_scaling(oracle, tmp_path):
+    g = golden("matvec_n1003.npz")
+    N = int(g["N"])
+    p = tmp_path / "a.phen"
+    oracle.write_phen(str(p), g["y"], na_idx=g["na_idx"])
+    phen, mask4, nonas, avg, sqn = oracle.read_phen(str(p), N)
+    assert np.array_equal(mask4, g["mask4"])
+    assert nonas == int(g["nonas"])
+    assert (avg, sqn) == tuple(g["intercept_scale"])
+    ds = oracle.Dataset(oracle.synth_bed(int(g["seed"]), 0, 4, N), N, phen=phen, mask4=mask4, nonas=nonas)
+    assert np.array_equal(ds.filter_pheno(), g["phen"])
+
+
+def test_stats_ax_atx_bit_level(oracle):
+    g = golden("matvec_n1003.npz")
+    bed, mask4, N, M = _matvec_dataset(oracle, g)
+    ds = oracle.Dataset(bed, N, mask4=mask4, nonas=int(g["nonas"]))
+    # same scalar loop order as data.cpp:447-485 / :944-1007 => bit-identical
+    assert np.array_equal(ds.mave, g["mave"])
+    assert np.array_equal(ds.msig, g["msig"])
+    assert np.array_equal(ds.Ax(g["v"]), g["Ax"])
+    assert relerr(ds.ATx(g["u"]), g["ATx"]) < 1e-14  # the reference reduces with OpenMP (order differs)
+    SB, LB = int(g["SB"]), int(g["LB"])
+    assert np.array_equal(ds.Ax(g["v"], SB, LB), g["Ax_sub"])
+    assert relerr(ds.ATx(g["u"][:4 * LB], SB, LB), g["ATx_sub"]) < 1e-14
+    # padded / NA individuals come out exactly zero in Ax (scalar-path semantics)
+    assert np.all(ds.Ax(g["v"])[N:] == 0) and np.all(ds.Ax(g["v"])[g["na_idx"]] == 0)
+
+
+def test_counts_match_stats(oracle):
+    """integer form of the statistics: mu=(2 n00+n10)/(n00+n10+n11), SS from counts."""
+    g = golden("matvec_n1003.npz")
+    bed, mask4, N, M = _matvec_dataset(oracle, g)
+    ds = oracle.Dataset(bed, N, mask4=mask4, nonas=int(g["nonas"]))
+    c = ds.counts().astype(float)
+    n00, n01, n10, n11 = c[:, 0], c[:, 1], c[:, 2], c[:, 3]
+    assert np.all(c[:, 4:].sum(axis=1) == N)
+    mu = (2 * n00 + n10) / (n00 + n10 + n11)
+    ss = n00 * (2 - mu) ** 2 + n10 * (1 - mu) ** 2 + n11 * mu ** 2
+    assert relerr(mu, g["mave"]) < 1e-14
+    assert relerr(1 / np.sqrt(ss / (int(g["nonas"]) - 1)), g["msig"]) < 1e-13
+
+
+def test_shard_and_alpha_scale(oracle):
+    g0, g = golden("matvec_n1003.npz"), golden("matvec_shard.npz")
+    bed, mask4, N, M = _matvec_dataset(oracle, g0)
+    S, Ms = int(g["S"]), int(g["M"])
+    ds = oracle.Dataset(bed[S:S + Ms], N, mask4=mask4, nonas=int(g0["nonas"]), alpha_scale=float(g["alpha_scale"]),
+                        Mt=int(g["Mt"]), S=S)
+    assert relerr(ds.mave, g["mave"]) < 1e-15 and relerr(ds.msig, g["msig"]) < 1e-14
+    assert relerr(ds.Ax(g0["v"][S:S + Ms]), g["Ax"]) < 1e-14
+    assert relerr(ds.ATx(g0["u"]), g["ATx"]) < 1e-14
+
+
+def test_denoiser_and_em(oracle):
+    g = golden("denoiser.npz")
+    r1, probs, vars_ = g["r1"], g["probs"], g["vars"]
+    for tag in "abc":
+        gam1 = float(g["gam1_" + tag])
+        # g1 = r + sigma*pkd/pk cancels catastrophically for tiny gam1 (iteration 1 runs at 1e-6): the error is
+        # measured against the input scale, not the (nearly cancelled) output
+        assert np.linalg.norm(oracle.g1(r1, gam1, probs, vars_) - g["g1_" + tag]) / np.linalg.norm(r1) < 1e-14
+        assert np.max(np.abs(oracle.g1d(r1, gam1, probs, vars_) - g["g1d_" + tag])) < 1e-13
+    M = len(r1)
+    p, v = oracle.update_prior(r1, 3.0, probs, vars_, M, 2, 1e-2)
+    assert relerr(p, g["em_probs"]) < 1e-12 and relerr(v, g["em_vars"]) < 1e-12
+    p, v = oracle.update_prior(r1, 3.0, g["em5_probs_in"], g["em5_vars_in"], M, 5, 1e-4)
+    assert len(p) == len(g["em5_probs"]) < 5, "the 0.1/0.12 pair must merge"
+    assert relerr(p, g["em5_probs"]) < 1e-12 and relerr(v, g["em5_vars"]) < 1e-12
+    p, v = oracle.update_prior(r1, 0.7, g["em5_probs_in"], g["em5_vars_in"], M, 3, 1e-4, learn_vars=0)
+    assert relerr(p, g["em5nl_probs"]) < 1e-12 and relerr(v, g["em5nl_vars"]) < 1e-12
+
+
+def test_cg_and_onsager(oracle):
+    g = golden("cg.npz")
+    N, M = int(g["N"]), int(g["M"])
+    ds = oracle.Dataset(oracle.synth_bed(int(g["seed"]), 0, M, N), N)
+    tau, gam2, K = float(g["tau"]), float(g["gam2"]), int(g["CG_max_iter"])
+    assert relerr(oracle.lmmse_mult(ds, g["rhs"], tau, gam2), g["lmmse"]) < 1e-13
+    mu, _ = oracle.precond_cg(ds, g["rhs"], np.zeros(M), tau, gam2, K, 1)
+    assert relerr(mu, g["mu"]) < 1e-11
+    mu_w, _ = oracle.precond_cg(ds, g["rhs"], g["mu"] * 0.9, tau, gam2, K, 1)
+    assert relerr(mu_w, g["mu_warm"]) < 1e-11
+    bern = oracle.bernoulli_probe(int(g["vamp_seed"]), 0, M, M)
+    assert np.array_equal(bern, g["bern"])
+    invq, _ = oracle.precond_cg(ds, bern, np.zeros(M), tau, gam2, K, 0)
+    assert relerr(invq, g["invq"]) < 1e-11
+    assert abs(gam2 * bern.dot(invq) / float(g["alpha2"]) - 1) < 1e-12
+
+
+def test_probit_pieces(oracle):
+    g = golden("probit_pieces.npz")
+    ref = g["erfcx"]
+    mine = oracle.erfcx(g["x"])
+    fin = np.isfinite(ref)
+    assert np.max(np.abs(mine[fin] / ref[fin] - 1)) < 1e-14
+    assert np.array_equal(np.isinf(mine), np.isinf(ref))
+    assert relerr(oracle.g1_bin_class(g["p"], float(g["tau1"]), g["y"], g["mcov"]), g["g"]) < 1e-14
+    assert relerr(oracle.g1d_bin_class(g["p"], float(g["tau1"]), g["y"], g["mcov"]), g["gd"]) < 1e-13
+
+
+def test_vamp_linear_end_to_end(oracle):
+    """numpy restatement of infere_linear vs main_real.exe's per-iteration output files."""
+    g = golden("vamp_linear.npz")
+    N, M, iters = int(g["N"]), int(g["M"]), int(g["iterations"])
+    bed = oracle.synth_bed(int(g["seed"]), 0, M, N)
+    # main_real.exe read y through the .phen file: scaled by 1/sd, not centred (data.cpp:171-186)
+    y = g["y"]
+    avg = float(np.cumsum(y)[-1]) / N
+    sqn = math.sqrt((N - 1) / float(np.cumsum((y - avg) * (y - avg))[-1]))
+    ds = oracle.Dataset(bed, N, phen=y * sqn)
+    cfg = oracle.VampConfig(iterations=iters, rho=0.5, probs=(0.9, 0.06, 0.04), vars=(0, 1e-4, 1e-3), CG_max_iter=20,
+                            gamw=1.0 / (1.0 - float(g["h2"])), seed=1)
+    tr = oracle.infere_linear(ds, cfg)
+    for it in range(1, iters + 1):
+        for key, arr in (("x1", tr.x1_hat), ("r1", tr.r1), ("r2", tr.r2), ("x2", tr.x2_hat)):
+            ref = g[f"{key}_{it}"]
+            if np.linalg.norm(ref) > 0:
+                assert relerr(arr[it - 1], ref) < 1e-8, (key, it)
+    assert np.allclose(tr.gam1s, g["gam1s"], rtol=1e-5)  # the csv holds 6 significant digits
+    assert np.allclose(tr.gam2s, g["gam2s"], rtol=1e-5)
+    assert np.allclose(tr.R2trains, g["R2trains"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(tr.gamw, g["gamw_log"][1::2], rtol=1e-5)
+    assert np.allclose(tr.vars[-1], g["prior_vars_last"], rtol=1e-5)
+    assert np.allclose(tr.probs[-1], g["prior_probs_last"], rtol=1e-5)
+    assert relerr(g["x1_last_manvect"], g[f"x1_{iters}"]) < 1e-10

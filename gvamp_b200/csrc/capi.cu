@@ -1,0 +1,482 @@
+// capi.cu -- context management, device vectors, the host-pointer Ax/ATx drop-ins, the LMMSE
+// operator and the preconditioned CG driver of the C ABI declared in include/gvamp_b200.h.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "gvb_internal.cuh"
+
+static thread_local char g_err[512] = "";
+
+void gvb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* gvb_last_error(void) { return g_err; }
+extern "C" const char* gvb_version(void) { return "gvamp_b200 0.1 (sm_100a)"; }
+
+extern "C" int gvb_device_count(int* n) {
+    GVB_ARG(n, "n");
+    *n = 0;
+    GVB_CUDA(cudaGetDeviceCount(n));
+    return GVB_OK;
+}
+
+extern "C" int gvb_nccl_unique_id(void* id128) {
+    GVB_ARG(id128, "id128");
+    static_assert(sizeof(ncclUniqueId) == GVB_NCCL_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    GVB_NCCL(ncclGetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return GVB_OK;
+}
+
+extern "C" void gvb_divide_work(long Mt, int nranks, int rank, long* M, long* S) {
+    // utilities.cpp:266-281
+    long modu = Mt % nranks, size = Mt / nranks;
+    long start = 0;
+    for (int i = 0; i < rank; i++) start += (i < modu) ? size + 1 : size;
+    if (M) *M = (rank < modu) ? size + 1 : size;
+    if (S) *S = start;
+}
+
+extern "C" int gvb_ctx_create(gvb_ctx** out, int device, int rank, int nranks, const void* id128) {
+    GVB_ARG(out, "out");
+    GVB_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "rank / nranks");
+    GVB_ARG(nranks == 1 || id128, "a NCCL unique id is required when nranks > 1");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        gvb_set_error("no CUDA device available (%s): libgvamp_b200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return GVB_ERR_CUDA;
+    }
+    GVB_ARG(device >= 0 && device < ndev, "device ordinal");
+    GVB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GVB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        gvb_set_error("device %d (%s, sm_%d%d) is not a Blackwell part: this library ships sm_100a code only", device, prop.name, prop.major, prop.minor);
+        return GVB_ERR_CUDA;
+    }
+    gvb_ctx* c = new gvb_ctx();
+    c->device = device;
+    c->rank = rank;
+    c->nranks = nranks;
+    c->sm_count = prop.multiProcessorCount;
+    GVB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) {
+        GVB_CUDA(cudaEventCreate(&c->ev_start[i]));
+        GVB_CUDA(cudaEventCreate(&c->ev_stop[i]));
+    }
+    GVB_CUDA(cudaMalloc(&c->red_partial, sizeof(double) * GVB_RED_BLOCKS * GVB_RED_MAXK));
+    GVB_CUDA(cudaMalloc(&c->red_result, sizeof(double) * GVB_RED_MAXK));
+    GVB_CUDA(cudaMallocHost(&c->h_red, sizeof(double) * GVB_RED_MAXK));
+    GVB_CUDA(cudaMalloc(&c->scal, sizeof(double) * 64));
+    GVB_CUDA(cudaMalloc(&c->work_counter, sizeof(int) * 16));
+    GVB_CUDA(cudaMemset(c->work_counter, 0, sizeof(int) * 16));
+    const char* gen = getenv("GVB_KERNELS");
+    c->kernel_gen = (gen && !strcmp(gen, "simple")) ? 0 : 1;
+    if (nranks > 1) {
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof(id));
+        GVB_NCCL(ncclCommInitRank(&c->comm, nranks, id, rank));
+    }
+    *out = c;
+    return GVB_OK;
+}
+
+extern "C" void gvb_ctx_destroy(gvb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (gvb_vec_s* v : c->vecs) {
+        if (v) { cudaFree(v->d); delete v; }
+    }
+    auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
+    fr(c->bed); fr(c->maskw); fr(c->validw); fr(c->mave); fr(c->msig); fr(c->counts);
+    fr(c->tmpN); fr(c->tmpN2); fr(c->tmpM); fr(c->tmpM2); fr(c->wv); fr(c->cv); fr(c->ax_partial);
+    fr(c->tab_u); fr(c->tab_v); fr(c->acc_i64); fr(c->red_partial); fr(c->red_result); fr(c->scal); fr(c->work_counter);
+    if (c->h_red) cudaFreeHost(c->h_red);
+    for (int i = 0; i < 8; i++) { cudaEventDestroy(c->ev_start[i]); cudaEventDestroy(c->ev_stop[i]); }
+    if (c->comm) ncclCommDestroy(c->comm);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int gvb_ctx_sync(gvb_ctx* c) {
+    GVB_ARG(c, "ctx");
+    GVB_CUDA(cudaStreamSynchronize(c->stream));
+    return GVB_OK;
+}
+extern "C" void* gvb_ctx_stream(gvb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" int gvb_ctx_info(gvb_ctx* c, long* N, long* Mt, long* S, long* M, long* mbytes) {
+    GVB_ARG(c, "ctx");
+    if (N) *N = c->N;
+    if (Mt) *Mt = c->Mt;
+    if (S) *S = c->S;
+    if (M) *M = c->M;
+    if (mbytes) *mbytes = c->mbytes;
+    return GVB_OK;
+}
+extern "C" int gvb_timer_start(gvb_ctx* c, int slot) {
+    GVB_ARG(c && slot >= 0 && slot < 8, "slot");
+    GVB_CUDA(cudaEventRecord(c->ev_start[slot], c->stream));
+    return GVB_OK;
+}
+extern "C" int gvb_timer_stop(gvb_ctx* c, int slot) {
+    GVB_ARG(c && slot >= 0 && slot < 8, "slot");
+    GVB_CUDA(cudaEventRecord(c->ev_stop[slot], c->stream));
+    return GVB_OK;
+}
+extern "C" int gvb_timer_elapsed_ms(gvb_ctx* c, int slot, float* ms) {
+    GVB_ARG(c && slot >= 0 && slot < 8 && ms, "slot");
+    GVB_CUDA(cudaEventSynchronize(c->ev_stop[slot]));
+    GVB_CUDA(cudaEventElapsedTime(ms, c->ev_start[slot], c->ev_stop[slot]));
+    return GVB_OK;
+}
+extern "C" long gvb_launch_count(gvb_ctx* c) { return c ? c->launches : 0; }
+extern "C" long gvb_sweep_count(gvb_ctx* c) { return c ? c->sweeps : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// device vectors
+// ------------------------------------------------------------------------------------------------
+static int vec_alloc_cap(gvb_ctx* c, long n, long cap, gvb_vec* out) {
+    GVB_ARG(c && out && n > 0 && cap >= n, "vector length");
+    GVB_CUDA(cudaSetDevice(c->device));
+    gvb_vec_s* v = new gvb_vec_s();
+    v->n = n;
+    v->cap = cap;
+    cudaError_t e = cudaMalloc(&v->d, cap * sizeof(double));
+    if (e != cudaSuccess) {
+        delete v;
+        gvb_set_error("cudaMalloc of a %ld-double vector failed: %s", cap, cudaGetErrorString(e));
+        return GVB_ERR_NOMEM;
+    }
+    GVB_CUDA(cudaMemsetAsync(v->d, 0, cap * sizeof(double), c->stream));
+    c->vecs.push_back(v);
+    *out = v;
+    return GVB_OK;
+}
+extern "C" int gvb_vec_alloc(gvb_ctx* c, long n, gvb_vec* out) { return vec_alloc_cap(c, n, n, out); }
+// M- and N-vectors carry zero padding up to the layout's tile sizes so the sweep kernels never branch on the tail
+extern "C" int gvb_vec_alloc_M(gvb_ctx* c, gvb_vec* out) {
+    GVB_ARG(c && c->bed, "matrix not loaded");
+    return vec_alloc_cap(c, c->M, c->Mg_pad * 4, out);
+}
+extern "C" int gvb_vec_alloc_N(gvb_ctx* c, gvb_vec* out) {
+    GVB_ARG(c && c->bed, "matrix not loaded");
+    return vec_alloc_cap(c, 4 * c->mbytes, c->Npad, out);
+}
+extern "C" void gvb_vec_free(gvb_ctx* c, gvb_vec v) {
+    if (!c || !v) return;
+    auto it = std::find(c->vecs.begin(), c->vecs.end(), v);
+    if (it != c->vecs.end()) c->vecs.erase(it);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(v->d);
+    delete v;
+}
+extern "C" long gvb_vec_len(gvb_vec v) { return v ? v->n : 0; }
+extern "C" void* gvb_vec_ptr(gvb_vec v) { return v ? (void*)v->d : nullptr; }
+extern "C" int gvb_vec_upload(gvb_ctx* c, gvb_vec dst, const double* src, long n) {
+    GVB_ARG(c && dst && src && n >= 0 && n <= dst->n, "upload length");
+    GVB_CUDA(cudaMemcpyAsync(dst->d, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GVB_CUDA(cudaStreamSynchronize(c->stream));   // src may be pageable / reused by the caller
+    return GVB_OK;
+}
+extern "C" int gvb_vec_download(gvb_ctx* c, gvb_vec src, double* dst, long n) {
+    GVB_ARG(c && dst && src && n >= 0 && n <= src->n, "download length");
+    GVB_CUDA(cudaMemcpyAsync(dst, src->d, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GVB_CUDA(cudaStreamSynchronize(c->stream));
+    return GVB_OK;
+}
+extern "C" int gvb_vec_copy(gvb_ctx* c, gvb_vec dst, gvb_vec src) {
+    GVB_ARG(c && dst && src && dst->n == src->n, "vector lengths");
+    GVB_CUDA(cudaMemcpyAsync(dst->d, src->d, src->n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return GVB_OK;
+}
+__global__ void fill_kernel(double* d, double v, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) d[i] = v;
+}
+extern "C" int gvb_vec_fill(gvb_ctx* c, gvb_vec dst, double value) {
+    GVB_ARG(c && dst, "vector");
+    if (value == 0.0) {
+        GVB_CUDA(cudaMemsetAsync(dst->d, 0, dst->n * sizeof(double), c->stream));
+        return GVB_OK;
+    }
+    fill_kernel<<<(unsigned)std::min((dst->n + 255) / 256, 1184l), 256, 0, c->stream>>>(dst->d, value, dst->n);
+    GVB_LAUNCHED(c);
+    return GVB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mat-vec dispatch (kernel generation) + NCCL allreduce of the partial N-vector
+// ------------------------------------------------------------------------------------------------
+int gvb_ax_dev(gvb_ctx* c, const double* v, double* out, bool allreduce) {
+    GVB_ARG(c->have_stats, "compute_stats must run before Ax");
+    GVB_CHECK(c->kernel_gen == 0 ? gvb_ax_simple(c, v, out) : gvb_ax_lut(c, v, out));
+    c->sweeps++;
+    if (allreduce && c->nranks > 1) {
+        // replaces MPI_Allreduce(Ax_temp, Ax_total, 4*LB, MPI_DOUBLE, MPI_SUM) -- data.cpp:995
+        GVB_NCCL(ncclAllReduce(out, out, (size_t)(4 * c->mbytes), ncclDouble, ncclSum, c->comm, c->stream));
+    }
+    return GVB_OK;
+}
+int gvb_atx_dev(gvb_ctx* c, const double* u, double* out) {
+    GVB_ARG(c->have_stats, "compute_stats must run before ATx");
+    GVB_CHECK(c->kernel_gen == 0 ? gvb_atx_simple(c, u, out) : gvb_atx_lut(c, u, out));
+    c->sweeps++;
+    return GVB_OK;
+}
+
+extern "C" int gvb_dAx(gvb_ctx* c, gvb_vec v, gvb_vec out) {
+    GVB_ARG(c && v && out && v->cap >= c->Mg_pad * 4 && out->cap >= c->Npad, "Ax needs an M-vector and an N-vector from gvb_vec_alloc_M/_N");
+    return gvb_ax_dev(c, v->d, out->d, true);
+}
+extern "C" int gvb_dATx(gvb_ctx* c, gvb_vec u, gvb_vec out) {
+    GVB_ARG(c && u && out && u->cap >= c->Npad && out->cap >= c->Mg_pad * 4, "ATx needs an N-vector and an M-vector from gvb_vec_alloc_N/_M");
+    return gvb_atx_dev(c, u->d, out->d);
+}
+
+__global__ void scale_slice_kernel(const double* __restrict__ in, long off, long n, double f, double* __restrict__ out) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) out[i] = in[off + i] * f;
+}
+__global__ void scale_inplace_kernel(double* __restrict__ x, long n, double f) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) x[i] *= f;
+}
+
+// data::Ax(double*, SB, LB): host in, host out.  A byte sub-range is the full product restricted to
+// the individuals [4SB, 4SB+4LB) and rescaled by sqrt(N)/sqrt(4LB) (data.cpp:998-1005).
+extern "C" int gvb_Ax(gvb_ctx* c, const double* v, double* out, long SB, long LB) {
+    GVB_ARG(c && c->bed && v && out, "ctx / matrix / pointers");
+    GVB_ARG(SB >= 0 && LB > 0 && SB + LB <= c->mbytes, "byte range");
+    GVB_CUDA(cudaMemcpyAsync(c->tmpM, v, c->M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GVB_CHECK(gvb_ax_dev(c, c->tmpM, c->tmpN, true));
+    bool full = (SB == 0 && LB == c->mbytes);
+    if (full) {
+        GVB_CUDA(cudaMemcpyAsync(out, c->tmpN, 4 * LB * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        double f = sqrt((double)c->N) / sqrt((double)(4 * LB));
+        scale_slice_kernel<<<(unsigned)std::min((4 * LB + 255) / 256, 1184l), 256, 0, c->stream>>>(c->tmpN, 4 * SB, 4 * LB, f, c->tmpN2);
+        GVB_LAUNCHED(c);
+        GVB_CUDA(cudaMemcpyAsync(out, c->tmpN2, 4 * LB * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    GVB_CUDA(cudaStreamSynchronize(c->stream));
+    return GVB_OK;
+}
+
+// data::ATx(double*, SB, LB): u indexes individuals relative to 4*SB; everything outside the range
+// (and any entry that would address an individual >= N) is treated as zero.
+extern "C" int gvb_ATx(gvb_ctx* c, const double* u, double* out, long SB, long LB) {
+    GVB_ARG(c && c->bed && u && out, "ctx / matrix / pointers");
+    GVB_ARG(SB >= 0 && LB > 0 && SB + LB <= c->mbytes, "byte range");
+    bool full = (SB == 0 && LB == c->mbytes);
+    long n_in = std::min(4 * LB, c->N - 4 * SB);
+    GVB_CUDA(cudaMemsetAsync(c->tmpN, 0, c->Npad * sizeof(double), c->stream));
+    if (n_in > 0) GVB_CUDA(cudaMemcpyAsync(c->tmpN + 4 * SB, u, n_in * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GVB_CHECK(gvb_atx_dev(c, c->tmpN, c->tmpM));
+    if (!full) {
+        double f = sqrt((double)c->N) / sqrt((double)(4 * LB));
+        scale_inplace_kernel<<<(unsigned)std::min((c->M + 255) / 256, 1184l), 256, 0, c->stream>>>(c->tmpM, c->M, f);
+        GVB_LAUNCHED(c);
+    }
+    GVB_CUDA(cudaMemcpyAsync(out, c->tmpM, c->M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GVB_CUDA(cudaStreamSynchronize(c->stream));
+    return GVB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LMMSE operator and preconditioned CG (vamp.cpp:1074-1229)
+// ------------------------------------------------------------------------------------------------
+__global__ void lmmse_combine_kernel(double* __restrict__ out, double tau, double gam2, const double* __restrict__ v, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        double r = out[i] * tau;     // vamp.cpp:1113-1114: res *= tau; res += gam2*v
+        out[i] = r + gam2 * v[i];
+    }
+}
+
+static int lmmse_mult_dev(gvb_ctx* c, const gvb_vec_s* v, double tau, double gam2, gvb_vec_s* out, bool known_nonzero) {
+    if (!known_nonzero) {
+        // vamp.cpp:1079-1080: an all-zero input returns zeros without touching the matrix
+        gvb_vec xs[1] = {const_cast<gvb_vec_s*>(v)};
+        double nn = 0.0;
+        GVB_CHECK(gvb_vec_dots(c, 1, xs, nullptr, 1, &nn));
+        if (nn == 0.0) return gvb_vec_fill(c, out, 0.0);
+    }
+    GVB_CHECK(gvb_ax_dev(c, v->d, c->tmpN2, true));
+    GVB_CHECK(gvb_atx_dev(c, c->tmpN2, out->d));
+    lmmse_combine_kernel<<<(unsigned)std::min((v->n + 255) / 256, 1184l), 256, 0, c->stream>>>(out->d, tau, gam2, v->d, v->n);
+    GVB_LAUNCHED(c);
+    return GVB_OK;
+}
+
+extern "C" int gvb_lmmse_mult(gvb_ctx* c, gvb_vec v, double tau, double gam2, gvb_vec out) {
+    GVB_ARG(c && v && out && v != out && v->cap >= c->Mg_pad * 4 && out->cap >= c->Mg_pad * 4, "M-vectors from gvb_vec_alloc_M");
+    return lmmse_mult_dev(c, v, tau, gam2, out, false);
+}
+
+// fused CG updates ---------------------------------------------------------------------------------
+// mu += alpha*p ; partial: <rhs,mu>, ||mu||^2
+__global__ void __launch_bounds__(256) cg_update_mu_kernel(double* __restrict__ mu, const double* __restrict__ p, const double* __restrict__ rhs,
+                                                           double alpha, long n, double* __restrict__ partial) {
+    double a0 = 0.0, a1 = 0.0;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        double m = mu[i] + alpha * p[i];
+        mu[i] = m;
+        a0 += rhs[i] * m;
+        a1 += m * m;
+    }
+    __shared__ double sm[8][2];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (lane == 0) { sm[warp][0] = a0; sm[warp][1] = a1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double s = 0.0;
+        for (int w = 0; w < 8; w++) s += sm[w][threadIdx.x];
+        partial[blockIdx.x * 2 + threadIdx.x] = s;
+    }
+}
+// r -= alpha*d ; partial: <r, r/diag>, ||r||^2
+__global__ void __launch_bounds__(256) cg_update_r_kernel(double* __restrict__ r, const double* __restrict__ d, double alpha, double diag, long n,
+                                                          double* __restrict__ partial) {
+    double a0 = 0.0, a1 = 0.0;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        double x = r[i] - d[i] * alpha;
+        r[i] = x;
+        a0 += x * (x / diag);
+        a1 += x * x;
+    }
+    __shared__ double sm[8][2];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (lane == 0) { sm[warp][0] = a0; sm[warp][1] = a1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double s = 0.0;
+        for (int w = 0; w < 8; w++) s += sm[w][threadIdx.x];
+        partial[blockIdx.x * 2 + threadIdx.x] = s;
+    }
+}
+// p = r/diag + beta*p
+__global__ void cg_update_p_kernel(double* __restrict__ p, const double* __restrict__ r, double beta, double diag, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = r[i] / diag + beta * p[i];
+}
+// r = rhs - q ; p = r/diag ; partial: <r, r/diag>, ||rhs||^2
+__global__ void __launch_bounds__(256) cg_init_kernel(double* __restrict__ r, double* __restrict__ p, const double* __restrict__ rhs,
+                                                      const double* __restrict__ q, double diag, long n, double* __restrict__ partial) {
+    double a0 = 0.0, a1 = 0.0;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        double b = rhs[i];
+        double x = b - q[i];
+        r[i] = x;
+        double z = x / diag;
+        p[i] = z;
+        a0 += x * z;
+        a1 += b * b;
+    }
+    __shared__ double sm[8][2];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (lane == 0) { sm[warp][0] = a0; sm[warp][1] = a1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double s = 0.0;
+        for (int w = 0; w < 8; w++) s += sm[w][threadIdx.x];
+        partial[blockIdx.x * 2 + threadIdx.x] = s;
+    }
+}
+
+static inline int cg_blocks(long n) { return (int)std::max(1l, std::min((n + 1023) / 1024, (long)GVB_RED_BLOCKS)); }
+
+// vamp::precondCG_solver, vamp.cpp:1130-1229.  z = r/diag is never materialised (diag is a constant,
+// :1137-1138); every scalar and every exit test is FP64 with the reference's formulas.
+extern "C" int gvb_cg_solve(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4) {
+    GVB_ARG(c && rhs && mu && rhs != mu, "vectors");
+    GVB_ARG(rhs->cap >= c->Mg_pad * 4 && mu->cap >= c->Mg_pad * 4, "M-vectors from gvb_vec_alloc_M");
+    long n = c->M;
+    gvb_vec r = nullptr, p = nullptr, d = nullptr;
+    GVB_CHECK(gvb_vec_alloc_M(c, &r));
+    GVB_CHECK(gvb_vec_alloc_M(c, &p));
+    GVB_CHECK(gvb_vec_alloc_M(c, &d));
+    int rc = GVB_OK;
+    int it_done = 0;
+    auto cleanup = [&]() { gvb_vec_free(c, r); gvb_vec_free(c, p); gvb_vec_free(c, d); };
+#define CGCHK(x) do { rc = (x); if (rc != GVB_OK) { cleanup(); return rc; } } while (0)
+    const double diag = tau * (double)(c->N - 1) / (double)c->N + gam2;
+    const int nb = cg_blocks(n);
+    double s2[2];
+    // r = rhs - lmmse_mult(mu_start) ; z = r/diag ; p = z
+    CGCHK(lmmse_mult_dev(c, mu, tau, gam2, d, false));
+    cg_init_kernel<<<nb, 256, 0, c->stream>>>(r->d, p->d, rhs->d, d->d, diag, n, c->red_partial);
+    c->launches++;
+    CGCHK(gvb_reduce_finish(c, nb, 2, true, s2));
+    double rz = s2[0];
+    const double norm_v = sqrt(s2[1]);
+    double rr = 0.0;
+    double prev_onsager = 0.0;
+    for (int i = 0; i < max_iter; i++) {
+        it_done = i + 1;
+        // d = A p  (p == 0 only when r == 0: the reference then returns zeros and alpha = 0/0)
+        CGCHK(lmmse_mult_dev(c, p, tau, gam2, d, rz != 0.0));
+        gvb_vec xs[1] = {d};
+        gvb_vec ys[1] = {p};
+        double dp = 0.0;
+        CGCHK(gvb_vec_dots(c, 1, xs, ys, 1, &dp));
+        double alpha = rz / dp;
+        cg_update_mu_kernel<<<nb, 256, 0, c->stream>>>(mu->d, p->d, rhs->d, alpha, n, c->red_partial);
+        c->launches++;
+        CGCHK(gvb_reduce_finish(c, nb, 2, true, s2));
+        double norm_mu = sqrt(s2[1]);
+        double ons_rel = -1.0;
+        if (denoiser == 0) {   // vamp.cpp:1174-1193
+            double onsager = gam2 * s2[0];
+            ons_rel = (onsager != 0.0) ? fabs((onsager - prev_onsager) / onsager) : 1.0;
+            if (ons_rel < 1e-8) {
+                if (log4) { log4[4 * i + 0] = -1.0; log4[4 * i + 1] = norm_mu; log4[4 * i + 2] = -1.0; log4[4 * i + 3] = ons_rel; }
+                break;
+            }
+            prev_onsager = onsager;
+        }
+        double beta = 1.0 / rz;   // vamp.cpp:1198
+        cg_update_r_kernel<<<nb, 256, 0, c->stream>>>(r->d, d->d, alpha, diag, n, c->red_partial);
+        c->launches++;
+        CGCHK(gvb_reduce_finish(c, nb, 2, true, s2));
+        rz = s2[0];
+        rr = s2[1];
+        beta *= rz;               // vamp.cpp:1207
+        cg_update_p_kernel<<<(unsigned)std::min((n + 255) / 256, 1184l), 256, 0, c->stream>>>(p->d, r->d, beta, diag, n);
+        c->launches++;
+        double rel_err = sqrt(rr) / norm_v;            // vamp.cpp:1215
+        double norm_z = sqrt(rr) / diag;               // ||z|| with z = r/diag
+        if (log4) { log4[4 * i + 0] = rel_err; log4[4 * i + 1] = norm_mu; log4[4 * i + 2] = norm_z / norm_v; log4[4 * i + 3] = ons_rel; }
+        if (rel_err < 1e-5) break;                     // vamp.cpp:1217-1223
+    }
+#undef CGCHK
+    cudaError_t e = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess) {
+        gvb_set_error("CUDA error in CG: %s", cudaGetErrorString(e));
+        return GVB_ERR_CUDA;
+    }
+    if (iters) *iters = it_done;
+    return GVB_OK;
+}

@@ -1,0 +1,158 @@
+// gvb_internal.cuh -- shared declarations of libgvamp_b200 (not part of the public C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gvamp_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// HBM layout of the packed genotype matrix ("striped, 4-marker interleaved SNP-major")
+//
+//   position p   = byte index inside a marker column (4 individuals), p in [0, mbytes)
+//   stripe  t    = p / 32            (128 individuals, one 128-byte line per marker group)
+//   group   g    = local marker / 4  (4 consecutive markers)
+//   word(t,g,l)  = bed32[(t * Mg_pad + g) * 32 + l],  byte q of the word = PLINK byte of marker
+//                  4g+q at position 32t+l.
+//
+// A stripe is one contiguous run of Mg_pad*128 bytes, so X^T.u (marker-stationary) and X.v
+// (individual-stationary) both stream long contiguous runs, every PLINK byte is stored exactly once
+// and unchanged, and a 32-bit word holds a 4x4 (marker x individual) block: byte q indexes a
+// per-position table for X^T.u, and the four codes of one individual are gathered with one
+// multiply for X.v (see matvec_lut.cu).  Padding bytes are 0x55 (four "missing" codes): they
+// contribute nothing to any product or count.
+// ------------------------------------------------------------------------------------------------
+#define GVB_STRIPE_POS 32         // byte positions per stripe
+#define GVB_STRIPE_IND 128        // individuals per stripe
+#define GVB_GROUP 4               // markers per interleaved word
+#define GVB_GROUP_TILE 32         // marker groups per table tile (Mg_pad is a multiple of this)
+#define GVB_PAD_BYTE 0x55u
+
+struct gvb_vec_s {
+    double* d;
+    long n;      // logical length
+    long cap;    // allocated doubles
+};
+
+struct gvb_ctx {
+    int device = 0, rank = 0, nranks = 1;
+    cudaStream_t stream = nullptr;
+    ncclComm_t comm = nullptr;
+    int sm_count = 148;
+
+    // problem dimensions
+    long N = 0, Mt = 0, S = 0, M = 0, mbytes = 0;
+    long n_stripes = 0, Npad = 0;   // Npad = n_stripes * 128
+    long Mg = 0, Mg_pad = 0;        // marker groups, padded to GVB_GROUP_TILE
+    size_t bed_words = 0;
+    uint32_t* bed = nullptr;        // the HBM-resident matrix
+
+    // phenotype mask / valid-individual mask, one 32-bit word per position: bits 0,2,4,6 of every
+    // byte are set when individual k of that position is present (resp. < N)
+    uint32_t* maskw = nullptr;
+    uint32_t* validw = nullptr;
+    int nonas = 0;
+    bool have_mask = false, have_stats = false;
+
+    // marker statistics
+    double* mave = nullptr;   // Mg_pad*4 (padded markers: 0)
+    double* msig = nullptr;   // padded markers: 0 (so they contribute nothing)
+    int64_t* counts = nullptr;
+    long total_missing = 0;   // sum over local markers of missing genotypes (i < N)
+    double alpha_scale = 1.0;
+
+    // scratch
+    double* red_partial = nullptr;  // [RED_BLOCKS][RED_MAXK]
+    double* red_result = nullptr;   // [RED_MAXK] device
+    double* h_red = nullptr;        // pinned host mirror
+    double* ax_partial = nullptr;   // Ax v0 partial sums
+    size_t ax_partial_cap = 0;
+    double* tmpN = nullptr;         // Npad
+    double* tmpN2 = nullptr;
+    double* tmpM = nullptr;         // Mg_pad*4
+    double* tmpM2 = nullptr;
+    double* wv = nullptr;           // sigma_j * v_j            (Mg_pad*4)
+    double* cv = nullptr;           // mu_j * sigma_j * v_j
+    // LUT-kernel scratch (matvec_lut.cu)
+    int32_t* tab_u = nullptr;       // per-position tables for X^T.u
+    size_t tab_u_cap = 0;
+    int32_t* tab_v = nullptr;       // per-marker-group tables for X.v
+    size_t tab_v_cap = 0;
+    unsigned long long* acc_i64 = nullptr;  // fixed-point accumulators
+    size_t acc_i64_cap = 0;
+    int* work_counter = nullptr;
+    double* scal = nullptr;         // small device scalars
+    int kernel_gen = 1;             // 0: simple FP64 kernels, 1: table kernels (env GVB_KERNELS)
+
+    // timers and counters
+    cudaEvent_t ev_start[8], ev_stop[8];
+    long launches = 0, sweeps = 0;
+    std::vector<gvb_vec_s*> vecs;
+};
+
+#define GVB_RED_BLOCKS 296
+#define GVB_RED_MAXK 80
+
+void gvb_set_error(const char* fmt, ...);
+
+#define GVB_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            gvb_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+            return GVB_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define GVB_NCCL(call)                                                                         \
+    do {                                                                                       \
+        ncclResult_t r_ = (call);                                                              \
+        if (r_ != ncclSuccess) {                                                               \
+            gvb_set_error("NCCL error %s at %s:%d (%s)", ncclGetErrorString(r_), __FILE__, __LINE__, #call); \
+            return GVB_ERR_NCCL;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define GVB_CHECK(call)                 \
+    do {                                \
+        int rc_ = (call);               \
+        if (rc_ != GVB_OK) return rc_;  \
+    } while (0)
+
+#define GVB_ARG(cond, msg)                                     \
+    do {                                                       \
+        if (!(cond)) {                                         \
+            gvb_set_error("invalid argument: %s (%s:%d)", msg, __FILE__, __LINE__); \
+            return GVB_ERR_ARG;                                \
+        }                                                      \
+    } while (0)
+
+// count + launch-error check after every kernel launch
+#define GVB_LAUNCHED(ctx)                     \
+    do {                                      \
+        (ctx)->launches++;                    \
+        GVB_CUDA(cudaGetLastError());         \
+    } while (0)
+
+static inline long gvb_roundup(long x, long m) { return (x + m - 1) / m * m; }
+
+// ---- internal entry points (implemented across the .cu files) ----
+int gvb_layout_alloc(gvb_ctx* c, long N, long Mt, long S, long M);
+int gvb_layout_retile(gvb_ctx* c, const uint8_t* d_snp_major, long j0, long nmark);   // device SNP-major chunk -> layout
+int gvb_stats_run(gvb_ctx* c);
+
+// full-range device matvecs; u/out N-vectors have Npad entries, v/out M-vectors have Mg_pad*4
+int gvb_ax_simple(gvb_ctx* c, const double* v, double* out);
+int gvb_atx_simple(gvb_ctx* c, const double* u, double* out);
+int gvb_ax_lut(gvb_ctx* c, const double* v, double* out);
+int gvb_atx_lut(gvb_ctx* c, const double* u, double* out);
+int gvb_ax_dev(gvb_ctx* c, const double* v, double* out, bool allreduce);
+int gvb_atx_dev(gvb_ctx* c, const double* u, double* out);
+
+// reductions: res (host) <- sum over blocks (and ranks if sync) of the K per-block partials written
+// by the caller's kernel into c->red_partial[b*K + k], b < nblocks
+int gvb_reduce_finish(gvb_ctx* c, int nblocks, int K, bool sync, double* res_host);

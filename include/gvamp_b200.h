@@ -1,0 +1,156 @@
+/* gvamp_b200.h -- C ABI of the B200-native gVAMP hot path (libgvamp_b200.so).
+ *
+ * One context (gvb_ctx) = one B200 = one contiguous marker shard [S, S+M) of an N x Mt genotype
+ * matrix, i.e. exactly what one MPI rank owns in the reference (utilities.cpp:259-291).  All
+ * entry points take plain pointers and sizes, return 0 on success and a non-zero code on error
+ * (text via gvb_last_error()); no C++ exception crosses this boundary.  There is no CPU fallback:
+ * every call fails with GVB_ERR_CUDA when no sm_100 device is usable.
+ *
+ * The reference has no FFI layer; the functions below replace the C++ member functions of
+ * `class data` / `class vamp` that make up the hot path.  Each declaration cites the reference
+ * interface it stands in for (file:line relative to the gVAMP source tree).
+ *
+ * Vector conventions: "host" pointers are ordinary host memory (pinned or not); `gvb_vec` handles
+ * are device-resident FP64 vectors owned by the context.  M-vectors are sharded like the markers,
+ * N-vectors (length 4*ceil(N/4), padded entries are zero) are replicated on every rank.
+ */
+#ifndef GVAMP_B200_H
+#define GVAMP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gvb_ctx gvb_ctx;
+typedef struct gvb_vec_s* gvb_vec; /* device vector handle */
+
+enum {
+    GVB_OK = 0,
+    GVB_ERR_CUDA = 1,     /* CUDA runtime / driver / no device */
+    GVB_ERR_NCCL = 2,
+    GVB_ERR_ARG = 3,      /* bad argument or call order */
+    GVB_ERR_IO = 4,       /* file could not be read */
+    GVB_ERR_NOMEM = 5
+};
+
+#define GVB_NCCL_ID_BYTES 128
+#define GVB_MAX_MIX 32 /* max mixture components L (the reference's default prior has 23) */
+
+/* ---- library / context -------------------------------------------------------------------- */
+const char* gvb_last_error(void);
+const char* gvb_version(void);
+int gvb_device_count(int* n);
+
+/* rank 0 calls this and ships the 128 bytes to the other ranks (torch.distributed broadcast, a
+ * file, ...); replaces MPI_Init's implicit communicator (main_real.cpp:17-27). */
+int gvb_nccl_unique_id(void* id128);
+
+/* device: CUDA ordinal; rank/nranks: position of this shard; id128 may be NULL when nranks==1. */
+int gvb_ctx_create(gvb_ctx** out, int device, int rank, int nranks, const void* id128);
+void gvb_ctx_destroy(gvb_ctx* ctx);
+int gvb_ctx_sync(gvb_ctx* ctx);                    /* cudaStreamSynchronize on the context's stream */
+void* gvb_ctx_stream(gvb_ctx* ctx);                /* the cudaStream_t every kernel is launched on */
+int gvb_ctx_info(gvb_ctx* ctx, long* N, long* Mt, long* S, long* M, long* mbytes);
+
+/* CUDA-event timers on the context's stream (bench.py times with these; torch.cuda.Event only
+ * sees torch's own stream). */
+int gvb_timer_start(gvb_ctx* ctx, int slot);
+int gvb_timer_stop(gvb_ctx* ctx, int slot);
+int gvb_timer_elapsed_ms(gvb_ctx* ctx, int slot, float* ms); /* synchronises on the stop event */
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+long gvb_launch_count(gvb_ctx* ctx);
+/* bed sweeps (Ax + ATx passes over the packed matrix) since creation */
+long gvb_sweep_count(gvb_ctx* ctx);
+
+/* ---- partition ------------------------------------------------------------------------------ */
+/* divide_work, utilities.cpp:259-291: first Mt%nranks ranks own Mt/nranks+1 contiguous markers */
+void gvb_divide_work(long Mt, int nranks, int rank, long* M, long* S);
+
+/* ---- genotype matrix ------------------------------------------------------------------------- */
+/* data::read_genotype_data, data.cpp:201-234: reads the shard's bytes at file offset 3+S*mbytes
+ * (magic bytes skipped, never validated -- same as the reference) and re-tiles them into the
+ * HBM-resident layout. */
+int gvb_bed_load_file(gvb_ctx* ctx, const char* bed_path, long N, long Mt, long S, long M);
+/* same, from a host buffer of M*ceil(N/4) SNP-major PLINK bytes (data::get_bed_data, data.hpp:66) */
+int gvb_bed_load_host(gvb_ctx* ctx, const uint8_t* bed, long N, long Mt, long S, long M);
+/* synthetic Binomial(2,p_j) genotypes generated directly in HBM (bench workloads up to 840 GB that
+ * never touch disk); byte-identical to oracle/gvamp_oracle.c:orc_synth_bed. */
+int gvb_bed_synth(gvb_ctx* ctx, uint64_t seed, long N, long Mt, long S, long M, double miss_rate);
+/* PLINK bytes of local markers [j0, j0+n) back to the host: the bit-exactness check of the layout */
+int gvb_bed_decode(gvb_ctx* ctx, long j0, long n, uint8_t* out);
+
+/* phenotype-present mask: data::mask4 / nonas, data.cpp:136-169 and :86-100.  mask4==NULL means
+ * "all N individuals present" (the y-vector constructor). */
+int gvb_set_mask(gvb_ctx* ctx, const uint8_t* mask4, int nonas);
+
+/* data::compute_markers_statistics, data.cpp:392-485 (scalar-branch semantics: mean 0 for an empty
+ * column, inverse sd 1 for a constant one, alpha_scale exponent). */
+int gvb_compute_stats(gvb_ctx* ctx, double alpha_scale);
+int gvb_get_stats(gvb_ctx* ctx, double* mave, double* msig);   /* data::get_mave / get_msig */
+/* counts[j*8+c]: individuals with code c and phenotype present; counts[j*8+4+c]: all i<N */
+int gvb_get_counts(gvb_ctx* ctx, int64_t* counts);
+
+/* ---- X.v and X^T.u, host-pointer drop-in --------------------------------------------------------- */
+/* data::Ax(double* v, SB, LB), data.cpp:848-1011 incl. the MPI_Allreduce at :995.
+ * v: M local entries; out: 4*LB entries.  COLLECTIVE when nranks>1. */
+int gvb_Ax(gvb_ctx* ctx, const double* v, double* out, long SB, long LB);
+/* data::ATx(double* u, SB, LB) + dot_product, data.cpp:728-835.  u: 4*LB entries (entries that
+ * would index individuals >= N are ignored); out: M entries.  Local, no communication. */
+int gvb_ATx(gvb_ctx* ctx, const double* u, double* out, long SB, long LB);
+
+/* ---- device vectors ------------------------------------------------------------------------------ */
+int gvb_vec_alloc(gvb_ctx* ctx, long n, gvb_vec* out);          /* zero-initialised */
+int gvb_vec_alloc_M(gvb_ctx* ctx, gvb_vec* out);                /* length M (local markers) */
+int gvb_vec_alloc_N(gvb_ctx* ctx, gvb_vec* out);                /* length 4*ceil(N/4) */
+void gvb_vec_free(gvb_ctx* ctx, gvb_vec v);
+long gvb_vec_len(gvb_vec v);
+void* gvb_vec_ptr(gvb_vec v);                                   /* raw device pointer */
+int gvb_vec_upload(gvb_ctx* ctx, gvb_vec dst, const double* src, long n);
+int gvb_vec_download(gvb_ctx* ctx, gvb_vec src, double* dst, long n);
+int gvb_vec_copy(gvb_ctx* ctx, gvb_vec dst, gvb_vec src);
+int gvb_vec_fill(gvb_ctx* ctx, gvb_vec dst, double value);
+/* out = a*x + b*y (y may be NULL); the M-vector algebra of infere_linear, vamp.cpp:348-354,485-486,
+ * 590-591,706-707 */
+int gvb_vec_axpby(gvb_ctx* ctx, gvb_vec out, double a, gvb_vec x, double b, gvb_vec y);
+/* res[k] = <x[k], y[k]> (y[k]==NULL: squared norm); inner_prod / l2_norm2, utilities.cpp:190-214.
+ * sync!=0 sums over ranks (one fused NCCL allreduce of n scalars instead of n MPI_Allreduce). */
+int gvb_vec_dots(gvb_ctx* ctx, int n, const gvb_vec* x, const gvb_vec* y, int sync, double* res);
+/* res[0] = ||x - y||^2 (local or rank-summed) -- the gamma re-estimation residuals, vamp.cpp:326,692 */
+int gvb_vec_dist2(gvb_ctx* ctx, gvb_vec x, gvb_vec y, int sync, double* res);
+
+/* device-resident matvecs used by the fused loop (same math as gvb_Ax / gvb_ATx, full range) */
+int gvb_dAx(gvb_ctx* ctx, gvb_vec v, gvb_vec out);
+int gvb_dATx(gvb_ctx* ctx, gvb_vec u, gvb_vec out);
+
+/* ---- denoiser and EM prior update ---------------------------------------------------------------- */
+/* x1_hat = g1(r1), sums[0] = sum_i g1d(r1_i) over ALL ranks, sums[1] = ||x1_hat - r1||^2 over all
+ * ranks: vamp::g1 / g1d, vamp.cpp:805-869 and the allreduce at :313. */
+int gvb_denoise(gvb_ctx* ctx, gvb_vec r1, double gam1, const double* probs, const double* vars, int L, gvb_vec x1_hat,
+                double* sums);
+/* One E-step of vamp::updatePrior, vamp.cpp:944-1013: sums[0] = sum pin; sums[1..L-1] = sum
+ * beta_j*pin; sums[L..2L-2] = sum beta_j*(m_j^2+v_j)*pin, all summed over ranks in ONE allreduce. */
+int gvb_em_stats(gvb_ctx* ctx, gvb_vec r1, double gam1, double lambda, const double* omegas, const double* vars, int L,
+                 double* sums);
+
+/* ---- LMMSE: operator, preconditioned CG, Onsager, noise precision ---------------------------------- */
+/* vamp::lmmse_mult, vamp.cpp:1074-1118: out = tau * ATx(Ax(v)) + gam2 * v */
+int gvb_lmmse_mult(gvb_ctx* ctx, gvb_vec v, double tau, double gam2, gvb_vec out);
+/* vamp::precondCG_solver, vamp.cpp:1130-1229.  mu holds the start vector on entry and the solution
+ * on exit.  denoiser==0 is the Onsager mode (exit on the trace estimate, :1174-1193).
+ * iters: iterations run; rel_res: ||r||/||rhs|| per iteration (room for max_iter doubles, may be NULL). */
+int gvb_cg_solve(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters,
+                 double* rel_res);
+
+/* ---- probit z-denoiser ---------------------------------------------------------------------------- */
+/* vamp::g1_bin_class / g1d_bin_class, vamp_probit.cpp:661-726 with erfcx (utilities.cpp:345-409):
+ * z1_hat[i] = g(p1[i]); sums[0] = sum_i g'(p1[i]) (i<N); sums[1] = ||z1_hat - p1||^2.  mcov may be NULL. */
+int gvb_probit_denoise(gvb_ctx* ctx, gvb_vec p1, gvb_vec y, gvb_vec mcov, double tau1, double probit_var, gvb_vec z1_hat,
+                       double* sums);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVAMP_B200_H */

@@ -1,0 +1,218 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden vectors.
+Integer / byte work must be bit-exact; floating point tolerances are written at each assert.
+The matvec tolerance is the north_star's 1e-6, measured norm-wise (||out-ref|| / ||ref||)."""
+import hashlib
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL_MATVEC = 1e-6     # BASELINE.json north_star: "Matvec outputs must agree within 1e-6 relative"
+KERNEL_GENS = ("simple", "lut")
+
+
+@pytest.fixture(scope="module")
+def C():
+    from gvamp_b200 import capi
+    capi.load()
+    assert capi.device_count() > 0, "no CUDA device: -m gpu tests need the B200 box"
+    return capi
+
+
+def make_ctx(C, gen):
+    os.environ["GVB_KERNELS"] = gen
+    return C.Context(0)
+
+
+@pytest.fixture(scope="module")
+def case_na(oracle):
+    """N % 4 != 0, 2 % missing genotypes, phenotype NAs (the golden matvec case)."""
+    g = golden("matvec_n1003.npz")
+    N, M = int(g["N"]), int(g["M"])
+    bed = oracle.synth_bed(int(g["seed"]), 0, M, N, miss_rate=float(g["miss_rate"]))
+    present = np.ones(N, bool)
+    present[g["na_idx"]] = False
+    mask4 = oracle.make_mask4(N, present)
+    ds = oracle.Dataset(bed, N, mask4=mask4, nonas=int(g["nonas"]))
+    return g, bed, mask4, ds
+
+
+def test_layout_roundtrip_bit_exact(C, oracle):
+    """PLINK bytes -> striped interleaved HBM layout -> PLINK bytes, for ragged shapes."""
+    for N, M in ((1003, 401), (128, 4), (5, 1), (4099, 67), (640, 130)):
+        bed = oracle.synth_bed(7, 0, M, N, miss_rate=0.05)
+        with C.Context(0) as ctx:
+            ctx.load_host(bed, N)
+            assert np.array_equal(ctx.decode(0, M), bed), (N, M)
+            if M > 3:
+                assert np.array_equal(ctx.decode(2, M - 3), bed[2:M - 1])
+
+
+def test_load_file_shard(C, oracle, tmp_path):
+    N, Mt = 1003, 400
+    bed = oracle.synth_bed(11, 0, Mt, N, miss_rate=0.02)
+    path = str(tmp_path / "x.bed")
+    oracle.write_bed(path, bed)
+    M, S = C.divide_work(Mt, 3, 1)
+    with C.Context(0) as ctx:
+        ctx.load_file(path, N, Mt, S, M)
+        assert np.array_equal(ctx.decode(0, M), bed[S:S + M])
+    with C.Context(0) as ctx:
+        with pytest.raises(C.GvbError):
+            ctx.load_file(str(tmp_path / "nope.bed"), N, Mt, S, M)
+
+
+def test_synth_matches_oracle_bytes(C, oracle):
+    for N, Mt, S, M, miss in ((1003, 900, 300, 257, 0.0), (2048, 64, 0, 64, 0.01), (777, 5000, 4100, 33, 0.3)):
+        with C.Context(0) as ctx:
+            ctx.synth(5, N, Mt, S, M, miss)
+            got = ctx.decode(0, M)
+        ref = oracle.synth_bed(5, S, M, N, miss_rate=miss)
+        assert np.array_equal(got, ref), (N, Mt, S, M)
+
+
+def test_counts_and_stats(C, case_na):
+    g, bed, mask4, ds = case_na
+    with C.Context(0) as ctx:
+        ctx.load_host(bed, ds.N).set_mask(mask4, ds.nonas).compute_stats(1.0)
+        assert np.array_equal(ctx.counts(), ds.counts())          # integers: bit-exact
+        mave, msig = ctx.stats()
+    assert relerr(mave, g["mave"]) < 1e-14 and relerr(msig, g["msig"]) < 1e-12
+    assert np.max(np.abs(mave - g["mave"])) < 1e-14
+
+
+def test_stats_alpha_scale_and_degenerate_columns(C, oracle):
+    N, M = 403, 12
+    bed = oracle.synth_bed(3, 0, M, N)
+    bed[0, :] = 0x55          # all missing   -> mean 0, inverse sd 1 (data.cpp:462-483)
+    bed[1, :] = 0xFF          # constant 0    -> inverse sd 1
+    bed[2, :] = 0x00          # constant 2
+    ds = oracle.Dataset(bed, N, alpha_scale=0.3)
+    with C.Context(0) as ctx:
+        ctx.load_host(bed, N).compute_stats(0.3)
+        mave, msig = ctx.stats()
+    assert relerr(mave, ds.mave) < 1e-14 and relerr(msig, ds.msig) < 1e-12
+    assert mave[0] == 0 and msig[0] == 1 and msig[1] == 1 and msig[2] == 1
+
+
+@pytest.mark.parametrize("gen", KERNEL_GENS)
+def test_ax_atx_golden(C, case_na, gen):
+    g, bed, mask4, ds = case_na
+    N = ds.N
+    with make_ctx(C, gen) as ctx:
+        ctx.load_host(bed, N).set_mask(mask4, ds.nonas).compute_stats(1.0)
+        ax = ctx.Ax(g["v"])
+        atx = ctx.ATx(g["u"])
+        SB, LB = int(g["SB"]), int(g["LB"])
+        ax_sub = ctx.Ax(g["v"], SB, LB)
+        atx_sub = ctx.ATx(g["u"][:4 * LB], SB, LB)
+    assert relerr(ax, g["Ax"]) < TOL_MATVEC and relerr(atx, g["ATx"]) < TOL_MATVEC
+    assert relerr(ax_sub, g["Ax_sub"]) < TOL_MATVEC and relerr(atx_sub, g["ATx_sub"]) < TOL_MATVEC
+    assert np.all(ax[N:] == 0) and np.all(ax[g["na_idx"]] == 0)      # pads and phenotype NAs are exactly zero
+    if gen == "simple":                                               # FP64 kernels: only the summation order differs
+        assert relerr(ax, g["Ax"]) < 1e-13 and relerr(atx, g["ATx"]) < 1e-13
+
+
+@pytest.mark.parametrize("gen", KERNEL_GENS)
+@pytest.mark.parametrize("N,M,miss", [(4096, 1024, 0.0), (1000, 2000, 0.0), (2500, 333, 0.01), (129, 5, 0.2), (20000, 4000, 0.0)])
+def test_ax_atx_vs_oracle(C, oracle, gen, N, M, miss):
+    bed = oracle.synth_bed(17, 0, M, N, miss_rate=miss)
+    ds = oracle.Dataset(bed, N)
+    rng = np.random.default_rng(N + M)
+    v = rng.normal(size=M) * np.where(rng.random(M) < 0.05, 30.0, 1.0)     # heavy-tailed like a sparse effect vector
+    u = rng.normal(size=N)
+    with make_ctx(C, gen) as ctx:
+        ctx.load_host(bed, N).compute_stats(1.0)
+        ax, atx = ctx.Ax(v), ctx.ATx(u)
+        # linearity and adjointness are size-independent properties of the operator pair
+        ax2 = ctx.Ax(2.5 * v)
+        lhs = float(np.dot(ax[:N], u))
+        rhs = float(np.dot(v, atx))
+    assert relerr(ax, ds.Ax(v)) < TOL_MATVEC
+    assert relerr(atx, ds.ATx(u)) < TOL_MATVEC
+    assert relerr(ax2, 2.5 * ax) < TOL_MATVEC
+    assert abs(lhs - rhs) <= 1e-6 * (np.linalg.norm(ax) * np.linalg.norm(u))
+
+
+def test_vector_ops(C, oracle):
+    N, M = 512, 3001
+    bed = oracle.synth_bed(1, 0, M, N)
+    rng = np.random.default_rng(0)
+    a, b = rng.normal(size=M), rng.normal(size=M)
+    with C.Context(0) as ctx:
+        ctx.load_host(bed, N)
+        va, vb, vo = ctx.vecM(a), ctx.vecM(b), ctx.vecM()
+        ctx.axpby(vo, 0.3, va, -1.7, vb)
+        assert relerr(vo.download(), 0.3 * a - 1.7 * b) < 1e-15
+        ctx.axpby(vo, 2.0, va)
+        assert np.array_equal(vo.download(), 2.0 * a)
+        d = ctx.dots([va, va, vb], [vb, None, None])
+        assert np.allclose(d, [a @ b, a @ a, b @ b], rtol=1e-13)
+        assert abs(ctx.dist2(va, vb) - ((a - b) ** 2).sum()) < 1e-10
+
+
+def test_denoiser_and_em_golden(C, oracle):
+    g = golden("denoiser.npz")
+    r1, probs, vars_ = g["r1"], g["probs"], g["vars"]
+    M = len(r1)
+    bed = oracle.synth_bed(1, 0, M, 64)
+    with C.Context(0) as ctx:
+        ctx.load_host(bed, 64)
+        vr, vx = ctx.vecM(r1), ctx.vecM()
+        for tag in "abc":
+            gam1 = float(g["gam1_" + tag])
+            sums = ctx.denoise(vr, gam1, probs, vars_, vx)
+            x1 = vx.download()
+            assert np.linalg.norm(x1 - g["g1_" + tag]) / np.linalg.norm(r1) < 1e-13
+            assert abs(sums[0] - g["g1d_" + tag].sum()) < 1e-9 * M
+            assert abs(sums[1] - ((g["g1_" + tag] - r1) ** 2).sum()) <= 1e-10 * max(1.0, sums[1])
+        # one E-step against the oracle restatement of vamp.cpp:944-1008
+        lam = 1 - probs[0]
+        om = probs.copy()
+        om[1:] /= lam
+        sums = ctx.em_stats(vr, 3.0, lam, om, vars_)
+        spin, res, resg = oracle.em_sufficient_stats(r1, 3.0, list(probs), list(vars_), lam, list(om))
+        assert relerr(sums, np.concatenate([[spin], res, resg])) < 1e-12
+
+
+def test_lmmse_and_cg_golden(C, oracle):
+    g = golden("cg.npz")
+    N, M = int(g["N"]), int(g["M"])
+    bed = oracle.synth_bed(int(g["seed"]), 0, M, N)
+    tau, gam2, K = float(g["tau"]), float(g["gam2"]), int(g["CG_max_iter"])
+    with C.Context(0) as ctx:
+        ctx.load_host(bed, N).compute_stats(1.0)
+        rhs, out, mu = ctx.vecM(g["rhs"]), ctx.vecM(), ctx.vecM()
+        ctx.lmmse_mult(rhs, tau, gam2, out)
+        assert relerr(out.download(), g["lmmse"]) < TOL_MATVEC
+        its, log = ctx.cg_solve(rhs, mu, tau, gam2, K, 1)
+        assert relerr(mu.download(), g["mu"]) < 1e-5            # CG stops at ||r||/||rhs|| < 1e-5 (vamp.cpp:1217)
+        mu.upload(g["mu"] * 0.9)
+        ctx.cg_solve(rhs, mu, tau, gam2, K, 1)
+        assert relerr(mu.download(), g["mu_warm"]) < 1e-5
+        bern, q = ctx.vecM(g["bern"]), ctx.vecM()
+        ctx.cg_solve(bern, q, tau, gam2, K, 0)
+        alpha2 = gam2 * ctx.dots([bern], [q])[0]
+        assert abs(alpha2 / float(g["alpha2"]) - 1) < 1e-6
+        # zero right-hand side start vector shortcut: lmmse_mult(0) == 0 (vamp.cpp:1079)
+        z = ctx.vecM()
+        ctx.lmmse_mult(z, tau, gam2, out)
+        assert not out.download().any()
+
+
+def test_probit_denoiser_golden(C, oracle):
+    g = golden("probit_pieces.npz")
+    n = len(g["p"])
+    bed = oracle.synth_bed(1, 0, 8, n)
+    with C.Context(0) as ctx:
+        ctx.load_host(bed, n)
+        p, y, mc, z = ctx.vecN(g["p"]), ctx.vecN(g["y"]), ctx.vecN(g["mcov"]), ctx.vecN()
+        sums = ctx.probit_denoise(p, y, mc, float(g["tau1"]), 1.0, z)
+        assert relerr(z.download(n), g["g"]) < 1e-14
+        assert abs(sums[0] - g["gd"].sum()) < 1e-10 * n
+        assert abs(sums[1] - ((g["g"] - g["p"]) ** 2).sum()) < 1e-10 * n

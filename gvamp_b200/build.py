@@ -67,7 +67,7 @@ def build_host(force=False, verbose=True):
     if not os.path.isdir(HOST):
         return []
     os.makedirs(BINDIR, exist_ok=True)
-    common = [os.path.join(HOST, f) for f in ("options.cpp", "data.cpp", "vamp.cpp", "utilities.cpp") if os.path.exists(os.path.join(HOST, f))]
+    common = [os.path.join(HOST, f) for f in ("options.cpp", "data.cpp", "vamp.cpp", "utilities.cpp", "comm.cpp") if os.path.exists(os.path.join(HOST, f))]
     headers = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")] + [os.path.join(ROOT, "include", "gvamp_b200.h")]
     outs = []
     flags = ["-O2", "-std=c++17", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + HOST, "-Wno-unused-result"]

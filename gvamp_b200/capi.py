@@ -28,6 +28,7 @@ SIGNATURES = {
     "gvb_device_count": (ci, [ctypes.POINTER(ci)]),
     "gvb_nccl_unique_id": (ci, [vp]),
     "gvb_ctx_create": (ci, [ctypes.POINTER(vp), ci, ci, ci, vp]),
+    "gvb_ctx_create_shared": (ci, [ctypes.POINTER(vp), vp]),
     "gvb_ctx_destroy": (None, [vp]),
     "gvb_ctx_sync": (ci, [vp]),
     "gvb_ctx_stream": (vp, [vp]),
@@ -37,6 +38,8 @@ SIGNATURES = {
     "gvb_timer_elapsed_ms": (ci, [vp, ci, ctypes.POINTER(ctypes.c_float)]),
     "gvb_launch_count": (cl, [vp]),
     "gvb_sweep_count": (cl, [vp]),
+    "gvb_profile_enable": (ci, [vp, ci]),
+    "gvb_profile_read": (ci, [vp, c_f64p]),
     "gvb_divide_work": (None, [cl, ci, ci, ctypes.POINTER(cl), ctypes.POINTER(cl)]),
     "gvb_bed_load_file": (ci, [vp, ctypes.c_char_p, cl, cl, cl, cl]),
     "gvb_bed_load_host": (ci, [vp, c_u8p, cl, cl, cl, cl]),
@@ -48,6 +51,8 @@ SIGNATURES = {
     "gvb_get_counts": (ci, [vp, c_i64p]),
     "gvb_Ax": (ci, [vp, c_f64p, c_f64p, cl, cl]),
     "gvb_ATx": (ci, [vp, c_f64p, c_f64p, cl, cl]),
+    "gvb_marker_dot": (ci, [vp, cl, c_f64p, cl, cl, c_f64p, c_f64p]),
+    "gvb_allreduce_host": (ci, [vp, c_f64p, ci]),
     "gvb_vec_alloc": (ci, [vp, cl, ctypes.POINTER(vp)]),
     "gvb_vec_alloc_M": (ci, [vp, ctypes.POINTER(vp)]),
     "gvb_vec_alloc_N": (ci, [vp, ctypes.POINTER(vp)]),
@@ -59,6 +64,7 @@ SIGNATURES = {
     "gvb_vec_copy": (ci, [vp, vp, vp]),
     "gvb_vec_fill": (ci, [vp, vp, cd]),
     "gvb_vec_axpby": (ci, [vp, vp, cd, vp, cd, vp]),
+    "gvb_vec_axpby_div": (ci, [vp, vp, cd, vp, cd, vp, cd]),
     "gvb_vec_dots": (ci, [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, c_f64p]),
     "gvb_vec_dist2": (ci, [vp, vp, vp, ci, c_f64p]),
     "gvb_dAx": (ci, [vp, vp, vp]),
@@ -330,6 +336,14 @@ class Context:
         ms = ctypes.c_float(0)
         _chk(self.L.gvb_timer_elapsed_ms(self.h, slot, ctypes.byref(ms)))
         return ms.value
+
+    def profile(self, on=True):
+        _chk(self.L.gvb_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        out = np.zeros(4)
+        _chk(self.L.gvb_profile_read(self.h, out.ctypes.data_as(c_f64p)))
+        return dict(ax_ms=out[0], ax_n=int(out[1]), atx_ms=out[2], atx_n=int(out[3]))
 
     def launches(self) -> int:
         return self.L.gvb_launch_count(self.h)

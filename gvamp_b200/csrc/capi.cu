@@ -46,6 +46,39 @@ extern "C" void gvb_divide_work(long Mt, int nranks, int rank, long* M, long* S)
     if (S) *S = start;
 }
 
+static int ctx_common_init(gvb_ctx* c) {
+    GVB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) {
+        GVB_CUDA(cudaEventCreate(&c->ev_start[i]));
+        GVB_CUDA(cudaEventCreate(&c->ev_stop[i]));
+    }
+    GVB_CUDA(cudaMalloc(&c->red_partial, sizeof(double) * GVB_RED_BLOCKS * GVB_RED_MAXK));
+    GVB_CUDA(cudaMalloc(&c->red_result, sizeof(double) * GVB_RED_MAXK));
+    GVB_CUDA(cudaMallocHost(&c->h_red, sizeof(double) * GVB_RED_MAXK));
+    GVB_CUDA(cudaMalloc(&c->scal, sizeof(double) * 64));
+    GVB_CUDA(cudaMalloc(&c->work_counter, sizeof(int) * 16));
+    GVB_CUDA(cudaMemset(c->work_counter, 0, sizeof(int) * 16));
+    const char* gen = getenv("GVB_KERNELS");
+    c->kernel_gen = (gen && !strcmp(gen, "simple")) ? 0 : 1;
+    return GVB_OK;
+}
+
+extern "C" int gvb_ctx_create_shared(gvb_ctx** out, gvb_ctx* parent) {
+    GVB_ARG(out && parent, "out / parent");
+    GVB_CUDA(cudaSetDevice(parent->device));
+    gvb_ctx* c = new gvb_ctx();
+    c->device = parent->device;
+    c->rank = parent->rank;
+    c->nranks = parent->nranks;
+    c->sm_count = parent->sm_count;
+    c->comm = parent->comm;
+    c->owns_comm = false;
+    int rc = ctx_common_init(c);
+    if (rc != GVB_OK) return rc;
+    *out = c;
+    return GVB_OK;
+}
+
 extern "C" int gvb_ctx_create(gvb_ctx** out, int device, int rank, int nranks, const void* id128) {
     GVB_ARG(out, "out");
     GVB_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "rank / nranks");
@@ -70,19 +103,7 @@ extern "C" int gvb_ctx_create(gvb_ctx** out, int device, int rank, int nranks, c
     c->rank = rank;
     c->nranks = nranks;
     c->sm_count = prop.multiProcessorCount;
-    GVB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 8; i++) {
-        GVB_CUDA(cudaEventCreate(&c->ev_start[i]));
-        GVB_CUDA(cudaEventCreate(&c->ev_stop[i]));
-    }
-    GVB_CUDA(cudaMalloc(&c->red_partial, sizeof(double) * GVB_RED_BLOCKS * GVB_RED_MAXK));
-    GVB_CUDA(cudaMalloc(&c->red_result, sizeof(double) * GVB_RED_MAXK));
-    GVB_CUDA(cudaMallocHost(&c->h_red, sizeof(double) * GVB_RED_MAXK));
-    GVB_CUDA(cudaMalloc(&c->scal, sizeof(double) * 64));
-    GVB_CUDA(cudaMalloc(&c->work_counter, sizeof(int) * 16));
-    GVB_CUDA(cudaMemset(c->work_counter, 0, sizeof(int) * 16));
-    const char* gen = getenv("GVB_KERNELS");
-    c->kernel_gen = (gen && !strcmp(gen, "simple")) ? 0 : 1;
+    GVB_CHECK(ctx_common_init(c));
     if (nranks > 1) {
         ncclUniqueId id;
         memcpy(&id, id128, sizeof(id));
@@ -105,7 +126,7 @@ extern "C" void gvb_ctx_destroy(gvb_ctx* c) {
     fr(c->tab_u); fr(c->tab_v); fr(c->acc_i64); fr(c->red_partial); fr(c->red_result); fr(c->scal); fr(c->work_counter);
     if (c->h_red) cudaFreeHost(c->h_red);
     for (int i = 0; i < 8; i++) { cudaEventDestroy(c->ev_start[i]); cudaEventDestroy(c->ev_stop[i]); }
-    if (c->comm) ncclCommDestroy(c->comm);
+    if (c->comm && c->owns_comm) ncclCommDestroy(c->comm);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -218,9 +239,47 @@ extern "C" int gvb_vec_fill(gvb_ctx* c, gvb_vec dst, double value) {
 // ------------------------------------------------------------------------------------------------
 // mat-vec dispatch (kernel generation) + NCCL allreduce of the partial N-vector
 // ------------------------------------------------------------------------------------------------
+static void prof_mark(gvb_ctx* c, int which) {
+    if (!c->profile) return;
+    if (c->prof_used[which] >= c->prof_ev[which].size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->prof_ev[which].push_back(e);
+    }
+    cudaEventRecord(c->prof_ev[which][c->prof_used[which]++], c->stream);
+}
+
+extern "C" int gvb_profile_enable(gvb_ctx* c, int on) {
+    GVB_ARG(c, "ctx");
+    c->profile = on != 0;
+    c->prof_used[0] = c->prof_used[1] = 0;
+    return GVB_OK;
+}
+
+extern "C" int gvb_profile_read(gvb_ctx* c, double* out4) {
+    GVB_ARG(c && out4, "ctx / out");
+    GVB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int w = 0; w < 2; w++) {
+        double tot = 0;
+        size_t n = c->prof_used[w] / 2;
+        for (size_t i = 0; i < n; i++) {
+            float ms = 0;
+            GVB_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[w][2 * i], c->prof_ev[w][2 * i + 1]));
+            tot += ms;
+        }
+        out4[2 * w] = tot;
+        out4[2 * w + 1] = (double)n;
+        c->prof_used[w] = 0;
+    }
+    return GVB_OK;
+}
+
 int gvb_ax_dev(gvb_ctx* c, const double* v, double* out, bool allreduce) {
     GVB_ARG(c->have_stats, "compute_stats must run before Ax");
-    GVB_CHECK(c->kernel_gen == 0 ? gvb_ax_simple(c, v, out) : gvb_ax_lut(c, v, out));
+    prof_mark(c, 0);
+    int rc_mv = c->kernel_gen == 0 ? gvb_ax_simple(c, v, out) : gvb_ax_lut(c, v, out);
+    prof_mark(c, 0);
+    GVB_CHECK(rc_mv);
     c->sweeps++;
     if (allreduce && c->nranks > 1) {
         // replaces MPI_Allreduce(Ax_temp, Ax_total, 4*LB, MPI_DOUBLE, MPI_SUM) -- data.cpp:995
@@ -230,7 +289,10 @@ int gvb_ax_dev(gvb_ctx* c, const double* v, double* out, bool allreduce) {
 }
 int gvb_atx_dev(gvb_ctx* c, const double* u, double* out) {
     GVB_ARG(c->have_stats, "compute_stats must run before ATx");
-    GVB_CHECK(c->kernel_gen == 0 ? gvb_atx_simple(c, u, out) : gvb_atx_lut(c, u, out));
+    prof_mark(c, 1);
+    int rc_mv = c->kernel_gen == 0 ? gvb_atx_simple(c, u, out) : gvb_atx_lut(c, u, out);
+    prof_mark(c, 1);
+    GVB_CHECK(rc_mv);
     c->sweeps++;
     return GVB_OK;
 }
@@ -288,6 +350,60 @@ extern "C" int gvb_ATx(gvb_ctx* c, const double* u, double* out, long SB, long L
     }
     GVB_CUDA(cudaMemcpyAsync(out, c->tmpM, c->M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     GVB_CUDA(cudaStreamSynchronize(c->stream));
+    return GVB_OK;
+}
+
+// the two accumulators of data::dot_product for one marker (data.cpp:758-779); a utility path: one block
+__global__ void marker_dot_kernel(const uint32_t* __restrict__ bed, long Mg_pad, long mloc, const double* __restrict__ u, long p_lo, long p_hi,
+                                  double* __restrict__ res) {
+    __shared__ double sa[256], sb[256];
+    double a = 0.0, b = 0.0;
+    long g = mloc >> 2;
+    int q = (int)(mloc & 3);
+    for (long p = p_lo + threadIdx.x; p < p_hi; p += blockDim.x) {
+        uint32_t w = bed[((p >> 5) * Mg_pad + g) * 32 + (p & 31)];
+        unsigned byte = (w >> (8 * q)) & 0xFFu;
+        for (int k = 0; k < 4; k++) {
+            unsigned code = (byte >> (2 * k)) & 3u;
+            double x = u[4 * p + k];
+            a += (code == 0u ? 2.0 : (code == 2u ? 1.0 : 0.0)) * x;
+            b += (code == 1u ? 0.0 : 1.0) * x;
+        }
+    }
+    sa[threadIdx.x] = a;
+    sb[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) { sa[threadIdx.x] += sa[threadIdx.x + s]; sb[threadIdx.x] += sb[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { res[0] = sa[0]; res[1] = sb[0]; }
+}
+
+extern "C" int gvb_marker_dot(gvb_ctx* c, long mloc, const double* u, long SB, long LB, double* dpa, double* dpb) {
+    GVB_ARG(c && c->bed && u && dpa && dpb, "ctx / matrix / pointers");
+    GVB_ARG(mloc >= 0 && mloc < c->M && SB >= 0 && LB > 0 && SB + LB <= c->mbytes, "marker / byte range");
+    long n_in = std::min(4 * LB, c->N - 4 * SB);
+    GVB_CUDA(cudaMemsetAsync(c->tmpN, 0, c->Npad * sizeof(double), c->stream));
+    if (n_in > 0) GVB_CUDA(cudaMemcpyAsync(c->tmpN + 4 * SB, u, n_in * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    marker_dot_kernel<<<1, 256, 0, c->stream>>>(c->bed, c->Mg_pad, mloc, c->tmpN, SB, SB + LB, c->red_result);
+    GVB_LAUNCHED(c);
+    GVB_CUDA(cudaMemcpyAsync(c->h_red, c->red_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GVB_CUDA(cudaStreamSynchronize(c->stream));
+    *dpa = c->h_red[0];
+    *dpb = c->h_red[1];
+    return GVB_OK;
+}
+
+extern "C" int gvb_allreduce_host(gvb_ctx* c, double* buf, int n) {
+    GVB_ARG(c && buf && n >= 0 && n <= GVB_RED_MAXK, "buffer of at most GVB_RED_MAXK doubles");
+    if (c->nranks <= 1 || n == 0) return GVB_OK;
+    for (int i = 0; i < n; i++) c->h_red[i] = buf[i];
+    GVB_CUDA(cudaMemcpyAsync(c->red_result, c->h_red, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GVB_NCCL(ncclAllReduce(c->red_result, c->red_result, n, ncclDouble, ncclSum, c->comm, c->stream));
+    GVB_CUDA(cudaMemcpyAsync(c->h_red, c->red_result, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GVB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; i++) buf[i] = c->h_red[i];
     return GVB_OK;
 }
 

@@ -42,6 +42,7 @@ struct gvb_ctx {
     int device = 0, rank = 0, nranks = 1;
     cudaStream_t stream = nullptr;
     ncclComm_t comm = nullptr;
+    bool owns_comm = true;
     int sm_count = 148;
 
     // problem dimensions
@@ -91,6 +92,9 @@ struct gvb_ctx {
     // timers and counters
     cudaEvent_t ev_start[8], ev_stop[8];
     long launches = 0, sweeps = 0;
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev[2];   // [0] X.v, [1] X^T.u : start/stop pairs
+    size_t prof_used[2] = {0, 0};
     std::vector<gvb_vec_s*> vecs;
 };
 

@@ -57,7 +57,8 @@ static inline int red_blocks(const gvb_ctx* c, long n) {
 // ------------------------------------------------------------------------------------------------
 // axpby, dots, dist2
 // ------------------------------------------------------------------------------------------------
-__global__ void axpby_kernel(double* __restrict__ out, double a, const double* __restrict__ x, double b, const double* __restrict__ y, long n) {
+// out may alias x or y (in-place damping), hence no __restrict__
+__global__ void axpby_kernel(double* out, double a, const double* x, double b, const double* y, long n) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
         out[i] = y ? a * x[i] + b * y[i] : a * x[i];
 }
@@ -67,6 +68,19 @@ extern "C" int gvb_vec_axpby(gvb_ctx* c, gvb_vec out, double a, gvb_vec x, doubl
     long n = x->n;
     int blocks = (int)std::min((n + 255) / 256, (long)c->sm_count * 8);
     axpby_kernel<<<blocks, 256, 0, c->stream>>>(out->d, a, x->d, b, y ? y->d : nullptr, n);
+    GVB_LAUNCHED(c);
+    return GVB_OK;
+}
+
+__global__ void axpby_div_kernel(double* out, double a, const double* x, double b, const double* y, double div, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) out[i] = (a * x[i] + b * y[i]) / div;
+}
+
+extern "C" int gvb_vec_axpby_div(gvb_ctx* c, gvb_vec out, double a, gvb_vec x, double b, gvb_vec y, double div) {
+    GVB_ARG(c && out && x && y && out->n == x->n && y->n == x->n, "vector lengths");
+    long n = x->n;
+    int blocks = (int)std::min((n + 255) / 256, (long)c->sm_count * 8);
+    axpby_div_kernel<<<blocks, 256, 0, c->stream>>>(out->d, a, x->d, b, y->d, div, n);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }

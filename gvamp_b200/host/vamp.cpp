@@ -1,0 +1,639 @@
+// vamp.cpp -- the gVAMP loop on a device-resident state.  Control flow, scalar formulas, exit tests,
+// log lines and output files follow the reference (vamp.cpp:149-1374 for the linear model,
+// vamp_probit.cpp:20-726 for the probit model); every vector operation is a kernel behind the C ABI.
+#include "vamp.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <numeric>
+#include <random>
+#include <stdexcept>
+
+#include "comm.hpp"
+#include "utilities.hpp"
+
+using gvb_host::wtime;
+
+namespace {
+[[noreturn]] void device_fatal(const char* what) {
+    std::cout << "FATAL: " << what << ": " << gvb_last_error() << std::endl;
+    exit(EXIT_FAILURE);
+}
+#define DEV(call)                                  \
+    do {                                           \
+        if ((call) != GVB_OK) device_fatal(#call); \
+    } while (0)
+
+inline double clampd(double x, double lo, double hi) { return std::min(std::max(x, lo), hi); }
+
+bool files_enabled() {
+    const char* e = getenv("GVB_NO_FILES");
+    return !(e && e[0] == '1');
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// constructors (vamp.cpp:32-139 of the reference: same defaults, same Options plumbing)
+// ---------------------------------------------------------------------------------------------------
+vamp::vamp(int N, int M, int Mt, double gam1, double gamw, int max_iter, double rho, std::vector<double> vars, std::vector<double> probs,
+           std::vector<double> true_signal, int rank, std::string out_dir, std::string out_name, std::string model, Options opt)
+    : N(N), M(M), Mt(Mt), C(opt.get_C()), max_iter(max_iter), rank(rank), gam1(gam1), gam2(0), eta1(0), eta2(0), rho(rho), gamw(gamw),
+      true_signal(true_signal), probs(probs), vars(vars), learn_vars(opt.get_learn_vars()), init_est(opt.get_init_est()), seed(opt.get_seed()),
+      gamma_damp(opt.get_gamma_damp()), model(model), out_dir(out_dir), out_name(out_name), use_freeze(opt.get_use_freeze()),
+      redglob(opt.get_redglob()), estimate_file(opt.get_estimate_file()), freeze_index_file(opt.get_freeze_index_file()) {
+    EM_max_iter = opt.get_EM_max_iter();
+    EM_err_thr = opt.get_EM_err_thr();
+    CG_max_iter = opt.get_CG_max_iter();
+    reverse = opt.get_use_XXT_denoiser();
+    use_lmmse_damp = opt.get_use_lmmse_damp();
+    stop_criteria_thr = opt.get_stop_criteria_thr();
+    probit_var = opt.get_probit_var();
+    gam1_init = opt.get_gam1_init();
+    gamw_init = opt.get_gamw_init();
+    r1_init_file = opt.get_estimate_file();
+    initialize_prior(this->probs, this->vars, N, Mt, rank);
+    nranks = gvb_host::world().nranks;
+    const char* d = getenv("GVB_DIAG");
+    extra_diagnostics = d && d[0] == '1';
+}
+
+vamp::vamp(int M, double gam1, double gamw, std::vector<double> true_signal, int rank, Options opt)
+    : M(M), C(opt.get_C()), rank(rank), gam1(gam1), gam2(0), eta1(0), eta2(0), rho(opt.get_rho()), gamw(gamw), true_signal(true_signal),
+      probs(opt.get_probs()), learn_vars(opt.get_learn_vars()), init_est(opt.get_init_est()), seed(opt.get_seed()),
+      gamma_damp(opt.get_gamma_damp()), model(opt.get_model()), out_dir(opt.get_out_dir()), out_name(opt.get_out_name()),
+      store_pvals(opt.get_store_pvals()), reverse(opt.get_use_XXT_denoiser()), use_lmmse_damp(opt.get_use_lmmse_damp()),
+      use_freeze(opt.get_use_freeze()), redglob(opt.get_redglob()), estimate_file(opt.get_estimate_file()),
+      freeze_index_file(opt.get_freeze_index_file()) {
+    N = opt.get_N();
+    Mt = opt.get_Mt();
+    max_iter = opt.get_iterations();
+    EM_max_iter = opt.get_EM_max_iter();
+    EM_err_thr = opt.get_EM_err_thr();
+    CG_max_iter = opt.get_CG_max_iter();
+    stop_criteria_thr = opt.get_stop_criteria_thr();
+    vars = opt.get_vars();
+    probit_var = opt.get_probit_var();
+    gam1_init = opt.get_gam1_init();
+    gamw_init = opt.get_gamw_init();
+    r1_init_file = opt.get_estimate_file();
+    initialize_prior(this->probs, this->vars, N, Mt, rank);
+    nranks = gvb_host::world().nranks;
+    const char* d = getenv("GVB_DIAG");
+    extra_diagnostics = d && d[0] == '1';
+}
+
+vamp::~vamp() { dev_close(); }
+
+// ---------------------------------------------------------------------------------------------------
+// device state
+// ---------------------------------------------------------------------------------------------------
+void vamp::dev_open(data* dataset) {
+    if (dev.ctx == dataset->device() && dev.r1) return;
+    dev_close();
+    dev.ctx = dataset->device();
+    gvb_vec* mvecs[] = {&dev.r1, &dev.r2, &dev.r2_prev, &dev.x1, &dev.x1_prev, &dev.x2, &dev.mu_last, &dev.rhs, &dev.bern, &dev.invq, &dev.tmpM, &dev.truth};
+    for (gvb_vec* v : mvecs) DEV(gvb_vec_alloc_M(dev.ctx, v));
+    gvb_vec* nvecs[] = {&dev.y, &dev.z1, &dev.tmpN, &dev.tmpN2};
+    for (gvb_vec* v : nvecs) DEV(gvb_vec_alloc_N(dev.ctx, v));
+    if ((int)true_signal.size() == M) DEV(gvb_vec_upload(dev.ctx, dev.truth, true_signal.data(), M));
+}
+
+void vamp::dev_close() {
+    if (!dev.ctx) return;
+    gvb_vec all[] = {dev.r1, dev.r2, dev.r2_prev, dev.x1, dev.x1_prev, dev.x2, dev.mu_last, dev.rhs, dev.bern, dev.invq, dev.tmpM, dev.truth,
+                     dev.y, dev.z1, dev.tmpN, dev.tmpN2, dev.p1, dev.p2, dev.z1h, dev.z2h, dev.mcov, dev.p1_prev};
+    for (gvb_vec v : all)
+        if (v) gvb_vec_free(dev.ctx, v);
+    dev = Dev();
+}
+
+void vamp::sync_host(gvb_vec v, std::vector<double>& h, size_t n) {
+    h.resize(n);
+    DEV(gvb_vec_download(dev.ctx, v, h.data(), (long)n));
+}
+
+// <out><name>: raw doubles of (v / div) at byte offset S*8, like mpi_store_vec_to_file (utilities.cpp:293-301)
+void vamp::store_scaled(gvb_vec v, const std::string& path, double div, int S) {
+    std::vector<double> h;
+    sync_host(v, h, M);
+    if (!files_enabled()) return;
+    for (double& x : h) x = x / div;
+    mpi_store_vec_to_file(path, h, S, M);
+}
+
+void vamp::dev_denoise(double g1_prec, double* sum_d, double* dist2) {
+    double sums[2];
+    DEV(gvb_denoise(dev.ctx, dev.r1, g1_prec, probs.data(), vars.data(), (int)probs.size(), dev.x1, sums));
+    *sum_d = sums[0];
+    *dist2 = sums[1];
+}
+
+int vamp::dev_cg(gvb_vec rhs, gvb_vec mu, double tau, int denoiser) {
+    std::vector<double> log(4 * (size_t)CG_max_iter, 0.0);
+    int iters = 0;
+    DEV(gvb_cg_solve(dev.ctx, rhs, mu, tau, gam2, CG_max_iter, denoiser, &iters, log.data()));
+    if (rank == 0) {
+        for (int i = 0; i < iters; i++) {
+            if (denoiser == 0 && log[4 * i + 3] >= 0 && log[4 * i + 0] >= 0)
+                std::cout << "[CG onsager] it = " << i << ": relative error for onsager is " << std::setprecision(10) << log[4 * i + 3] << std::endl;
+            if (log[4 * i + 0] >= 0)
+                std::cout << "[CG] it = " << i << ": ||r_it|| / ||RHS|| = " << std::setprecision(10) << log[4 * i + 0] << ", ||x_it|| = " << log[4 * i + 1]
+                          << ", ||z|| / ||RHS|| = " << log[4 * i + 2] << std::endl;
+        }
+    }
+    return iters;
+}
+
+// R2 = 1 - ||y - Ax||^2 / ||y||^2 over the N individuals (err_measures, vamp.cpp:1303-1317)
+double vamp::r2_train(gvb_vec ax) {
+    double num = 0, den = 0;
+    DEV(gvb_vec_dist2(dev.ctx, dev.y, ax, 0, &num));
+    gvb_vec xs[1] = {dev.y};
+    DEV(gvb_vec_dots(dev.ctx, 1, xs, nullptr, 0, &den));
+    double l2_pred_err = sqrt(num / den);
+    if (rank == 0) std::cout << "l2 prediction error = " << l2_pred_err << std::endl;
+    return 1 - l2_pred_err * l2_pred_err;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// entry point (vamp.cpp:149-183)
+// ---------------------------------------------------------------------------------------------------
+std::vector<double> vamp::infere(data* dataset) {
+    prepare(dataset);
+    if (!strcmp(model.c_str(), "linear")) return infere_linear(dataset);
+    if (!strcmp(model.c_str(), "bin_class")) return infere_bin_class(dataset);
+    throw "invalid model specification!";
+}
+
+void vamp::prepare(data* dataset) {
+    y = dataset->get_phen();
+    // the design matrix is scaled by 1/sqrt(N), so the effect variances are scaled by N
+    for (double& v : vars) v *= N;
+    if (reverse == 1) {
+        std::cout << "FATAL: --use-XXT-denoiser 1 (N x N LMMSE) is outside the B200 hot path and not built" << std::endl;
+        exit(EXIT_FAILURE);
+    }
+    if (redglob != 0 || use_freeze != 0) {
+        std::cout << "FATAL: --red / --use-freeze are not supported by the B200 build" << std::endl;
+        exit(EXIT_FAILURE);
+    }
+    if (strcmp(model.c_str(), "linear") && strcmp(model.c_str(), "bin_class")) throw "invalid model specification!";
+}
+
+// ---------------------------------------------------------------------------------------------------
+// linear model (vamp.cpp:190-803)
+// ---------------------------------------------------------------------------------------------------
+std::vector<double> vamp::infere_linear(data* dataset) {
+    linear_begin(dataset);
+    for (int it = 1; it <= max_iter; it++)
+        if (linear_iteration(dataset, it)) break;
+    return linear_end();
+}
+
+void vamp::upload_iteration_inputs(const double* y_host, const double* r1_host) {
+    if (y_host) DEV(gvb_vec_upload(dev.ctx, dev.y, y_host, N));
+    if (r1_host) DEV(gvb_vec_upload(dev.ctx, dev.r1, r1_host, M));
+}
+
+void vamp::linear_begin(data* dataset) {
+    dev_open(dataset);
+    gvb_ctx* ctx = dev.ctx;
+    const int S = dataset->get_S();
+    shard_S = S;
+    alpha1 = 0;
+
+    std::vector<double> yf = dataset->filter_pheno();   // NA phenotypes -> 0
+    yf.resize(N, 0.0);
+    DEV(gvb_vec_fill(ctx, dev.y, 0.0));
+    DEV(gvb_vec_upload(ctx, dev.y, yf.data(), N));
+    DEV(gvb_vec_fill(ctx, dev.r1, 0.0));
+    DEV(gvb_vec_fill(ctx, dev.x1, 0.0));
+    DEV(gvb_vec_fill(ctx, dev.r2, 0.0));
+
+    if (gam1_init != -1) {   // restart (vamp.cpp:226-233)
+        gam1 = gam1_init;
+        gamw = gamw_init;
+        std::vector<double> r1_init = mpi_read_vec_from_file(r1_init_file, M, S);
+        for (double& v : r1_init) v /= sqrt((double)N);
+        DEV(gvb_vec_upload(ctx, dev.r1, r1_init.data(), M));
+    }
+    if (init_est == 1) {     // start from a supplied estimate (vamp.cpp:244-258)
+        std::vector<double> x_est;
+        std::string ext = estimate_file.substr(estimate_file.find(".") + 1);
+        x_est = (ext == "bin") ? mpi_read_vec_from_file(estimate_file, M, S) : read_vec_from_file(estimate_file, M, S);
+        for (double& v : x_est) v *= sqrt((double)N);
+        x_est.resize(M, 0.0);
+        DEV(gvb_vec_upload(ctx, dev.x1, x_est.data(), M));
+        DEV(gvb_vec_upload(ctx, dev.r1, x_est.data(), M));
+    }
+
+    x1_hat_stored.assign(M, 0.0);
+}
+
+bool vamp::linear_iteration(data* dataset, int it) {
+    gvb_ctx* ctx = dev.ctx;
+    const int S = shard_S;
+    const double scale = sqrt((double)N);
+    {
+        // ================= denoising step =================
+        double start_denoising = wtime();
+        const long sweeps0 = gvb_sweep_count(ctx);
+        if (rank == 0)
+            std::cout << std::endl << "********************" << std::endl << "iteration = " << it << std::endl << "********************" << std::endl
+                      << "->DENOISING" << std::endl;
+        DEV(gvb_vec_copy(ctx, dev.x1_prev, dev.x1));
+        probs_before = probs;
+        vars_before = vars;
+        double alpha1_prev = alpha1;
+        double gam1_reEst_prev;
+        int it_revar = 1;
+        for (; it_revar <= auto_var_max_iter; it_revar++) {
+            double sum_d = 0, dist2 = 0;
+            dev_denoise(gam1, &sum_d, &dist2);
+            if (it == 1 && init_est == 1) {
+                DEV(gvb_vec_copy(ctx, dev.x1, dev.r1));
+                dist2 = 0;
+            }
+            alpha1 = sum_d / Mt;
+            eta1 = gam1 / alpha1;
+            if (it <= 1) break;
+            gam1_reEst_prev = gam1;
+            gam1 = clampd(1.0 / (1.0 / eta1 + dist2 / Mt), gamma_min, gamma_max);
+            updatePrior(0);
+            if (rank == 0) std::cout << "[old] it_revar = " << it_revar << ": gam1 = " << gam1 << std::endl;
+            if (std::fabs(gam1 - gam1_reEst_prev) < 1e-3) break;
+        }
+        gam1s.push_back(gam1);
+        if (rank == 0) std::cout << "A total of " << std::max(it_revar - 1, 1) << " variance and prior tuning iterations were performed" << std::endl;
+
+        if (it > 1) {   // damping (vamp.cpp:348-414)
+            DEV(gvb_vec_axpby(ctx, dev.x1, rho, dev.x1, 1 - rho, dev.x1_prev));
+            alpha1 = rho * alpha1 + (1 - rho) * alpha1_prev;
+        }
+
+        double start_z1 = wtime();
+        DEV(gvb_dAx(ctx, dev.x1, dev.z1));
+        sync_host(dev.z1, z1, 4 * dataset->get_mbytes());
+        double end_z1 = wtime();
+        if (rank == 0) std::cout << "time needed to calculate z1 = " << end_z1 - start_z1 << " seconds" << std::endl;
+        std::string filepath_out_z1 = out_dir + out_name + "_z1_it_" + std::to_string(it) + ".csv";
+        if (files_enabled() && rank == 0) {
+            std::ofstream f(filepath_out_z1);
+            for (double v : z1) f << v << '\n';
+        }
+        if (rank == 0) std::cout << "filepath_out_z1 = " << filepath_out_z1 << std::endl;
+        if (rank == 0) std::cout << "rho = " << rho << std::endl;
+
+        double start_saving = wtime();
+        std::string filepath_out = out_dir + out_name + "_it_" + std::to_string(it) + ".bin";
+        sync_host(dev.x1, x1_hat, M);
+        for (int i = 0; i < M; i++) x1_hat_stored[i] = x1_hat[i] / scale;
+        if (files_enabled()) mpi_store_vec_to_file(filepath_out, x1_hat_stored, S, M);
+        if (rank == 0) std::cout << "x1_hat filepath_out is " << filepath_out << std::endl;
+        std::string filepath_out_r1 = out_dir + out_name + "_r1_it_" + std::to_string(it) + ".bin";
+        store_scaled(dev.r1, filepath_out_r1, scale, S);
+        if (rank == 0) std::cout << "r1 filepath_out is " << filepath_out_r1 << std::endl;
+        if (rank == 0) std::cout << "time needed to save beta1 to an external file = " << wtime() - start_saving << " seconds" << std::endl;
+
+        gam_before = gam2;
+        gam2 = clampd(eta1 - gam1, gamma_min, gamma_max);
+        if (rank == 0) {
+            std::cout << "eta1 = " << eta1 << std::endl;
+            std::cout << "gam2 = " << gam2 << std::endl;
+        }
+        DEV(gvb_vec_copy(ctx, dev.r2_prev, dev.r2));
+        DEV(gvb_vec_axpby_div(ctx, dev.r2, eta1, dev.x1, -gam1, dev.r1, gam2));   // r2 = (eta1 x1 - gam1 r1)/gam2
+        if (use_lmmse_damp == 1) {
+            double xi = std::min(2 * rho, 1.0);
+            if (it > 1) gam2 = 1.0 / pow(xi / sqrt(gam2) + (1 - xi) / sqrt(gam_before), 2);
+        }
+        // larger damping factors if the Onsager terms allow it (vamp.cpp:501-502)
+        double xi = std::min(2 * std::min(alpha1, alpha2), 1.0);
+        rho = std::max(rho, xi);
+        {
+            double se = 0;
+            DEV(gvb_vec_axpby(ctx, dev.tmpM, scale, dev.truth, 0.0, nullptr));
+            DEV(gvb_vec_dist2(ctx, dev.r2, dev.tmpM, 1, &se));
+            if (rank == 0) std::cout << "true gam2 = " << Mt / se << std::endl;
+        }
+        double start_prior_up = wtime();
+        if (auto_var_max_iter == 0 || it <= 1) updatePrior(1);
+        if (rank == 0) std::cout << "time needed to calculate conditional expectation = " << wtime() - start_prior_up << " seconds" << std::endl;
+        err_measures(dataset, 1);
+        double end_denoising = wtime();
+        if (rank == 0) std::cout << "denoising step took " << end_denoising - start_denoising << " seconds." << std::endl;
+
+        // ================= LMMSE step =================
+        std::string filepath_out_r2 = out_dir + out_name + "_r2_it_" + std::to_string(it) + ".bin";
+        store_scaled(dev.r2, filepath_out_r2, scale, S);
+        if (rank == 0) std::cout << "r2 filepath_out is " << filepath_out_r2 << std::endl;
+        double start_lmmse_step = wtime();
+        if (rank == 0) std::cout << "______________________" << std::endl << "->LMMSE" << std::endl;
+
+        double start_CG = wtime();
+        // v = gamw * A^T y + gam2 * r2
+        DEV(gvb_dATx(ctx, dev.y, dev.tmpM));
+        DEV(gvb_vec_axpby(ctx, dev.rhs, gamw, dev.tmpM, gam2, dev.r2));
+        if (it == 1)
+            DEV(gvb_vec_fill(ctx, dev.x2, 0.0));
+        else
+            DEV(gvb_vec_copy(ctx, dev.x2, dev.mu_last));   // warm start from the previous LMMSE estimate
+        last_cg_iters[0] = dev_cg(dev.rhs, dev.x2, gamw, 1);
+        DEV(gvb_vec_copy(ctx, dev.mu_last, dev.x2));
+        dev.ax_x2_valid = false;
+        std::string filepath_out_x2 = out_dir + out_name + "_it_" + std::to_string(it) + "_x2_hat.bin";
+        store_scaled(dev.x2, filepath_out_x2, scale, S);
+        if (rank == 0) std::cout << "x2_hat filepath_out is " << filepath_out_x2 << std::endl;
+        if (rank == 0) std::cout << "CG took " << wtime() - start_CG << " seconds." << std::endl;
+
+        double start_onsager = wtime();
+        alpha2 = g2d_onsager(gam2, gamw, dataset);
+        if (rank == 0) std::cout << "onsager took " << wtime() - start_onsager << " seconds." << std::endl;
+        if (rank == 0) std::cout << "alpha2 = " << alpha2 << std::endl;
+
+        if (it > 1 && extra_diagnostics) {   // print-only diagnostics of the reference (vamp.cpp:646-681)
+            DEV(gvb_vec_axpby(ctx, dev.tmpM, 1.0, dev.r2, -1.0, dev.r2_prev));
+            gvb_vec xs[2] = {dev.x2, dev.r2}, ys[2] = {dev.tmpM, dev.tmpM};
+            double d2[2];
+            DEV(gvb_vec_dots(ctx, 2, xs, ys, 1, d2));
+            if (rank == 0) std::cout << "onsager approx = " << d2[0] / d2[1] << std::endl;
+        }
+        eta2 = gam2 / alpha2;
+
+        if (auto_var_max_iter >= 1 && it > 2) {   // re-estimation of gam2 (vamp.cpp:691-693)
+            double dist2 = 0;
+            DEV(gvb_vec_dist2(ctx, dev.x2, dev.r2, 1, &dist2));
+            gam2 = clampd(1 / (1 / eta2 + dist2 / Mt), gamma_min, gamma_max);
+        }
+        if (rank == 0) std::cout << "gam2 re-est = " << gam2 << std::endl;
+        gam2s.push_back(gam2);
+
+        gam1 = clampd(eta2 - gam2, gamma_min, gamma_max);
+        DEV(gvb_vec_axpby_div(ctx, dev.r1, eta2, dev.x2, -gam2, dev.r2, gam1));   // r1 = (eta2 x2 - gam2 r2)/gam1
+        if (rank == 0) std::cout << "gam1 = " << gam1 << std::endl;
+        {
+            double se = 0;
+            DEV(gvb_vec_axpby(ctx, dev.tmpM, scale, dev.truth, 0.0, nullptr));
+            DEV(gvb_vec_dist2(ctx, dev.r1, dev.tmpM, 1, &se));
+            if (rank == 0) std::cout << "true gam1 = " << Mt / se << std::endl;
+        }
+
+        updateNoisePrec(dataset);
+        err_measures(dataset, 2);
+
+        double end_lmmse_step = wtime();
+        if (rank == 0) std::cout << "lmmse step took " << end_lmmse_step - start_lmmse_step << " seconds." << std::endl;
+        total_sweeps += gvb_sweep_count(ctx) - sweeps0;
+        if (rank == 0) std::cout << "bed sweeps this iteration = " << gvb_sweep_count(ctx) - sweeps0 << std::endl;
+
+        // stopping rule (vamp.cpp:741-749)
+        double dd = 0, nn = 0;
+        DEV(gvb_vec_dist2(ctx, dev.x1_prev, dev.x1, 1, &dd));
+        gvb_vec xs[1] = {dev.x1_prev};
+        DEV(gvb_vec_dots(ctx, 1, xs, nullptr, 1, &nn));
+        if (it > 1 && sqrt(dd / nn) < stop_criteria_thr) {
+            if (rank == 0) std::cout << "VAMP stopping criteria fulfilled with threshold = " << stop_criteria_thr << "." << std::endl;
+            return true;
+        }
+        if (rank == 0) std::cout << "total iteration time = " << end_denoising - start_denoising + end_lmmse_step - start_lmmse_step << std::endl;
+        total_comp_time += end_denoising - start_denoising + end_lmmse_step - start_lmmse_step;
+        if (rank == 0) std::cout << "total computation time so far = " << total_comp_time << std::endl;
+        if (rank == 0) std::cout << std::endl << std::endl;
+    }
+    return false;
+}
+
+std::vector<double> vamp::linear_end() {
+    if (store_pvals == 1 && rank == 0)
+        std::cout << "NOTE: --store-pvals (LOO / LOCO association tests) is post-processing outside the B200 hot path; skipped" << std::endl;
+
+    if (files_enabled() && rank == 0) {
+        store_vec_to_file(out_dir + out_name + "_gam1s.csv", gam1s);
+        store_vec_to_file(out_dir + out_name + "_gam2s.csv", gam2s);
+        store_vec_to_file(out_dir + out_name + "_R2trains.csv", R2trains);
+    }
+    if (rank == 0) {
+        std::cout << "gam1s filepath_out is " << out_dir + out_name + "_gam1s.csv" << std::endl;
+        std::cout << "gam2s filepath_out is " << out_dir + out_name + "_gam2s.csv" << std::endl;
+        std::cout << "R2trains filepath_out is " << out_dir + out_name + "_R2trains.csv" << std::endl;
+        int best = (int)(std::max_element(R2trains.begin(), R2trains.end()) - R2trains.begin());
+        std::cout << "index of max train R2 iteration = " << best << std::endl;
+    }
+    return x1_hat_stored;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// scalar denoisers (vamp.cpp:805-869): host evaluations for API parity; the loop uses gvb_denoise
+// ---------------------------------------------------------------------------------------------------
+double vamp::g1(double x, double gam1) {
+    const double sigma = 1 / gam1;
+    if (sigma < 1e-10 && sigma > -1e-10) return x;
+    const double eta_max = *std::max_element(vars.begin(), vars.end());
+    double pk = 0, pkd = 0;
+    for (size_t i = 0; i < probs.size(); i++) {
+        double vs = vars[i] + sigma;
+        double z = probs[i] / sqrt(vs) * exp(-0.5 * x * x * (eta_max - vars[i]) / vs / (eta_max + sigma));
+        pk += z;
+        pkd -= z / vs * x;
+    }
+    return x + sigma * pkd / pk;
+}
+
+double vamp::g1d(double x, double gam1) {
+    const double sigma = 1 / gam1;
+    if (sigma < 1e-10 && sigma > -1e-10) return 1;
+    const double eta_max = *std::max_element(vars.begin(), vars.end());
+    double pk = 0, pkd = 0, pkdd = 0;
+    for (size_t i = 0; i < probs.size(); i++) {
+        double vs = vars[i] + sigma;
+        double ex = exp(-0.5 * x * x * (eta_max - vars[i]) / vs / (eta_max + sigma));
+        double z = probs[i] / sqrt(vs) * ex;
+        pk += z;
+        z = z / vs * x;
+        pkd -= z;
+        pkdd = pkdd - probs[i] / pow(vs, 1.5) * ex + z / vs * x;
+    }
+    return 1 + sigma * (pkdd / pk - pow(pkd / pk, 2));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Onsager correction by a Hutchinson probe (vamp.cpp:871-889)
+// ---------------------------------------------------------------------------------------------------
+double vamp::g2d_onsager(double gam2, double tau, data* dataset) {
+    dev_open(dataset);
+    // Rademacher probe +-1/sqrt(Mt) from mt19937{seed + S}: identical stream to the reference on every shard
+    std::mt19937 rd{seed + (long unsigned int)dataset->get_S()};
+    std::bernoulli_distribution bern(0.5);
+    bern_vec.assign(M, 0.0);
+    for (int i = 0; i < M; i++) bern_vec[i] = (2 * bern(rd) - 1) / sqrt(Mt);
+    DEV(gvb_vec_upload(dev.ctx, dev.bern, bern_vec.data(), M));
+    DEV(gvb_vec_fill(dev.ctx, dev.invq, 0.0));
+    this->gam2 = gam2;
+    last_cg_iters[1] = dev_cg(dev.bern, dev.invq, tau, 0);
+    gvb_vec xs[1] = {dev.bern}, ys[1] = {dev.invq};
+    double dot = 0;
+    DEV(gvb_vec_dots(dev.ctx, 1, xs, ys, 1, &dot));
+    return gam2 * dot;   // gam2 * Tr[(tau X^T X + gam2 I)^-1] / Mt
+}
+
+// ---------------------------------------------------------------------------------------------------
+// noise precision (vamp.cpp:892-927)
+// ---------------------------------------------------------------------------------------------------
+void vamp::updateNoisePrec(data* dataset) {
+    gvb_ctx* ctx = dev.ctx;
+    DEV(gvb_dAx(ctx, dev.x2, dev.tmpN2));   // also reused by err_measures(2)
+    dev.ax_x2_valid = true;
+    double temp_norm2 = 0;
+    DEV(gvb_vec_dist2(ctx, dev.tmpN2, dev.y, 0, &temp_norm2));
+    DEV(gvb_dAx(ctx, dev.invq, dev.tmpN));
+    DEV(gvb_dATx(ctx, dev.tmpN, dev.tmpM));
+    gvb_vec xs[1] = {dev.bern}, ys[1] = {dev.tmpM};
+    double dot = 0;
+    DEV(gvb_vec_dots(ctx, 1, xs, ys, 1, &dot));
+    double trace_corr = dot * Mt;
+    if (rank == 0) {
+        std::cout << "l2_norm2(temp) / N = " << temp_norm2 / N << std::endl;
+        std::cout << "trace_correction / N = " << trace_corr / N << std::endl;
+    }
+    gamw = (double)N / (temp_norm2 + trace_corr);
+    (void)dataset;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// EM update of the prior (vamp.cpp:929-1072): the E-step sums come from one kernel + one allreduce
+// ---------------------------------------------------------------------------------------------------
+void vamp::updatePrior(int verbose) {
+    double lambda = 1 - probs[0];
+    std::vector<double> omegas = probs;
+    for (size_t j = 1; j < omegas.size(); j++) omegas[j] /= lambda;
+    const int L = (int)probs.size();
+    int it;
+    for (it = 0; it < EM_max_iter; it++) {
+        std::vector<double> probs_prev = probs, vars_prev = vars;
+        std::vector<double> sums(2 * L - 1, 0.0);
+        if (L >= 2) DEV(gvb_em_stats(dev.ctx, dev.r1, gam1, lambda, omegas.data(), vars.data(), L, sums.data()));
+        const double sum_of_pin = sums[0];
+        lambda = sum_of_pin / Mt;
+        for (int j = 0; j < L - 1; j++) {
+            double res = sums[1 + j], res_gammas = sums[L + j];
+            if (learn_vars == 1) vars[j + 1] = res_gammas / res;
+            omegas[j + 1] = res / sum_of_pin;
+            probs[j + 1] = lambda * omegas[j + 1];
+        }
+        probs[0] = 1 - lambda;
+        double dp = 0, np = 0, dv = 0, nv = 0;
+        for (int j = 0; j < L; j++) {
+            dp += (probs[j] - probs_prev[j]) * (probs[j] - probs_prev[j]);
+            np += probs[j] * probs[j];
+            dv += (vars[j] - vars_prev[j]) * (vars[j] - vars_prev[j]);
+            nv += vars[j] * vars[j];
+        }
+        double dist_probs = sqrt(dp / np), dist_vars = sqrt(dv / nv);
+        if (verbose == 1 && rank == 0) std::cout << "it = " << it << ": dist_probs = " << dist_probs << " & dist_vars = " << dist_vars << std::endl;
+        if (dist_probs < EM_err_thr && dist_vars < EM_err_thr) break;
+    }
+    if (verbose == 1 && rank == 0) std::cout << "Final number of prior EM iterations = " << std::min(it + 1, EM_max_iter) << " / " << EM_max_iter << std::endl;
+
+    // merge components whose variances are within 50 % of each other (vamp.cpp:1054-1071)
+    for (size_t j = 0; j < vars.size(); j++) {
+        for (size_t k = j + 1; k < vars.size(); k++) {
+            double denom = (vars[j] != 0) ? std::min(vars[j], vars[k]) : 1e-7;
+            if (std::fabs(vars[j] - vars[k]) / denom < 5e-1) {
+                probs[j] += probs[k];
+                vars.erase(vars.begin() + k);
+                probs.erase(probs.begin() + k);
+                k--;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-vector wrappers with the reference's signatures (vamp.cpp:1074-1229)
+// ---------------------------------------------------------------------------------------------------
+std::vector<double> vamp::lmmse_mult(std::vector<double> v, double tau, data* dataset, int red) {
+    if (red != 0) {
+        std::cout << "FATAL: reduced (--red) LMMSE products are not supported by the B200 build" << std::endl;
+        exit(EXIT_FAILURE);
+    }
+    dev_open(dataset);
+    DEV(gvb_vec_upload(dev.ctx, dev.tmpM, v.data(), M));
+    gvb_vec out = nullptr;
+    DEV(gvb_vec_alloc_M(dev.ctx, &out));
+    DEV(gvb_lmmse_mult(dev.ctx, dev.tmpM, tau, gam2, out));
+    std::vector<double> res(M);
+    DEV(gvb_vec_download(dev.ctx, out, res.data(), M));
+    gvb_vec_free(dev.ctx, out);
+    return res;
+}
+
+std::vector<double> vamp::precondCG_solver(std::vector<double> v, double tau, int denoiser, data* dataset, int red) {
+    return precondCG_solver(v, std::vector<double>(M, 0.0), tau, denoiser, dataset, red);
+}
+
+std::vector<double> vamp::precondCG_solver(std::vector<double> v, std::vector<double> mu_start, double tau, int denoiser, data* dataset, int red) {
+    if (red != 0) {
+        std::cout << "FATAL: reduced (--red) CG solves are not supported by the B200 build" << std::endl;
+        exit(EXIT_FAILURE);
+    }
+    dev_open(dataset);
+    gvb_vec rhs = nullptr, mu = nullptr;
+    DEV(gvb_vec_alloc_M(dev.ctx, &rhs));
+    DEV(gvb_vec_alloc_M(dev.ctx, &mu));
+    DEV(gvb_vec_upload(dev.ctx, rhs, v.data(), M));
+    DEV(gvb_vec_upload(dev.ctx, mu, mu_start.data(), M));
+    dev_cg(rhs, mu, tau, denoiser);
+    std::vector<double> res(M);
+    DEV(gvb_vec_download(dev.ctx, mu, res.data(), M));
+    if (denoiser == 1) mu_CG_last = res;
+    gvb_vec_free(dev.ctx, rhs);
+    gvb_vec_free(dev.ctx, mu);
+    return res;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// error measures (vamp.cpp:1232-1374)
+// ---------------------------------------------------------------------------------------------------
+void vamp::err_measures(data* dataset, int ind) {
+    gvb_ctx* ctx = dev.ctx;
+    gvb_vec est = (ind == 1) ? dev.x1 : dev.x2;
+    {
+        gvb_vec xs[3] = {est, est, dev.truth}, ys[3] = {dev.truth, nullptr, nullptr};
+        double d[3];
+        DEV(gvb_vec_dots(ctx, 3, xs, ys, 1, d));
+        double corr = d[0] / sqrt(d[1] * d[2]);
+        if (rank == 0) std::cout << "correlation " << (ind == 1 ? "x1_hat" : "x2_hat") << " = " << corr << std::endl;
+        DEV(gvb_vec_axpby(ctx, dev.tmpM, sqrt(1.0 / (double)N), est, -1.0, dev.truth));
+        gvb_vec x2s[1] = {dev.tmpM};
+        double e = 0;
+        DEV(gvb_vec_dots(ctx, 1, x2s, nullptr, 1, &e));
+        if (rank == 0) std::cout << "l2 signal error = " << sqrt(e / d[2]) << std::endl;
+    }
+    double R2;
+    if (ind == 1) {
+        R2 = r2_train(dev.z1);   // z1 = A x1_hat is already on the device
+    } else {
+        if (!dev.ax_x2_valid) {
+            DEV(gvb_dAx(ctx, dev.x2, dev.tmpN2));
+            dev.ax_x2_valid = true;
+        }
+        R2 = r2_train(dev.tmpN2);
+    }
+    R2trains.push_back(R2);
+    if (rank == 0) {
+        std::cout << "R2 = " << R2 << std::endl;
+        std::cout << "prior variances = ";
+        for (double v : vars) std::cout << v << ' ';
+        std::cout << std::endl << "prior probabilities = ";
+        for (double p : probs) std::cout << p << ' ';
+        std::cout << std::endl << "gamw = " << gamw << std::endl;
+    }
+    (void)dataset;
+}
+
+#include "vamp_probit.inc"

@@ -1,0 +1,148 @@
+// vamp.hpp -- class vamp: the gVAMP inference loop (linear and probit models).
+//
+// Public surface follows the reference's class vamp (vamp.hpp:78-148): two constructors, infere(),
+// the scalar denoisers g1/g1d/g1_bin_class/g1d_bin_class, updatePrior, g2d_onsager, updateNoisePrec,
+// lmmse_mult and precondCG_solver with std::vector arguments.  Internally every M- and N-vector of
+// the loop is resident in HBM and all vector math runs through the C ABI (include/gvamp_b200.h);
+// the host keeps only scalars, the L-component prior and the file output.
+// Out of scope: --model robust, --use-XXT-denoiser, cross-validation, state evolution.
+#pragma once
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "data.hpp"
+#include "options.hpp"
+
+class vamp {
+private:
+    int N, M, Mt, C, max_iter, rank, nranks;
+    double gam1, gam2, gam_before, eta1, eta2;
+    std::vector<double> gam1s, gam2s, R2trains;
+    double tau1, tau2;
+    double alpha1 = 0, alpha2 = 0;
+    double rho;
+    double gamw;
+
+    std::vector<double> x1_hat, x2_hat, true_signal;   // host mirrors, refreshed when files are written
+    std::vector<double> z1_hat, z2_hat;
+    std::vector<double> y;
+    std::vector<double> z1;
+    std::vector<double> r1, r2;
+    std::vector<double> p1, p2;
+    std::vector<double> cov_eff;
+    std::vector<double> mu_CG_last;
+
+    std::vector<double> probs, probs_before;
+    std::vector<double> vars, vars_before;
+
+    double gamma_min = 1e-11;
+    double gamma_max = 1e11;
+    double probit_var;
+    int EM_max_iter;
+    double EM_err_thr;
+    int CG_max_iter;
+    int auto_var_max_iter = 5;
+    int learn_vars;
+    int init_est;
+    long unsigned int seed;
+    double stop_criteria_thr;
+    double gamma_damp;
+
+    std::string model;
+    std::string out_dir;
+    std::string out_name;
+    std::vector<double> bern_vec;
+    std::vector<double> invQ_bern_vec;
+
+    int store_pvals = 1;
+    double total_comp_time = 0;
+    int reverse = 1;
+    int use_lmmse_damp = 0;
+    int use_freeze = 0;
+    int SBglob = 0, LBglob = 0, redglob = 0;
+
+    double gam1_init;
+    double gamw_init;
+    std::string r1_init_file;
+    std::string estimate_file;
+    std::string freeze_index_file;
+    std::vector<double> x1_hat_stored;
+    int shard_S = 0;
+    bool extra_diagnostics = false;   // GVB_DIAG=1: the reference's "onsager approx"/polynomial prints (3 extra sweeps)
+
+    // ---- device-resident state (HBM) ----
+    struct Dev {
+        gvb_ctx* ctx = nullptr;
+        gvb_vec r1 = nullptr, r2 = nullptr, r2_prev = nullptr, x1 = nullptr, x1_prev = nullptr, x2 = nullptr, mu_last = nullptr;
+        gvb_vec rhs = nullptr, bern = nullptr, invq = nullptr, tmpM = nullptr, truth = nullptr;
+        gvb_vec y = nullptr, z1 = nullptr, tmpN = nullptr, tmpN2 = nullptr;
+        gvb_vec p1 = nullptr, p2 = nullptr, z1h = nullptr, z2h = nullptr, mcov = nullptr, p1_prev = nullptr;
+        bool ax_x2_valid = false;   // tmpN2 holds Ax(x2) of the current iteration
+    } dev;
+    void dev_open(data* dataset);
+    void dev_close();
+    void dev_denoise(double g1_prec, double* sum_d, double* dist2);
+    int dev_cg(gvb_vec rhs, gvb_vec mu, double tau, int denoiser);
+    void sync_host(gvb_vec v, std::vector<double>& h, size_t n);
+    void store_scaled(gvb_vec v, const std::string& path, double div, int S);
+    double r2_train(gvb_vec ax);
+
+public:
+    vamp(int N, int M, int Mt, double gam1, double gamw, int max_iter, double rho, std::vector<double> vars, std::vector<double> probs,
+         std::vector<double> true_signal, int rank, std::string out_dir, std::string out_name, std::string model, Options opt = Options());
+    vamp(int M, double gam1, double gamw, std::vector<double> true_signal, int rank, Options opt);
+    ~vamp();
+
+    std::vector<double> infere(data* dataset);
+    std::vector<double> infere_linear(data* dataset);
+    std::vector<double> infere_bin_class(data* dataset);
+    // the linear loop in three pieces so that a harness can time single iterations: infere_linear() is
+    // linear_begin(); for (it) if (linear_iteration(it)) break; linear_end()
+    void linear_begin(data* dataset);
+    bool linear_iteration(data* dataset, int it);   // true when the stopping rule fired
+    std::vector<double> linear_end();
+    void prepare(data* dataset);                    // the scaling / checks infere() does before the loop
+    // refresh the iteration's inputs from host memory (the reference keeps y and r1 in host RAM)
+    void upload_iteration_inputs(const double* y_host, const double* r1_host);
+
+    double g1(double x, double gam1);
+    double g1_bin_class(double p, double tau1, double y, double m_cov);
+    double g1d(double x, double gam1);
+    double g1d_bin_class(double p, double tau1, double y, double m_cov);
+    double g2d_onsager(double gam2, double tau, data* dataset);
+
+    void updatePrior(int verbose);
+    void updateNoisePrec(data* dataset);
+
+    std::vector<double> lmmse_mult(std::vector<double> v, double tau, data* dataset, int red = 0);
+    std::vector<double> precondCG_solver(std::vector<double> v, double tau, int denoiser, data* dataset, int red = 0);
+    std::vector<double> precondCG_solver(std::vector<double> v, std::vector<double> mu_start, double tau, int denoiser, data* dataset, int red = 0);
+
+    void err_measures(data* dataset, int ind);
+    void probit_err_measures(data* dataset, int sync, std::vector<double> true_signal, std::vector<double> est, std::string var_name);
+
+    std::vector<double> grad_cov(std::vector<double> y, std::vector<double> gg, double probit_var, std::vector<std::vector<double>> Z,
+                                 std::vector<double> eta);
+    double mlogL_probit(std::vector<double> y, std::vector<double> gg, double probit_var, std::vector<std::vector<double>> Z,
+                        std::vector<double> eta);
+    std::vector<double> Newton_method_cov(std::vector<double> y, std::vector<double> gg, std::vector<std::vector<double>> Z,
+                                          std::vector<double> eta);
+
+    void set_SBglob(int SB) { SBglob = SB; }
+    void set_LBglob(int LB) { LBglob = LB; }
+    void set_gam2(double gam) { gam2 = gam; }
+    std::vector<double> get_cov_eff() const { return cov_eff; }
+
+    // state accessors used by the tests / the C shim (host_capi.cpp)
+    std::vector<double> get_probs() const { return probs; }
+    std::vector<double> get_vars() const { return vars; }
+    double get_gamw() const { return gamw; }
+    double get_gam1() const { return gam1; }
+    double get_gam2() const { return gam2; }
+    double get_alpha2() const { return alpha2; }
+    const std::vector<double>& get_gam1s() const { return gam1s; }
+    const std::vector<double>& get_R2trains() const { return R2trains; }
+    int last_cg_iters[2] = {0, 0};   // main solve / Onsager solve of the last iteration
+    long total_sweeps = 0;
+};

@@ -50,6 +50,9 @@ int gvb_nccl_unique_id(void* id128);
 
 /* device: CUDA ordinal; rank/nranks: position of this shard; id128 may be NULL when nranks==1. */
 int gvb_ctx_create(gvb_ctx** out, int device, int rank, int nranks, const void* id128);
+/* a second context (e.g. the test-set matrix of --run-mode both) on the same device that shares the
+ * parent's NCCL communicator; destroy it before the parent. */
+int gvb_ctx_create_shared(gvb_ctx** out, gvb_ctx* parent);
 void gvb_ctx_destroy(gvb_ctx* ctx);
 int gvb_ctx_sync(gvb_ctx* ctx);                    /* cudaStreamSynchronize on the context's stream */
 void* gvb_ctx_stream(gvb_ctx* ctx);                /* the cudaStream_t every kernel is launched on */
@@ -64,6 +67,11 @@ int gvb_timer_elapsed_ms(gvb_ctx* ctx, int slot, float* ms); /* synchronises on 
 long gvb_launch_count(gvb_ctx* ctx);
 /* bed sweeps (Ax + ATx passes over the packed matrix) since creation */
 long gvb_sweep_count(gvb_ctx* ctx);
+/* per-sweep device timing: when enabled every X.v / X^T.u sweep is bracketed by CUDA events on the
+ * context's stream.  gvb_profile_read synchronises, returns out[0..3] = {X.v total ms, X.v sweeps,
+ * X^T.u total ms, X^T.u sweeps} since the last read and resets the counters. */
+int gvb_profile_enable(gvb_ctx* ctx, int on);
+int gvb_profile_read(gvb_ctx* ctx, double* out4);
 
 /* ---- partition ------------------------------------------------------------------------------ */
 /* divide_work, utilities.cpp:259-291: first Mt%nranks ranks own Mt/nranks+1 contiguous markers */
@@ -101,6 +109,12 @@ int gvb_Ax(gvb_ctx* ctx, const double* v, double* out, long SB, long LB);
  * would index individuals >= N are ignored); out: M entries.  Local, no communication. */
 int gvb_ATx(gvb_ctx* ctx, const double* u, double* out, long SB, long LB);
 
+/* sum_i a_i u_i and sum_i b_i u_i of ONE local marker over the byte range [SB, SB+LB): the two
+ * accumulators of data::dot_product (data.cpp:728-801) before the caller's mu / sigma are applied. */
+int gvb_marker_dot(gvb_ctx* ctx, long mloc, const double* u, long SB, long LB, double* dpa, double* dpb);
+/* in-place sum over ranks of n host doubles: MPI_Allreduce(MPI_SUM) for the driver's host scalars */
+int gvb_allreduce_host(gvb_ctx* ctx, double* buf, int n);
+
 /* ---- device vectors ------------------------------------------------------------------------------ */
 int gvb_vec_alloc(gvb_ctx* ctx, long n, gvb_vec* out);          /* zero-initialised */
 int gvb_vec_alloc_M(gvb_ctx* ctx, gvb_vec* out);                /* length M (local markers) */
@@ -115,6 +129,8 @@ int gvb_vec_fill(gvb_ctx* ctx, gvb_vec dst, double value);
 /* out = a*x + b*y (y may be NULL); the M-vector algebra of infere_linear, vamp.cpp:348-354,485-486,
  * 590-591,706-707 */
 int gvb_vec_axpby(gvb_ctx* ctx, gvb_vec out, double a, gvb_vec x, double b, gvb_vec y);
+/* out = (a*x + b*y) / div, evaluated in that order like r2 = (eta1*x1 - gam1*r1)/gam2, vamp.cpp:486,707 */
+int gvb_vec_axpby_div(gvb_ctx* ctx, gvb_vec out, double a, gvb_vec x, double b, gvb_vec y, double div);
 /* res[k] = <x[k], y[k]> (y[k]==NULL: squared norm); inner_prod / l2_norm2, utilities.cpp:190-214.
  * sync!=0 sums over ranks (one fused NCCL allreduce of n scalars instead of n MPI_Allreduce). */
 int gvb_vec_dots(gvb_ctx* ctx, int n, const gvb_vec* x, const gvb_vec* y, int sync, double* res);

@@ -120,12 +120,14 @@ int gvb_layout_alloc(gvb_ctx* c, long N, long Mt, long S, long M) {
     c->Mg = (M + 3) / 4;
     c->Mg_pad = gvb_roundup(c->Mg, GVB_GROUP_TILE);
     c->bed_words = (size_t)c->n_stripes * (size_t)c->Mg_pad * 32;
-    cudaError_t e = cudaMalloc(&c->bed, c->bed_words * sizeof(uint32_t));
+    // 64 KB of slack behind the last stripe: the X^T.u kernel's last marker block may read past Mg_pad
+    const size_t slack_words = 16384;
+    cudaError_t e = cudaMalloc(&c->bed, (c->bed_words + slack_words) * sizeof(uint32_t));
     if (e != cudaSuccess) {
         gvb_set_error("cannot allocate %.3f GB of HBM for the packed genotype matrix: %s", c->bed_words * 4.0 / 1e9, cudaGetErrorString(e));
         return GVB_ERR_NOMEM;
     }
-    GVB_CUDA(cudaMemsetAsync(c->bed, 0x55, c->bed_words * sizeof(uint32_t), c->stream));
+    GVB_CUDA(cudaMemsetAsync(c->bed, 0x55, (c->bed_words + slack_words) * sizeof(uint32_t), c->stream));
     size_t npos = (size_t)c->n_stripes * 32;
     size_t mp = (size_t)c->Mg_pad * 4;
     GVB_CUDA(cudaMalloc(&c->maskw, npos * 4));

@@ -23,7 +23,13 @@ def _run_case(oracle, tmp_path, g, gen):
     oracle.write_phen(phenp, g["y"])
     outd = str(tmp_path / f"out_{gen}") + "/"
     args = ["--run-mode", "infere", "--model", "linear", "--bed-file", bedp, "--phen-files", phenp, "--N", str(N), "--Mt", str(M),
-            "--out-dir", outd, "--out-name", "g"] + [str(a) for a in g["args"]]
+            "--out-dir", outd, "--out-name", "g"]
+    # the remaining options exactly as the reference run used them (make_golden.py), minus its own paths / sizes
+    extra = [str(a) for a in g["args"]]
+    skip = {"--N", "--Mt", "--out-dir", "--out-name"}
+    for k in range(0, len(extra), 2):
+        if extra[k] not in skip:
+            args += [extra[k], extra[k + 1]]
     env = dict(os.environ, GVB_KERNELS=gen)
     r = subprocess.run([EXE] + args, capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -529,13 +529,17 @@ extern "C" int gvb_cg_solve(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, dou
     GVB_ARG(c && rhs && mu && rhs != mu, "vectors");
     GVB_ARG(rhs->cap >= c->Mg_pad * 4 && mu->cap >= c->Mg_pad * 4, "M-vectors from gvb_vec_alloc_M");
     long n = c->M;
-    gvb_vec r = nullptr, p = nullptr, d = nullptr;
-    GVB_CHECK(gvb_vec_alloc_M(c, &r));
-    GVB_CHECK(gvb_vec_alloc_M(c, &p));
-    GVB_CHECK(gvb_vec_alloc_M(c, &d));
+    for (int k = 0; k < 3; k++) {
+        if (c->cg_ws[k] && c->cg_ws[k]->cap != c->Mg_pad * 4) {   // matrix was reloaded with another shape
+            gvb_vec_free(c, c->cg_ws[k]);
+            c->cg_ws[k] = nullptr;
+        }
+        if (!c->cg_ws[k]) GVB_CHECK(gvb_vec_alloc_M(c, &c->cg_ws[k]));
+    }
+    gvb_vec r = c->cg_ws[0], p = c->cg_ws[1], d = c->cg_ws[2];
     int rc = GVB_OK;
     int it_done = 0;
-    auto cleanup = [&]() { gvb_vec_free(c, r); gvb_vec_free(c, p); gvb_vec_free(c, d); };
+    auto cleanup = [&]() {};
 #define CGCHK(x) do { rc = (x); if (rc != GVB_OK) { cleanup(); return rc; } } while (0)
     const double diag = tau * (double)(c->N - 1) / (double)c->N + gam2;
     const int nb = cg_blocks(n);

@@ -96,6 +96,7 @@ struct gvb_ctx {
     std::vector<cudaEvent_t> prof_ev[2];   // [0] X.v, [1] X^T.u : start/stop pairs
     size_t prof_used[2] = {0, 0};
     std::vector<gvb_vec_s*> vecs;
+    gvb_vec_s* cg_ws[3] = {nullptr, nullptr, nullptr};   // r, p, d of the CG solver (allocated once: no cudaMalloc in the loop)
 };
 
 #define GVB_RED_BLOCKS 296

@@ -59,7 +59,7 @@ static int ctx_common_init(gvb_ctx* c) {
     GVB_CUDA(cudaMalloc(&c->work_counter, sizeof(int) * 16));
     GVB_CUDA(cudaMemset(c->work_counter, 0, sizeof(int) * 16));
     const char* gen = getenv("GVB_KERNELS");
-    c->kernel_gen = (gen && !strcmp(gen, "simple")) ? 0 : 1;
+    c->kernel_gen = (gen && !strcmp(gen, "simple")) ? 0 : ((gen && !strcmp(gen, "lut1")) ? 1 : 2);
     return GVB_OK;
 }
 

@@ -87,7 +87,7 @@ struct gvb_ctx {
     size_t acc_i64_cap = 0;
     int* work_counter = nullptr;
     double* scal = nullptr;         // small device scalars
-    int kernel_gen = 1;             // 0: simple FP64 kernels, 1: table kernels (env GVB_KERNELS)
+    int kernel_gen = 2;             // 0: simple FP64 kernels, 1: gen-1 table kernels, 2: gen-2 tile kernels (env GVB_KERNELS)
 
     // timers and counters
     cudaEvent_t ev_start[8], ev_stop[8];
@@ -155,6 +155,9 @@ int gvb_ax_simple(gvb_ctx* c, const double* v, double* out);
 int gvb_atx_simple(gvb_ctx* c, const double* u, double* out);
 int gvb_ax_lut(gvb_ctx* c, const double* v, double* out);
 int gvb_atx_lut(gvb_ctx* c, const double* u, double* out);
+int gvb_ax_tile_main(gvb_ctx* c, unsigned long long* accN);    // gen-2 main kernels (matvec_tile.cu)
+int gvb_atx_tile_main(gvb_ctx* c, unsigned long long* acc);
+int gvb_atx_tile_window();
 int gvb_ax_dev(gvb_ctx* c, const double* v, double* out, bool allreduce);
 int gvb_atx_dev(gvb_ctx* c, const double* u, double* out);
 

@@ -359,10 +359,7 @@ TileTune tune_from_env() {
     if (const char* e = getenv("GVB_ATX_SPC")) t.atx_stripes_per_chunk = std::max(1, atoi(e));
     return t;
 }
-const TileTune& tune() {
-    static TileTune t = tune_from_env();
-    return t;
-}
+TileTune tune() { return tune_from_env(); }   // read per launch: the tests vary the chunking within one process
 
 template <int NW, int NS, bool USE_MAD>
 int launch_ax(gvb_ctx* c, unsigned long long* accN) {
@@ -406,14 +403,14 @@ int launch_atx(gvb_ctx* c, unsigned long long* acc) {
 
 // main kernel of X.v: accN[i] += sum over local markers of the table values (c->tab_v built by the caller)
 int gvb_ax_tile_main(gvb_ctx* c, unsigned long long* accN) {
-    const TileTune& t = tune();
+    const TileTune t = tune();
     if (t.variant == 1) return t.use_mad ? launch_ax<12, 3, true>(c, accN) : launch_ax<12, 3, false>(c, accN);
     return t.use_mad ? launch_ax<16, 2, true>(c, accN) : launch_ax<16, 2, false>(c, accN);
 }
 
 // main kernel of X^T.u for shards without missing genotypes: acc[j] += sum_i a_ij U_i (c->tab_u built by the caller)
 int gvb_atx_tile_main(gvb_ctx* c, unsigned long long* acc) {
-    const TileTune& t = tune();
+    const TileTune t = tune();
     if (t.variant == 1) return t.use_mad ? launch_atx<12, 3, true>(c, acc) : launch_atx<12, 3, false>(c, acc);
     return t.use_mad ? launch_atx<16, 2, true>(c, acc) : launch_atx<16, 2, false>(c, acc);
 }

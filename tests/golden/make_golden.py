@@ -153,6 +153,57 @@ def case_vamp_linear(tmp):
         fh.write("\n".join(l for l in log.splitlines() if not l.startswith("[CG")) + "\n")
 
 
+def case_vamp_probit(tmp):
+    """main_real_probit.exe --run-mode infere --model bin_class with C = 3 covariates, end to end
+    (vamp_probit.cpp:20-658; y = 1[U <= Phi(g + Z eta)] as in sim_probit.cpp:195-205)."""
+    from scipy.special import ndtr
+    N, M, seed, h2, CV, iters, C = 1000, 2000, 13, 0.5, 200, 5, 3
+    bed = O.synth_bed(seed, 0, M, N)
+    bedp = os.path.join(tmp, "p.bed")
+    O.write_bed(bedp, bed)
+    ds0 = O.Dataset(bed, N)
+    beta = O.synth_beta(seed, M, CV, h2)
+    rng = np.random.default_rng(seed)
+    Z = rng.normal(size=(N, C))
+    eta = np.array([0.25, -0.25, 0.25])
+    g = ds0.Ax(beta * math.sqrt(N))[:N] / math.sqrt(1.0 - h2)
+    y = (rng.random(N) <= ndtr(g + Z @ eta)).astype(float)
+    phenp, covp = os.path.join(tmp, "p.phen"), os.path.join(tmp, "p.cov")
+    O.write_phen(phenp, y)
+    with open(covp, "w") as fh:
+        for i in range(N):
+            fh.write(" ".join(repr(float(z)) for z in Z[i]) + "\n")   # C values per line, no id columns (data.cpp:286-331)
+    outd = os.path.join(tmp, "outp") + "/"
+    args = ["--run-mode", "infere", "--model", "bin_class", "--bed-file", bedp, "--phen-files", phenp, "--N", str(N), "--Mt", str(M),
+            "--out-dir", outd, "--out-name", "p", "--iterations", str(iters), "--CG-max-iter", "20", "--rho", "0.5",
+            "--probs", ",".join(map(str, PROBS)), "--vars", ",".join(map(str, VARS)), "--seed", "1", "--cov-file", covp, "--C", str(C)]
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    log = subprocess.run([R.exe("main_real_probit_scalar.exe")] + args, check=True, capture_output=True, text=True, env=env).stdout
+    out = dict(N=N, M=M, seed=seed, h2=h2, CV=CV, iterations=iters, C=C, args=np.array(args[8:]), y=y, Z=Z, beta=beta)
+    n_it = 0
+    for it in range(1, iters + 1):
+        f = f"{outd}p_probit_it_{it}.bin"
+        if not os.path.exists(f):
+            break
+        out[f"x1_{it}"] = np.fromfile(f)
+        f = f"{outd}p_probit_r1_it_{it}.bin"
+        if os.path.exists(f):
+            out[f"r1_{it}"] = np.fromfile(f)
+        n_it = it
+    out["iterations_done"] = n_it
+
+    def grab(prefix):
+        return np.array([float(l.split("=")[-1]) for l in log.splitlines() if l.startswith(prefix)])
+    for key, prefix in (("gam1_log", "gam1 = "), ("gam2_log", "gam2 = "), ("alpha2_log", "alpha2 = "), ("tau1_log", "tau1 = "), ("tau2_log", "tau2 = "),
+                        ("beta1_log", "beta1 = "), ("beta2_log", "beta2 = "), ("eta1_log", "eta1 = ")):
+        out[key] = grab(prefix)
+    cov = [l for l in log.splitlines() if l.startswith("cov_eff[")]
+    out["cov_eff_log"] = np.array([float(tok.split("=")[1]) for l in cov for tok in l.split(",") if "=" in tok])
+    np.savez_compressed(os.path.join(OUT, "vamp_probit.npz"), **out)
+    with open(os.path.join(OUT, "vamp_probit.log"), "w") as fh:
+        fh.write("\n".join(l for l in log.splitlines() if not l.startswith("[CG")) + "\n")
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first: make -C oracle ref"
     with tempfile.TemporaryDirectory() as tmp:
@@ -161,4 +212,5 @@ if __name__ == "__main__":
         case_probit_pieces()
         case_cg(tmp)
         case_vamp_linear(tmp)
+        case_vamp_probit(tmp)
     print("golden vectors written to", OUT)

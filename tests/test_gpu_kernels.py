@@ -13,7 +13,7 @@ from conftest import golden, relerr
 pytestmark = pytest.mark.gpu
 
 TOL_MATVEC = 1e-6     # BASELINE.json north_star: "Matvec outputs must agree within 1e-6 relative"
-KERNEL_GENS = ("simple", "lut")
+KERNEL_GENS = ("simple", "lut1", "lut")     # FP64 cross-check kernels, gen-1 table kernels, gen-2 tile kernels (default)
 
 
 @pytest.fixture(scope="module")
@@ -137,6 +137,45 @@ def test_ax_atx_vs_oracle(C, oracle, gen, N, M, miss):
     assert relerr(atx, ds.ATx(u)) < TOL_MATVEC
     assert relerr(ax2, 2.5 * ax) < TOL_MATVEC
     assert abs(lhs - rhs) <= 1e-6 * (np.linalg.norm(ax) * np.linalg.norm(u))
+
+
+@pytest.mark.parametrize("variant,tpc,spc", [(0, 3, 5), (1, 2, 7), (0, 64, 64)])
+def test_tile_kernels_many_work_items(C, oracle, variant, tpc, spc, monkeypatch):
+    """gen-2 tile kernels with small work items: several marker chunks / stripe chunks per CTA, partial last chunks,
+    inactive warps (stripes and marker tiles that are not multiples of the CTA shape), both CTA shapes."""
+    monkeypatch.setenv("GVB_TILE_VARIANT", str(variant))
+    monkeypatch.setenv("GVB_AX_TPC", str(tpc))
+    monkeypatch.setenv("GVB_ATX_SPC", str(spc))
+    N, M = 6100, 9000          # 48 stripes (3 CTA rows of 16), 71 marker tiles
+    bed = oracle.synth_bed(23, 0, M, N)
+    ds = oracle.Dataset(bed, N)
+    rng = np.random.default_rng(1)
+    v, u = rng.normal(size=M), rng.normal(size=N)
+    with make_ctx(C, "lut") as ctx:
+        ctx.load_host(bed, N).compute_stats(1.0)
+        ax, atx = ctx.Ax(v), ctx.ATx(u)
+        ax_again, atx_again = ctx.Ax(v), ctx.ATx(u)
+    assert relerr(ax, ds.Ax(v)) < TOL_MATVEC and relerr(atx, ds.ATx(u)) < TOL_MATVEC
+    # fixed-point accumulation: bit-reproducible, whatever order the work items ran in
+    assert np.array_equal(ax, ax_again) and np.array_equal(atx, atx_again)
+
+
+def test_tile_kernels_reproducible_across_chunking(C, oracle, monkeypatch):
+    """integer accumulation => the result does not depend on the tiling of the work at all (bit-exact)."""
+    N, M = 3000, 5000
+    bed = oracle.synth_bed(29, 0, M, N)
+    rng = np.random.default_rng(2)
+    v, u = rng.normal(size=M), rng.normal(size=N)
+    res = []
+    for variant, tpc, spc in ((0, 64, 64), (1, 1, 1), (0, 5, 3)):
+        monkeypatch.setenv("GVB_TILE_VARIANT", str(variant))
+        monkeypatch.setenv("GVB_AX_TPC", str(tpc))
+        monkeypatch.setenv("GVB_ATX_SPC", str(spc))
+        with make_ctx(C, "lut") as ctx:
+            ctx.load_host(bed, N).compute_stats(1.0)
+            res.append((ctx.Ax(v), ctx.ATx(u)))
+    for ax, atx in res[1:]:
+        assert np.array_equal(ax, res[0][0]) and np.array_equal(atx, res[0][1])
 
 
 def test_vector_ops(C, oracle):

@@ -81,3 +81,49 @@ def test_test_mode_r2(oracle, tmp_path):
     sd2 = (np.sum(phen ** 2) - N * phen.mean() ** 2) / (N - 1)
     want = 1 - np.sum((phen - z) ** 2) / (sd2 * N)
     assert abs(got - want) < TOL_FINAL
+
+
+EXE_PROBIT = os.path.join(ROOT, "gvamp_b200", "bin", "main_real_probit")
+
+
+@pytest.mark.parametrize("gen", ["simple", "lut"])
+def test_probit_vamp_matches_reference_files(oracle, tmp_path, gen):
+    """main_real_probit --model bin_class with C = 3 covariates against the files and log values of the UNMODIFIED
+    reference (tests/golden/vamp_probit.npz, made by make_golden.py:case_vamp_probit; vamp_probit.cpp:20-658)."""
+    g = golden("vamp_probit.npz")
+    N, M, iters, C = int(g["N"]), int(g["M"]), int(g["iterations"]), int(g["C"])
+    bed = oracle.synth_bed(int(g["seed"]), 0, M, N)
+    bedp, phenp, covp = str(tmp_path / "p.bed"), str(tmp_path / "p.phen"), str(tmp_path / "p.cov")
+    oracle.write_bed(bedp, bed)
+    oracle.write_phen(phenp, g["y"])
+    with open(covp, "w") as fh:
+        for row in g["Z"]:
+            fh.write(" ".join(repr(float(z)) for z in row) + "\n")
+    outd = str(tmp_path / f"outp_{gen}") + "/"
+    args = ["--run-mode", "infere", "--model", "bin_class", "--bed-file", bedp, "--phen-files", phenp, "--N", str(N), "--Mt", str(M),
+            "--out-dir", outd, "--out-name", "p", "--cov-file", covp, "--C", str(C)]
+    extra = [str(a) for a in g["args"]]
+    skip = {"--N", "--Mt", "--out-dir", "--out-name", "--cov-file", "--C"}
+    for k in range(0, len(extra), 2):
+        if extra[k] not in skip:
+            args += [extra[k], extra[k + 1]]
+    r = subprocess.run([EXE_PROBIT] + args, capture_output=True, text=True, env=dict(os.environ, GVB_KERNELS=gen), timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert int(g["iterations_done"]) == iters
+    for it in range(1, iters + 1):
+        for key, fn in (("x1", f"p_probit_it_{it}.bin"), ("r1", f"p_probit_r1_it_{it}.bin")):
+            ref, got = g[f"{key}_{it}"], np.fromfile(outd + fn)
+            assert got.shape == ref.shape
+            if np.linalg.norm(ref) > 0:
+                assert relerr(got, ref) < TOL_FINAL, (key, it, relerr(got, ref))
+
+    def grab(prefix):
+        return np.array([float(l.split("=")[-1]) for l in r.stdout.splitlines() if l.startswith(prefix)])
+    for key, prefix in (("gam1_log", "gam1 = "), ("gam2_log", "gam2 = "), ("alpha2_log", "alpha2 = "), ("tau1_log", "tau1 = "), ("tau2_log", "tau2 = "),
+                        ("beta1_log", "beta1 = "), ("beta2_log", "beta2 = "), ("eta1_log", "eta1 = ")):
+        got = grab(prefix)
+        assert got.shape == g[key].shape, (key, got, g[key])
+        assert np.allclose(got, g[key], rtol=5 * TOL_FINAL), (key, got, g[key])     # log lines carry 6 significant digits
+    cov = [l for l in r.stdout.splitlines() if l.startswith("cov_eff[")]
+    got_cov = np.array([float(tok.split("=")[1]) for l in cov for tok in l.split(",") if "=" in tok])
+    assert np.allclose(got_cov, g["cov_eff_log"], rtol=5 * TOL_FINAL)

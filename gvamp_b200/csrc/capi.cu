@@ -56,6 +56,7 @@ static int ctx_common_init(gvb_ctx* c) {
     GVB_CUDA(cudaMalloc(&c->red_result, sizeof(double) * GVB_RED_MAXK));
     GVB_CUDA(cudaMallocHost(&c->h_red, sizeof(double) * GVB_RED_MAXK));
     GVB_CUDA(cudaMalloc(&c->scal, sizeof(double) * 64));
+    GVB_CUDA(cudaMemset(c->scal, 0, sizeof(double) * 64));
     GVB_CUDA(cudaMalloc(&c->work_counter, sizeof(int) * 16));
     GVB_CUDA(cudaMemset(c->work_counter, 0, sizeof(int) * 16));
     const char* gen = getenv("GVB_KERNELS");
@@ -277,7 +278,7 @@ extern "C" int gvb_profile_read(gvb_ctx* c, double* out4) {
 int gvb_ax_dev(gvb_ctx* c, const double* v, double* out, bool allreduce) {
     GVB_ARG(c->have_stats, "compute_stats must run before Ax");
     prof_mark(c, 0);
-    int rc_mv = c->kernel_gen == 0 ? gvb_ax_simple(c, v, out) : gvb_ax_lut(c, v, out);
+    int rc_mv = c->kernel_gen == 0 ? gvb_ax_simple(c, v, out) : (c->kernel_gen == 1 ? gvb_ax_lut(c, v, out) : gvb_ax_tile(c, v, out));
     prof_mark(c, 0);
     GVB_CHECK(rc_mv);
     c->sweeps++;
@@ -290,7 +291,7 @@ int gvb_ax_dev(gvb_ctx* c, const double* v, double* out, bool allreduce) {
 int gvb_atx_dev(gvb_ctx* c, const double* u, double* out) {
     GVB_ARG(c->have_stats, "compute_stats must run before ATx");
     prof_mark(c, 1);
-    int rc_mv = c->kernel_gen == 0 ? gvb_atx_simple(c, u, out) : gvb_atx_lut(c, u, out);
+    int rc_mv = c->kernel_gen == 0 ? gvb_atx_simple(c, u, out) : (c->kernel_gen == 1 ? gvb_atx_lut(c, u, out) : gvb_atx_tile(c, u, out));
     prof_mark(c, 1);
     GVB_CHECK(rc_mv);
     c->sweeps++;

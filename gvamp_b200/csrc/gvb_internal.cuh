@@ -57,6 +57,7 @@ struct gvb_ctx {
     uint32_t* maskw = nullptr;
     uint32_t* validw = nullptr;
     int nonas = 0;
+    long mask_present = 0;          // individuals the mask selects (== nonas when the caller is consistent)
     bool have_mask = false, have_stats = false;
 
     // marker statistics
@@ -155,9 +156,9 @@ int gvb_ax_simple(gvb_ctx* c, const double* v, double* out);
 int gvb_atx_simple(gvb_ctx* c, const double* u, double* out);
 int gvb_ax_lut(gvb_ctx* c, const double* v, double* out);
 int gvb_atx_lut(gvb_ctx* c, const double* u, double* out);
-int gvb_ax_tile_main(gvb_ctx* c, unsigned long long* accN);    // gen-2 main kernels (matvec_tile.cu)
-int gvb_atx_tile_main(gvb_ctx* c, unsigned long long* acc);
-int gvb_atx_tile_window();
+int gvb_ax_tile(gvb_ctx* c, const double* v, double* out);     // gen-2 sweeps (matvec_tile.cu)
+int gvb_atx_tile(gvb_ctx* c, const double* u, double* out);
+int gvb_count_tile_main(gvb_ctx* c, const int* tab, unsigned long long* acc);
 int gvb_ax_dev(gvb_ctx* c, const double* v, double* out, bool allreduce);
 int gvb_atx_dev(gvb_ctx* c, const double* u, double* out);
 

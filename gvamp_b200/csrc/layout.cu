@@ -274,11 +274,13 @@ extern "C" int gvb_set_mask(gvb_ctx* c, const uint8_t* mask4, int nonas) {
     GVB_ARG(c && c->maskw, "ctx / matrix not allocated");
     size_t npos = (size_t)c->n_stripes * 32;
     std::vector<uint32_t> mw(npos, 0u), vw(npos, 0u);
+    long present = 0;
     for (long p = 0; p < c->mbytes; p++) {
         unsigned valid = 0;
         for (int k = 0; k < 4; k++)
             if (4 * p + k < c->N) valid |= 1u << k;
         unsigned m = mask4 ? (mask4[p] & 0xFu & valid) : valid;
+        present += __builtin_popcount(m);
         auto spread = [](unsigned nib) { return ((nib & 1u) | ((nib & 2u) << 1) | ((nib & 4u) << 2) | ((nib & 8u) << 3)) * 0x01010101u; };
         mw[p] = spread(m);
         vw[p] = spread(valid);
@@ -287,6 +289,7 @@ extern "C" int gvb_set_mask(gvb_ctx* c, const uint8_t* mask4, int nonas) {
     GVB_CUDA(cudaMemcpyAsync(c->validw, vw.data(), npos * 4, cudaMemcpyHostToDevice, c->stream));
     GVB_CUDA(cudaStreamSynchronize(c->stream));
     c->nonas = nonas;
+    c->mask_present = present;
     c->have_mask = true;
     c->have_stats = false;
     return GVB_OK;

@@ -350,17 +350,13 @@ int gvb_atx_lut(gvb_ctx* c, const double* u, double* out) {
     int nb = (int)std::max(1l, std::min((npos + 255) / 256, (long)GVB_RED_BLOCKS));
     atx_bound_kernel<<<nb, 256, 0, c->stream>>>(u, npos, c->red_partial);
     GVB_LAUNCHED(c);
-    const bool tile = c->kernel_gen >= 2 && !miss;   // gen 2 (matvec_tile.cu); shards with missing genotypes stay on gen 1
-    const double window = tile ? (double)gvb_atx_tile_window() : (double)std::min((long)AT_CHUNK, c->n_stripes);
-    scale_from_bound_kernel<<<1, 1, 0, c->stream>>>(c->red_partial, nb, window, 4.0, c->scal, usum);
+    scale_from_bound_kernel<<<1, 1, 0, c->stream>>>(c->red_partial, nb, (double)std::min((long)AT_CHUNK, c->n_stripes), 4.0, c->scal, usum);
     GVB_LAUNCHED(c);
     long total = c->n_stripes * 8192;
     atx_build_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(u, c->n_stripes, c->scal, c->tab_u, miss ? c->tab_u + total : nullptr, usum);
     GVB_LAUNCHED(c);
     if (miss)
         GVB_CHECK((launch_atx<6, 2, true>(c, acc, accm)));
-    else if (tile)
-        GVB_CHECK(gvb_atx_tile_main(c, acc));
     else
         GVB_CHECK((launch_atx<12, 3, false>(c, acc, accm)));
     atx_finish_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, c->stream>>>(acc, miss ? accm : nullptr, usum, c->scal, c->mave, c->msig, (long)Mpad,
@@ -568,15 +564,11 @@ int gvb_ax_lut(gvb_ctx* c, const double* v, double* out) {
         GVB_CUDA(cudaFuncSetAttribute(ax_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    if (c->kernel_gen >= 2) {
-        GVB_CHECK(gvb_ax_tile_main(c, accN));
-    } else {
-        int n_sblocks = (int)((c->n_stripes + AX_WARPS - 1) / AX_WARPS);
-        int n_gchunks = (int)((c->Mg_pad + AX_GCHUNK - 1) / AX_GCHUNK);
-        int grid = std::min(n_sblocks * n_gchunks, c->sm_count);
-        ax_lut_kernel<<<grid, AX_THREADS, smem, c->stream>>>(c->bed, c->tab_v, c->Mg_pad, c->n_stripes, n_sblocks, n_gchunks, c->work_counter, accN);
-        GVB_LAUNCHED(c);
-    }
+    int n_sblocks = (int)((c->n_stripes + AX_WARPS - 1) / AX_WARPS);
+    int n_gchunks = (int)((c->Mg_pad + AX_GCHUNK - 1) / AX_GCHUNK);
+    int grid = std::min(n_sblocks * n_gchunks, c->sm_count);
+    ax_lut_kernel<<<grid, AX_THREADS, smem, c->stream>>>(c->bed, c->tab_v, c->Mg_pad, c->n_stripes, n_sblocks, n_gchunks, c->work_counter, accN);
+    GVB_LAUNCHED(c);
     ax_finish_kernel2<<<(unsigned)((c->Npad + 255) / 256), 256, 0, c->stream>>>(accN, c->scal, c->maskw, c->Npad, 1.0 / sqrt((double)c->N), out);
     GVB_LAUNCHED(c);
     return GVB_OK;

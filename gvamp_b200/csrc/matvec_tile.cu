@@ -125,6 +125,19 @@ __device__ __forceinline__ void stage_table(uint32_t tab_sm, int buf, const int*
     }
 }
 
+// work_counter[0] hands out items, work_counter[1] counts the CTAs that ran dry: the last one re-arms both for the
+// next launch on the stream (no memset node between the sweeps)
+__device__ __forceinline__ void release_work_counter(int* work_counter) {
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(work_counter + 1, 1);
+        if (done == (int)gridDim.x - 1) {
+            work_counter[0] = 0;
+            work_counter[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
 // ===================================================================================================
 //  X . v : warp = stripe, lane = byte position (4 individuals), walk over the marker tiles of a chunk
 // ===================================================================================================
@@ -234,6 +247,7 @@ ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, l
                 if (acc64[k] != 0) atomicAdd(acc_out + (t * 32 + lane) * 4 + k, (unsigned long long)acc64[k]);
         }
     }
+    release_work_counter(work_counter);
 }
 
 // ===================================================================================================
@@ -255,7 +269,10 @@ __device__ __forceinline__ void atx_consume(const char* __restrict__ tabc, uint3
     }
 }
 
-template <int NW, int NS, bool USE_MAD>
+// MODE 0: plain sums (X^T.u).  MODE 1: every table entry packs three 10-bit counters (marker statistics, stats.cu); a
+// stripe adds at most 32 x 4 = 128 to each of them, and the per-stripe flush widens them to three 21-bit counters of
+// the int64 accumulator.
+template <int NW, int NS, bool USE_MAD, int MODE>
 __global__ void __launch_bounds__(NW * 32, 1)
 atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, long Mg_pad, long n_stripes, int n_gblocks, int n_schunks,
                 int stripes_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out, int one) {
@@ -329,7 +346,15 @@ atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
             n_use++;                                                                           \
             int a32[4] = {0, 0, 0, 0};                                                         \
             atx_consume<B, USE_MAD>(smem, bed_sm + s * TILE_BYTES + lane_off, spack, one, a32); \
-            _Pragma("unroll") for (int q = 0; q < 4; q++) acc64[q] += (long long)a32[q];       \
+            _Pragma("unroll") for (int q = 0; q < 4; q++) {                                    \
+                if (MODE == 0) {                                                               \
+                    acc64[q] += (long long)a32[q];                                             \
+                } else {                                                                       \
+                    const unsigned a = (unsigned)a32[q];                                       \
+                    acc64[q] += (long long)((unsigned long long)(a & 0x3FFu) | ((unsigned long long)((a >> 10) & 0x3FFu) << 21) | \
+                                            ((unsigned long long)(a >> 20) << 42));            \
+                }                                                                              \
+            }                                                                                  \
         }                                                                                      \
     }
             ATX_STEP(0)
@@ -343,6 +368,7 @@ atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
                 if (acc64[q] != 0) atomicAdd(acc_out + (T * 32 + lane) * 4 + q, (unsigned long long)acc64[q]);
         }
     }
+    release_work_counter(work_counter);
 }
 
 struct TileTune {
@@ -352,14 +378,22 @@ struct TileTune {
 };
 
 TileTune tune_from_env() {
-    TileTune t{0, false, 64, 64};
+    TileTune t{0, false, 0, 0};   // chunk lengths 0: chosen per launch from the problem size (pick_chunk)
     if (const char* e = getenv("GVB_TILE_VARIANT")) t.variant = atoi(e);
     if (const char* e = getenv("GVB_TILE_MAD")) t.use_mad = atoi(e) != 0;
     if (const char* e = getenv("GVB_AX_TPC")) t.ax_tiles_per_chunk = std::max(1, atoi(e));
     if (const char* e = getenv("GVB_ATX_SPC")) t.atx_stripes_per_chunk = std::max(1, atoi(e));
     return t;
 }
-TileTune tune() { return tune_from_env(); }   // read per launch: the tests vary the chunking within one process
+TileTune tune() { return tune_from_env(); }
+
+// steps (tiles of X.v / stripes of X^T.u) per work item: long enough to amortise the pipeline fill and to let the CTAs
+// of a wave share table tiles in L2 (<= 64), short enough that a small matrix still yields >= 4 items per SM
+int pick_chunk(int requested, long rows, long steps, int sm_count) {
+    if (requested > 0) return requested;
+    long per = (rows * steps + 4l * sm_count - 1) / (4l * sm_count);
+    return (int)std::max(4l, std::min(64l, per));
+}   // read per launch: the tests vary the chunking within one process
 
 template <int NW, int NS, bool USE_MAD>
 int launch_ax(gvb_ctx* c, unsigned long long* accN) {
@@ -370,9 +404,9 @@ int launch_ax(gvb_ctx* c, unsigned long long* accN) {
         GVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         attr_done = true;
     }
-    const int tpc = tune().ax_tiles_per_chunk;
     const long n_tiles = c->Mg_pad / 32;
     int n_sblocks = (int)((c->n_stripes + NW - 1) / NW);
+    const int tpc = pick_chunk(tune().ax_tiles_per_chunk, n_sblocks, n_tiles, c->sm_count);
     int n_gchunks = (int)((n_tiles + tpc - 1) / tpc);
     int grid = std::min(n_sblocks * n_gchunks, c->sm_count);
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(c->bed, c->tab_v, c->Mg_pad, c->n_stripes, n_sblocks, n_gchunks, tpc, c->work_counter, accN, 1);
@@ -380,40 +414,267 @@ int launch_ax(gvb_ctx* c, unsigned long long* accN) {
     return GVB_OK;
 }
 
-template <int NW, int NS, bool USE_MAD>
-int launch_atx(gvb_ctx* c, unsigned long long* acc) {
+template <int NW, int NS, bool USE_MAD, int MODE>
+int launch_atx(gvb_ctx* c, const int* tab, unsigned long long* acc) {
     using Cfg = TileCfg<NW, NS>;
-    auto kern = atx_tile_kernel<NW, NS, USE_MAD>;
+    auto kern = atx_tile_kernel<NW, NS, USE_MAD, MODE>;
     static bool attr_done = false;
     if (!attr_done) {
         GVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         attr_done = true;
     }
-    const int spc = tune().atx_stripes_per_chunk;
     const long n_tiles = c->Mg_pad / 32;
     int n_gblocks = (int)((n_tiles + NW - 1) / NW);
+    const int spc = pick_chunk(tune().atx_stripes_per_chunk, n_gblocks, c->n_stripes, c->sm_count);
     int n_schunks = (int)((c->n_stripes + spc - 1) / spc);
     int grid = std::min(n_gblocks * n_schunks, c->sm_count);
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(c->bed, c->tab_u, c->Mg_pad, c->n_stripes, n_gblocks, n_schunks, spc, c->work_counter, acc, 1);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(c->bed, tab, c->Mg_pad, c->n_stripes, n_gblocks, n_schunks, spc, c->work_counter, acc, 1);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }
 
-}   // namespace
 
-// main kernel of X.v: accN[i] += sum over local markers of the table values (c->tab_v built by the caller)
-int gvb_ax_tile_main(gvb_ctx* c, unsigned long long* accN) {
+// ===================================================================================================
+//  pre- and post-kernels of a sweep (fixed-point scales, lookup tables, conversion back to FP64)
+// ===================================================================================================
+// scal[] layout (device doubles): [0] scale of X^T.u, [1] its inverse, [2] scale of X.v, [3] its inverse,
+// [8] / [9]: running maxima (bit patterns of non-negative doubles, ordered like unsigned integers) of the X^T.u / X.v
+// magnitude bounds; the finish kernel of a sweep re-arms its maximum to 0 for the next sweep.
+#define SCAL_ATX_BOUND 8
+#define SCAL_AX_BOUND 9
+
+// power-of-two scale such that `window` table entries of magnitude <= bound * scale (+ slack) cannot overflow an int32
+__device__ __forceinline__ double scale_for(double bound, double window, double slack) {
+    double s = 1.0;
+    if (bound > 0.0 && isfinite(bound)) {
+        double limit = (2147483647.0 / window - slack) / bound;
+        int e;
+        frexp(limit, &e);   // limit = f * 2^e, f in [0.5, 1)  ->  2^(e-1) <= limit
+        e = max(-1000, min(1000, e - 1));
+        s = ldexp(1.0, e);
+    }
+    return s;
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+__device__ __forceinline__ int dosage_of(unsigned code) { return code == 0u ? 2 : (code == 2u ? 1 : 0); }
+
+// ---- X . v ----------------------------------------------------------------------------------------
+// pass 1 (one block per marker tile of 128): bound = max over tiles of sum_j max_c |val_j(c)|, the largest |table entry
+// sum| a 32-lookup window can see; also clears the int64 accumulators of the individuals
+__global__ void __launch_bounds__(128) ax_prep_kernel(const double* __restrict__ v, const double* __restrict__ mave, const double* __restrict__ msig,
+                                                      double* __restrict__ scal, unsigned long long* __restrict__ accN, long Npad) {
+    const long j = blockIdx.x * 128l + threadIdx.x;
+    const double w = msig[j] * v[j], mu = mave[j];
+    double e = fmax(fmax(fabs((2.0 - mu) * w), fabs(mu * w)), fabs((1.0 - mu) * w));
+    __shared__ double sm[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) atomic_max_nonneg(scal + SCAL_AX_BOUND, sm[0] + sm[1] + sm[2] + sm[3]);
+    for (long i = j; i < Npad; i += (long)gridDim.x * 128) accN[i] = 0ull;
+}
+
+// pass 2 (one block per marker tile): tabv[(T*256 + e)*32 + s] = sum_q Q_{4g+q}(c_q(e)), g = 32 T + s,
+// Q_j(c) = rint(val_j(c) * scale), val_j(00) = (2-mu) w, val_j(10) = (1-mu) w, val_j(11) = -mu w, val_j(missing) = 0
+__global__ void __launch_bounds__(256) ax_build_kernel(const double* __restrict__ v, const double* __restrict__ mave, const double* __restrict__ msig,
+                                                       double* __restrict__ scal, int* __restrict__ tabv) {
+    __shared__ int Qs[4][4][32];   // [q][code][slot]: a warp reads one (q, code) row -> conflict free
+    __shared__ double s_scale;
+    const long T = blockIdx.x;
+    if (threadIdx.x == 0) {
+        const double sc = scale_for(scal[SCAL_AX_BOUND], 1.0, 64.0 + 1.0);
+        s_scale = sc;
+        if (T == 0) {
+            scal[2] = sc;
+            scal[3] = 1.0 / sc;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const long j = T * 128 + threadIdx.x;
+        const int s = threadIdx.x >> 2, q = threadIdx.x & 3;
+        const double w = msig[j] * v[j], mu = mave[j], sc = s_scale;
+        Qs[q][0][s] = (int)rint((2.0 - mu) * w * sc);
+        Qs[q][1][s] = 0;
+        Qs[q][2][s] = (int)rint((1.0 - mu) * w * sc);
+        Qs[q][3][s] = (int)rint(-mu * w * sc);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int* dst = tabv + T * 8192 + lane;
+#pragma unroll 4
+    for (int e = warp; e < 256; e += 8)
+        dst[e * 32] = Qs[0][e & 3][lane] + Qs[1][(e >> 2) & 3][lane] + Qs[2][(e >> 4) & 3][lane] + Qs[3][e >> 6][lane];
+}
+
+// out[i] = present_i ? acc_i / scale / sqrt(N) : 0   (the mask m_i of data.cpp:972; pads are never present)
+__global__ void ax_finish_kernel(const unsigned long long* __restrict__ acc, double* __restrict__ scal, const uint32_t* __restrict__ maskw, long Npad,
+                                 double inv_sqrt_n, double* __restrict__ out) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i == 0) scal[SCAL_AX_BOUND] = 0.0;
+    if (i >= Npad) return;
+    bool present = (maskw[i >> 2] >> (2 * (i & 3))) & 1u;
+    out[i] = present ? (double)(long long)acc[i] * scal[3] * inv_sqrt_n : 0.0;
+}
+
+// ---- X^T . u --------------------------------------------------------------------------------------
+// pass 1: bound = max over byte positions p of 2 (|u_4p| + ... + |u_4p+3|), the largest |table entry| / scale; clears
+// the accumulators of the markers and the running sum of U
+__global__ void __launch_bounds__(256) atx_prep_kernel(const double* __restrict__ u, long npos, double* __restrict__ scal,
+                                                       unsigned long long* __restrict__ acc, long nacc, long long* __restrict__ usum) {
+    double m = 0.0;
+    const long tid = blockIdx.x * (long)blockDim.x + threadIdx.x, nth = (long)gridDim.x * blockDim.x;
+    for (long p = tid; p < npos; p += nth) {
+        const double2* up = reinterpret_cast<const double2*>(u + 4 * p);
+        double2 a = up[0], b = up[1];
+        m = fmax(m, 2.0 * (fabs(a.x) + fabs(a.y) + fabs(b.x) + fabs(b.y)));
+    }
+    for (long i = tid; i < nacc; i += nth) acc[i] = 0ull;
+    if (tid == 0) *usum = 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomic_max_nonneg(scal + SCAL_ATX_BOUND, m);
+}
+
+// pass 2 (one block per stripe): tab[(t*256 + B)*32 + l] = sum_k a(code_k(B)) U_{4p+k}, p = 32 t + l, U = rint(u * scale);
+// tabm (shards with missing genotypes) holds the same sum over the MISSING codes with weight 1; accumulates sum_i U_i
+__global__ void __launch_bounds__(256) atx_build_kernel(const double* __restrict__ u, double window, double* __restrict__ scal, int* __restrict__ tab,
+                                                        int* __restrict__ tabm, long long* __restrict__ usum) {
+    __shared__ int Us[4][32];   // [k][position]
+    __shared__ double s_scale;
+    const long t = blockIdx.x;
+    if (threadIdx.x == 0) {
+        const double sc = scale_for(scal[SCAL_ATX_BOUND], window, 4.0);
+        s_scale = sc;
+        if (t == 0) {
+            scal[0] = sc;
+            scal[1] = 1.0 / sc;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int Ui = (int)rint(u[t * 128 + threadIdx.x] * s_scale);
+        Us[threadIdx.x & 3][threadIdx.x >> 2] = Ui;
+        long long ls = Ui;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
+        if ((threadIdx.x & 31) == 0 && ls != 0) atomicAdd(reinterpret_cast<unsigned long long*>(usum), (unsigned long long)ls);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int U0 = Us[0][lane], U1 = Us[1][lane], U2 = Us[2][lane], U3 = Us[3][lane];
+    int* dst = tab + t * 8192 + lane;
+    int* dstm = tabm ? tabm + t * 8192 + lane : nullptr;
+#pragma unroll 4
+    for (int B = warp; B < 256; B += 8) {
+        const unsigned c0 = B & 3, c1 = (B >> 2) & 3, c2 = (B >> 4) & 3, c3 = B >> 6;
+        dst[B * 32] = dosage_of(c0) * U0 + dosage_of(c1) * U1 + dosage_of(c2) * U2 + dosage_of(c3) * U3;
+        if (dstm) dstm[B * 32] = (c0 == 1u ? U0 : 0) + (c1 == 1u ? U1 : 0) + (c2 == 1u ? U2 : 0) + (c3 == 1u ? U3 : 0);
+    }
+}
+
+// out[j] = sigma_j * (A_j - mu_j * B_j) / scale / sqrt(N),  B_j = sum_i U_i - sum_{i missing in j} U_i
+__global__ void atx_finish_kernel(const unsigned long long* __restrict__ acc, const unsigned long long* __restrict__ accm, const long long* __restrict__ usum,
+                                  double* __restrict__ scal, const double* __restrict__ mave, const double* __restrict__ msig, long Mpad,
+                                  double inv_sqrt_n, double* __restrict__ out) {
+    long j = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (j == 0) scal[SCAL_ATX_BOUND] = 0.0;
+    if (j >= Mpad) return;
+    long long A = (long long)acc[j];
+    long long Bs = *usum - (accm ? (long long)accm[j] : 0ll);
+    double inv_s = scal[1];
+    out[j] = msig[j] * ((double)A * inv_s - mave[j] * ((double)Bs * inv_s)) * inv_sqrt_n;
+}
+
+int ensure_scratch(gvb_ctx* c, bool need_tab_u, bool need_tab_v, bool miss) {
+    if (need_tab_u) {
+        const size_t tab_ints = (size_t)c->n_stripes * 8192 * (miss ? 2 : 1);
+        if (c->tab_u_cap < tab_ints) {
+            if (c->tab_u) cudaFree(c->tab_u);
+            c->tab_u = nullptr;
+            GVB_CUDA(cudaMalloc(&c->tab_u, tab_ints * sizeof(int)));
+            c->tab_u_cap = tab_ints;
+        }
+    }
+    if (need_tab_v) {
+        const size_t tab_ints = (size_t)(c->Mg_pad / 32) * 8192;
+        if (c->tab_v_cap < tab_ints) {
+            if (c->tab_v) cudaFree(c->tab_v);
+            c->tab_v = nullptr;
+            GVB_CUDA(cudaMalloc(&c->tab_v, tab_ints * sizeof(int)));
+            c->tab_v_cap = tab_ints;
+        }
+    }
+    const size_t acc_need = 2 * (size_t)c->Mg_pad * 4 + (size_t)c->Npad + 8;
+    if (c->acc_i64_cap < acc_need) {
+        if (c->acc_i64) cudaFree(c->acc_i64);
+        c->acc_i64 = nullptr;
+        GVB_CUDA(cudaMalloc(&c->acc_i64, acc_need * sizeof(unsigned long long)));
+        c->acc_i64_cap = acc_need;
+    }
+    return GVB_OK;
+}
+
+int ax_main(gvb_ctx* c, unsigned long long* accN) {
     const TileTune t = tune();
     if (t.variant == 1) return t.use_mad ? launch_ax<12, 3, true>(c, accN) : launch_ax<12, 3, false>(c, accN);
     return t.use_mad ? launch_ax<16, 2, true>(c, accN) : launch_ax<16, 2, false>(c, accN);
 }
 
-// main kernel of X^T.u for shards without missing genotypes: acc[j] += sum_i a_ij U_i (c->tab_u built by the caller)
-int gvb_atx_tile_main(gvb_ctx* c, unsigned long long* acc) {
+int atx_main(gvb_ctx* c, const int* tab, unsigned long long* acc) {
     const TileTune t = tune();
-    if (t.variant == 1) return t.use_mad ? launch_atx<12, 3, true>(c, acc) : launch_atx<12, 3, false>(c, acc);
-    return t.use_mad ? launch_atx<16, 2, true>(c, acc) : launch_atx<16, 2, false>(c, acc);
+    if (t.variant == 1) return t.use_mad ? launch_atx<12, 3, true, 0>(c, tab, acc) : launch_atx<12, 3, false, 0>(c, tab, acc);
+    return t.use_mad ? launch_atx<16, 2, true, 0>(c, tab, acc) : launch_atx<16, 2, false, 0>(c, tab, acc);
 }
 
-// int32 accumulation window of atx_tile_kernel in table entries (one stripe: 32 positions)
-int gvb_atx_tile_window() { return 32; }
+}   // namespace
+
+// X . v of the local shard (reference data::Ax, data.cpp:848-1011, before its MPI_Allreduce): 4 launches
+int gvb_ax_tile(gvb_ctx* c, const double* v, double* out) {
+    GVB_CHECK(ensure_scratch(c, false, true, false));
+    const long n_tiles = c->Mg_pad / 32;
+    unsigned long long* accN = c->acc_i64 + 2 * (size_t)c->Mg_pad * 4;
+    ax_prep_kernel<<<(unsigned)n_tiles, 128, 0, c->stream>>>(v, c->mave, c->msig, c->scal, accN, c->Npad);
+    GVB_LAUNCHED(c);
+    ax_build_kernel<<<(unsigned)n_tiles, 256, 0, c->stream>>>(v, c->mave, c->msig, c->scal, c->tab_v);
+    GVB_LAUNCHED(c);
+    GVB_CHECK(ax_main(c, accN));
+    ax_finish_kernel<<<(unsigned)((c->Npad + 255) / 256), 256, 0, c->stream>>>(accN, c->scal, c->maskw, c->Npad, 1.0 / sqrt((double)c->N), out);
+    GVB_LAUNCHED(c);
+    return GVB_OK;
+}
+
+// X^T . u of the local shard (reference dot_product + ATx, data.cpp:728-835): 4 launches, 5 for shards with missing
+// genotypes (a second walk with the table of the missing codes gives sum_{i missing in j} U_i)
+int gvb_atx_tile(gvb_ctx* c, const double* u, double* out) {
+    const bool miss = c->total_missing > 0;
+    GVB_CHECK(ensure_scratch(c, true, false, miss));
+    const size_t Mpad = (size_t)c->Mg_pad * 4;
+    const long npos = c->n_stripes * 32, total = c->n_stripes * 8192;
+    unsigned long long* acc = c->acc_i64;
+    unsigned long long* accm = c->acc_i64 + Mpad;
+    long long* usum = reinterpret_cast<long long*>(c->acc_i64 + 2 * Mpad + c->Npad);
+    int nb = (int)std::max(1l, std::min((npos + 255) / 256, 2l * c->sm_count));
+    atx_prep_kernel<<<nb, 256, 0, c->stream>>>(u, npos, c->scal, acc, (long)((miss ? 2 : 1) * Mpad), usum);
+    GVB_LAUNCHED(c);
+    atx_build_kernel<<<(unsigned)c->n_stripes, 256, 0, c->stream>>>(u, 32.0, c->scal, c->tab_u, miss ? c->tab_u + total : nullptr, usum);
+    GVB_LAUNCHED(c);
+    GVB_CHECK(atx_main(c, c->tab_u, acc));
+    if (miss) GVB_CHECK(atx_main(c, c->tab_u + total, accm));
+    atx_finish_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, c->stream>>>(acc, miss ? accm : nullptr, usum, c->scal, c->mave, c->msig, (long)Mpad,
+                                                                             1.0 / sqrt((double)c->N), out);
+    GVB_LAUNCHED(c);
+    return GVB_OK;
+}
+
+// the table walk of X^T.u with packed counters (MODE 1): acc[j] = n00 | n10 << 21 | n11 << 42 over the individuals the table weights
+int gvb_count_tile_main(gvb_ctx* c, const int* tab, unsigned long long* acc) {
+    const TileTune t = tune();
+    if (t.variant == 1) return launch_atx<12, 3, false, 1>(c, tab, acc);
+    return launch_atx<16, 2, false, 1>(c, tab, acc);
+}

@@ -53,6 +53,72 @@ __global__ void __launch_bounds__(256) counts_kernel(const uint32_t* __restrict_
         }
 }
 
+// ---- gen 2: the counts as a table walk (matvec_tile.cu, MODE 1) -------------------------------------------------
+// tab[(t*256 + B)*32 + l] = sum over the individuals k of position p = 32t+l that the weight word selects of
+// 1 << (10 * class(code_k(B))), class 00 -> 0, 10 -> 1, 11 -> 2; the missing code adds nothing (n01 follows from the total)
+__global__ void __launch_bounds__(256) count_table_kernel(const uint32_t* __restrict__ weightw, long n_stripes, int* __restrict__ tab) {
+    long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (idx >= n_stripes * 8192) return;
+    int l = (int)(idx & 31);
+    unsigned B = (unsigned)((idx >> 5) & 255);
+    long t = idx >> 13;
+    uint32_t mw = weightw[t * 32 + l];
+    int e = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        unsigned code = (B >> (2 * k)) & 3u;
+        bool present = (mw >> (2 * k)) & 1u;
+        if (present && code != 1u) e += 1 << (10 * (code == 0u ? 0 : (code == 2u ? 1 : 2)));
+    }
+    tab[idx] = e;
+}
+
+// packed n00 | n10 << 21 | n11 << 42 -> counts[j*8 + base + {0,1,2,3}] = n00, n01, n10, n11 (n01 = total - the rest)
+__global__ void unpack_counts_kernel(const unsigned long long* __restrict__ packed, long Mpad, long total, int base, bool also_other,
+                                     int64_t* __restrict__ counts) {
+    long j = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (j >= Mpad) return;
+    unsigned long long p = packed[j];
+    long n00 = (long)(p & 0x1FFFFFull), n10 = (long)((p >> 21) & 0x1FFFFFull), n11 = (long)(p >> 42);
+    long n01 = total - n00 - n10 - n11;
+    for (int b = base; b <= (also_other ? 4 : base); b += 4) {
+        counts[j * 8 + b + 0] = n00;
+        counts[j * 8 + b + 1] = n01;
+        counts[j * 8 + b + 2] = n10;
+        counts[j * 8 + b + 3] = n11;
+    }
+}
+
+static int counts_tile_run(gvb_ctx* c) {
+    const size_t tab_ints = (size_t)c->n_stripes * 8192;
+    if (c->tab_u_cap < tab_ints) {
+        if (c->tab_u) cudaFree(c->tab_u);
+        c->tab_u = nullptr;
+        GVB_CUDA(cudaMalloc(&c->tab_u, tab_ints * sizeof(int)));
+        c->tab_u_cap = tab_ints;
+    }
+    const size_t Mpad = (size_t)c->Mg_pad * 4;
+    const size_t acc_need = 2 * Mpad + (size_t)c->Npad + 8;
+    if (c->acc_i64_cap < acc_need) {
+        if (c->acc_i64) cudaFree(c->acc_i64);
+        c->acc_i64 = nullptr;
+        GVB_CUDA(cudaMalloc(&c->acc_i64, acc_need * sizeof(unsigned long long)));
+        c->acc_i64_cap = acc_need;
+    }
+    // no phenotype NAs: the masked and the unmasked counts coincide and one walk serves both
+    const bool same = c->mask_present == c->N;
+    for (int pass = 0; pass < (same ? 1 : 2); pass++) {
+        GVB_CUDA(cudaMemsetAsync(c->acc_i64, 0, Mpad * sizeof(unsigned long long), c->stream));
+        count_table_kernel<<<(unsigned)((tab_ints + 255) / 256), 256, 0, c->stream>>>(pass == 0 ? c->maskw : c->validw, c->n_stripes, c->tab_u);
+        GVB_LAUNCHED(c);
+        GVB_CHECK(gvb_count_tile_main(c, c->tab_u, c->acc_i64));
+        unpack_counts_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, c->stream>>>(c->acc_i64, (long)Mpad, pass == 0 ? c->mask_present : c->N, pass == 0 ? 0 : 4,
+                                                                                     same, c->counts);
+        GVB_LAUNCHED(c);
+    }
+    return GVB_OK;
+}
+
 __global__ void stats_from_counts_kernel(const int64_t* __restrict__ counts, long M, long Mpad, int nonas, double alpha_scale,
                                          double* __restrict__ mave, double* __restrict__ msig, unsigned long long* __restrict__ total_missing) {
     long j = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -84,8 +150,12 @@ int gvb_stats_run(gvb_ctx* c) {
     int warps = 8;
     long blocks = (c->Mg + warps - 1) / warps;
     GVB_CUDA(cudaMemsetAsync(c->counts, 0, (size_t)c->Mg_pad * 4 * 8 * sizeof(int64_t), c->stream));
-    counts_kernel<<<(unsigned)blocks, warps * 32, 0, c->stream>>>(c->bed, c->maskw, c->validw, c->Mg, c->Mg_pad, c->n_stripes, c->counts);
-    GVB_LAUNCHED(c);
+    if (c->kernel_gen >= 2 && c->N < (1l << 21)) {   // 21-bit packed counters
+        GVB_CHECK(counts_tile_run(c));
+    } else {
+        counts_kernel<<<(unsigned)blocks, warps * 32, 0, c->stream>>>(c->bed, c->maskw, c->validw, c->Mg, c->Mg_pad, c->n_stripes, c->counts);
+        GVB_LAUNCHED(c);
+    }
     unsigned long long* d_miss = (unsigned long long*)c->scal;
     GVB_CUDA(cudaMemsetAsync(d_miss, 0, sizeof(unsigned long long), c->stream));
     long Mpad = c->Mg_pad * 4;

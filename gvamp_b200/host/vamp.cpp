@@ -96,7 +96,7 @@ void vamp::dev_open(data* dataset) {
     if (dev.ctx == dataset->device() && dev.r1) return;
     dev_close();
     dev.ctx = dataset->device();
-    gvb_vec* mvecs[] = {&dev.r1, &dev.r2, &dev.r2_prev, &dev.x1, &dev.x1_prev, &dev.x2, &dev.mu_last, &dev.rhs, &dev.bern, &dev.invq, &dev.tmpM, &dev.truth};
+    gvb_vec* mvecs[] = {&dev.r1, &dev.r2, &dev.r2_prev, &dev.x1, &dev.x1_prev, &dev.x2, &dev.mu_last, &dev.rhs, &dev.bern, &dev.invq, &dev.tmpM, &dev.truth, &dev.aty};
     for (gvb_vec* v : mvecs) DEV(gvb_vec_alloc_M(dev.ctx, v));
     gvb_vec* nvecs[] = {&dev.y, &dev.z1, &dev.tmpN, &dev.tmpN2};
     for (gvb_vec* v : nvecs) DEV(gvb_vec_alloc_N(dev.ctx, v));
@@ -105,7 +105,7 @@ void vamp::dev_open(data* dataset) {
 
 void vamp::dev_close() {
     if (!dev.ctx) return;
-    gvb_vec all[] = {dev.r1, dev.r2, dev.r2_prev, dev.x1, dev.x1_prev, dev.x2, dev.mu_last, dev.rhs, dev.bern, dev.invq, dev.tmpM, dev.truth,
+    gvb_vec all[] = {dev.r1, dev.r2, dev.r2_prev, dev.x1, dev.x1_prev, dev.x2, dev.mu_last, dev.rhs, dev.bern, dev.invq, dev.tmpM, dev.truth, dev.aty,
                      dev.y, dev.z1, dev.tmpN, dev.tmpN2, dev.p1, dev.p2, dev.z1h, dev.z2h, dev.mcov, dev.p1_prev};
     for (gvb_vec v : all)
         if (v) gvb_vec_free(dev.ctx, v);
@@ -196,7 +196,10 @@ std::vector<double> vamp::infere_linear(data* dataset) {
 }
 
 void vamp::upload_iteration_inputs(const double* y_host, const double* r1_host) {
-    if (y_host) DEV(gvb_vec_upload(dev.ctx, dev.y, y_host, N));
+    if (y_host) {
+        DEV(gvb_vec_upload(dev.ctx, dev.y, y_host, N));
+        dev.aty_valid = false;
+    }
     if (r1_host) DEV(gvb_vec_upload(dev.ctx, dev.r1, r1_host, M));
 }
 
@@ -211,6 +214,7 @@ void vamp::linear_begin(data* dataset) {
     yf.resize(N, 0.0);
     DEV(gvb_vec_fill(ctx, dev.y, 0.0));
     DEV(gvb_vec_upload(ctx, dev.y, yf.data(), N));
+    dev.aty_valid = false;
     DEV(gvb_vec_fill(ctx, dev.r1, 0.0));
     DEV(gvb_vec_fill(ctx, dev.x1, 0.0));
     DEV(gvb_vec_fill(ctx, dev.r2, 0.0));
@@ -337,8 +341,11 @@ bool vamp::linear_iteration(data* dataset, int it) {
 
         double start_CG = wtime();
         // v = gamw * A^T y + gam2 * r2
-        DEV(gvb_dATx(ctx, dev.y, dev.tmpM));
-        DEV(gvb_vec_axpby(ctx, dev.rhs, gamw, dev.tmpM, gam2, dev.r2));
+        if (!dev.aty_valid) {
+            DEV(gvb_dATx(ctx, dev.y, dev.aty));
+            dev.aty_valid = true;
+        }
+        DEV(gvb_vec_axpby(ctx, dev.rhs, gamw, dev.aty, gam2, dev.r2));
         if (it == 1)
             DEV(gvb_vec_fill(ctx, dev.x2, 0.0));
         else

@@ -79,6 +79,8 @@ private:
         gvb_vec y = nullptr, z1 = nullptr, tmpN = nullptr, tmpN2 = nullptr;
         gvb_vec p1 = nullptr, p2 = nullptr, z1h = nullptr, z2h = nullptr, mcov = nullptr, p1_prev = nullptr;
         bool ax_x2_valid = false;   // tmpN2 holds Ax(x2) of the current iteration
+        gvb_vec aty = nullptr;      // A^T y: y is constant over the linear model's iterations, so the reference's per-iteration
+        bool aty_valid = false;     // sweep (vamp.cpp:588) is done once and reused until y is uploaded again
     } dev;
     void dev_open(data* dataset);
     void dev_close();

@@ -17,7 +17,13 @@ ap.add_argument("--miss", type=float, default=0.0)
 a = ap.parse_args()
 ctx = capi.Context(0)
 ctx.synth(1, a.N, a.M, 0, a.M, a.miss)
-ctx.compute_stats(1.0)
+import time  # noqa: E402
+for _ in range(2):
+    ctx.sync()
+    t0 = time.perf_counter()
+    ctx.compute_stats(1.0)
+    dt = time.perf_counter() - t0
+print(f"compute_stats: {dt * 1e3:.3f} ms = {a.M * ((a.N + 3) // 4) / dt / 1e9:.0f} GB/s (host wall clock, includes the final sync)")
 rng = np.random.default_rng(0)
 v, u = ctx.vecM(rng.normal(size=a.M)), ctx.vecN(rng.normal(size=a.N))
 ov, ou = ctx.vecN(), ctx.vecM()

@@ -74,6 +74,7 @@ SIGNATURES = {
     "gvb_lmmse_mult": (ci, [vp, vp, cd, cd, vp]),
     "gvb_cg_solve": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p]),
     "gvb_probit_denoise": (ci, [vp, vp, vp, vp, cd, cd, vp, c_f64p]),
+    "gvb_missing_list_entries": (cl, [vp]),
 }
 
 _LIB = None
@@ -350,3 +351,6 @@ class Context:
 
     def sweeps(self) -> int:
         return self.L.gvb_sweep_count(self.h)
+
+    def missing_list_entries(self) -> int:
+        return self.L.gvb_missing_list_entries(self.h)

@@ -4,6 +4,7 @@
 #include <nccl.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <string>
 #include <vector>
@@ -65,6 +66,12 @@ struct gvb_ctx {
     double* msig = nullptr;   // padded markers: 0 (so they contribute nothing)
     int64_t* counts = nullptr;
     long total_missing = 0;   // sum over local markers of missing genotypes (i < N)
+    // sparse list of the missing genotypes (misslist.cu): the X^T.u correction sum_{i missing in j} U_i as a gather
+    uint16_t* miss_idx = nullptr;             // 16-bit indices into a 32768-individual block, segments padded to groups of 4
+    unsigned long long* miss_off = nullptr;   // [miss_nblk * Mg_pad*4 + 1] segment offsets in groups, block-major / marker-minor
+    int* uq = nullptr;                        // quantised u of the running X^T.u sweep (Npad)
+    long miss_nblk = 0, miss_entries = 0;
+    int miss_state = 0;                       // 0: not built yet, 1: built, -1: not available (X^T.u walks the bed a second time)
     double alpha_scale = 1.0;
 
     // scratch
@@ -159,6 +166,9 @@ int gvb_atx_lut(gvb_ctx* c, const double* u, double* out);
 int gvb_ax_tile(gvb_ctx* c, const double* v, double* out);     // gen-2 sweeps (matvec_tile.cu)
 int gvb_atx_tile(gvb_ctx* c, const double* u, double* out);
 int gvb_count_tile_main(gvb_ctx* c, const int* tab, unsigned long long* acc);
+void gvb_misslist_reset(gvb_ctx* c);                                   // misslist.cu
+int gvb_misslist_build(gvb_ctx* c);
+int gvb_misslist_sum(gvb_ctx* c, unsigned long long* accm);
 int gvb_ax_dev(gvb_ctx* c, const double* v, double* out, bool allreduce);
 int gvb_atx_dev(gvb_ctx* c, const double* u, double* out);
 

@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(256) atx_prep_kernel(const double* __restrict_
 // pass 2 (one block per stripe): tab[(t*256 + B)*32 + l] = sum_k a(code_k(B)) U_{4p+k}, p = 32 t + l, U = rint(u * scale);
 // tabm (shards with missing genotypes) holds the same sum over the MISSING codes with weight 1; accumulates sum_i U_i
 __global__ void __launch_bounds__(256) atx_build_kernel(const double* __restrict__ u, double window, double* __restrict__ scal, int* __restrict__ tab,
-                                                        int* __restrict__ tabm, long long* __restrict__ usum) {
+                                                        int* __restrict__ tabm, long long* __restrict__ usum, int* __restrict__ uq) {
     __shared__ int Us[4][32];   // [k][position]
     __shared__ double s_scale;
     const long t = blockIdx.x;
@@ -560,6 +560,7 @@ __global__ void __launch_bounds__(256) atx_build_kernel(const double* __restrict
     if (threadIdx.x < 128) {
         const int Ui = (int)rint(u[t * 128 + threadIdx.x] * s_scale);
         Us[threadIdx.x & 3][threadIdx.x >> 2] = Ui;
+        if (uq) uq[t * 128 + threadIdx.x] = Ui;   // the gather of misslist.cu reads the same integers
         long long ls = Ui;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
@@ -650,10 +651,13 @@ int gvb_ax_tile(gvb_ctx* c, const double* v, double* out) {
 }
 
 // X^T . u of the local shard (reference dot_product + ATx, data.cpp:728-835): 4 launches, 5 for shards with missing
-// genotypes (a second walk with the table of the missing codes gives sum_{i missing in j} U_i)
+// genotypes: sum_{i missing in j} U_i comes from the sparse list of misslist.cu (a gather over 2 bytes per missing
+// genotype), or, when that list cannot be held in HBM, from a second walk with the table of the missing codes
 int gvb_atx_tile(gvb_ctx* c, const double* u, double* out) {
     const bool miss = c->total_missing > 0;
-    GVB_CHECK(ensure_scratch(c, true, false, miss));
+    if (miss && c->miss_state == 0) GVB_CHECK(gvb_misslist_build(c));
+    const bool list = miss && c->miss_state == 1;
+    GVB_CHECK(ensure_scratch(c, true, false, miss && !list));
     const size_t Mpad = (size_t)c->Mg_pad * 4;
     const long npos = c->n_stripes * 32, total = c->n_stripes * 8192;
     unsigned long long* acc = c->acc_i64;
@@ -662,10 +666,14 @@ int gvb_atx_tile(gvb_ctx* c, const double* u, double* out) {
     int nb = (int)std::max(1l, std::min((npos + 255) / 256, 2l * c->sm_count));
     atx_prep_kernel<<<nb, 256, 0, c->stream>>>(u, npos, c->scal, acc, (long)((miss ? 2 : 1) * Mpad), usum);
     GVB_LAUNCHED(c);
-    atx_build_kernel<<<(unsigned)c->n_stripes, 256, 0, c->stream>>>(u, 32.0, c->scal, c->tab_u, miss ? c->tab_u + total : nullptr, usum);
+    atx_build_kernel<<<(unsigned)c->n_stripes, 256, 0, c->stream>>>(u, 32.0, c->scal, c->tab_u, (miss && !list) ? c->tab_u + total : nullptr, usum,
+                                                                    list ? c->uq : nullptr);
     GVB_LAUNCHED(c);
     GVB_CHECK(atx_main(c, c->tab_u, acc));
-    if (miss) GVB_CHECK(atx_main(c, c->tab_u + total, accm));
+    if (list)
+        GVB_CHECK(gvb_misslist_sum(c, accm));
+    else if (miss)
+        GVB_CHECK(atx_main(c, c->tab_u + total, accm));
     atx_finish_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, c->stream>>>(acc, miss ? accm : nullptr, usum, c->scal, c->mave, c->msig, (long)Mpad,
                                                                              1.0 / sqrt((double)c->N), out);
     GVB_LAUNCHED(c);

@@ -101,6 +101,12 @@ int gvb_get_stats(gvb_ctx* ctx, double* mave, double* msig);   /* data::get_mave
 /* counts[j*8+c]: individuals with code c and phenotype present; counts[j*8+4+c]: all i<N */
 int gvb_get_counts(gvb_ctx* ctx, int64_t* counts);
 
+/* entries (16-bit indices, padding included) of the sparse list of missing genotypes that X^T.u uses for the na_lut
+ * term of data::dot_product (data.cpp:766) on shards with missing genotypes; 0 when the shard has none, the list is
+ * not built yet (it is built by the first X^T.u after gvb_compute_stats) or X^T.u walks the bed a second time instead
+ * (list larger than half the bed / out of memory / env GVB_MISS=twopass). */
+long gvb_missing_list_entries(gvb_ctx* ctx);
+
 /* ---- X.v and X^T.u, host-pointer drop-in --------------------------------------------------------- */
 /* data::Ax(double* v, SB, LB), data.cpp:848-1011 incl. the MPI_Allreduce at :995.
  * v: M local entries; out: 4*LB entries.  COLLECTIVE when nranks>1. */

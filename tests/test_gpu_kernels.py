@@ -178,6 +178,26 @@ def test_tile_kernels_reproducible_across_chunking(C, oracle, monkeypatch):
         assert np.array_equal(ax, res[0][0]) and np.array_equal(atx, res[0][1])
 
 
+@pytest.mark.parametrize("N,M,miss", [(70_001, 301, 0.02), (33_000, 130, 0.001), (2500, 333, 0.05)])
+def test_missing_list_equals_second_walk(C, oracle, N, M, miss, monkeypatch):
+    """X^T.u on a shard with missing genotypes: the sparse missing-genotype list (misslist.cu; several 32768-individual
+    blocks, M % 4 != 0, padded segments) and the second table walk are two integer evaluations of the same sums, so
+    they must agree BIT FOR BIT; both are within the mat-vec tolerance of the oracle."""
+    bed = oracle.synth_bed(31, 0, M, N, miss_rate=miss)
+    ds = oracle.Dataset(bed, N)
+    u = np.random.default_rng(3).normal(size=N)
+    res = {}
+    for mode in ("list", "twopass"):
+        monkeypatch.setenv("GVB_MISS", mode)
+        with make_ctx(C, "lut") as ctx:
+            ctx.load_host(bed, N).compute_stats(1.0)
+            res[mode] = (ctx.ATx(u), ctx.ATx(u), ctx.missing_list_entries())
+    assert res["list"][2] > 0 and res["twopass"][2] == 0          # the list was really built / really bypassed
+    assert res["list"][2] % 4 == 0 and res["list"][2] >= ds.counts()[:, 5].sum()
+    assert np.array_equal(res["list"][0], res["twopass"][0]) and np.array_equal(res["list"][0], res["list"][1])
+    assert relerr(res["list"][0], ds.ATx(u)) < TOL_MATVEC
+
+
 def test_vector_ops(C, oracle):
     N, M = 512, 3001
     bed = oracle.synth_bed(1, 0, M, N)

@@ -430,6 +430,10 @@ def ours_arm(args):
     if world > 1:
         dist.destroy_process_group()
     if rank == 0:
+        keep = os.environ.get("GVB_BENCH_KEEP_LOG")     # the host layer's progress lines (per-phase wall times) of rank 0
+        if keep:
+            import shutil
+            shutil.copyfile(logf, keep)
         print(json.dumps(line))
     return 0
 

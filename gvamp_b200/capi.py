@@ -75,6 +75,7 @@ SIGNATURES = {
     "gvb_cg_solve": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p]),
     "gvb_probit_denoise": (ci, [vp, vp, vp, vp, cd, cd, vp, c_f64p]),
     "gvb_missing_list_entries": (cl, [vp]),
+    "gvb_assoc_pvals": (ci, [vp, vp, vp, vp, vp]),
 }
 
 _LIB = None
@@ -351,6 +352,9 @@ class Context:
 
     def sweeps(self) -> int:
         return self.L.gvb_sweep_count(self.h)
+
+    def assoc_pvals(self, yres, coef, select, pvals):
+        _chk(self.L.gvb_assoc_pvals(self.h, yres.h, coef.h if coef is not None else None, select.h if select is not None else None, pvals.h))
 
     def missing_list_entries(self) -> int:
         return self.L.gvb_missing_list_entries(self.h)

@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(256) atx_build_kernel(const double* __restrict
 // out[j] = sigma_j * (A_j - mu_j * B_j) / scale / sqrt(N),  B_j = sum_i U_i - sum_{i missing in j} U_i
 __global__ void atx_finish_kernel(const unsigned long long* __restrict__ acc, const unsigned long long* __restrict__ accm, const long long* __restrict__ usum,
                                   double* __restrict__ scal, const double* __restrict__ mave, const double* __restrict__ msig, long Mpad,
-                                  double inv_sqrt_n, double* __restrict__ out) {
+                                  double inv_sqrt_n, double* __restrict__ out, double* __restrict__ outB) {
     long j = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (j == 0) scal[SCAL_ATX_BOUND] = 0.0;
     if (j >= Mpad) return;
@@ -592,6 +592,7 @@ __global__ void atx_finish_kernel(const unsigned long long* __restrict__ acc, co
     long long Bs = *usum - (accm ? (long long)accm[j] : 0ll);
     double inv_s = scal[1];
     out[j] = msig[j] * ((double)A * inv_s - mave[j] * ((double)Bs * inv_s)) * inv_sqrt_n;
+    if (outB) outB[j] = (double)Bs * inv_s;   // sum_i b_ij u_i on its own (association tests, assoc.cu)
 }
 
 int ensure_scratch(gvb_ctx* c, bool need_tab_u, bool need_tab_v, bool miss) {
@@ -661,7 +662,7 @@ int gvb_ax_tile(gvb_ctx* c, const double* v, double* out) {
 // X^T . u of the local shard (reference dot_product + ATx, data.cpp:728-835): 4 launches, 5 for shards with missing
 // genotypes: sum_{i missing in j} U_i comes from the sparse list of misslist.cu (a gather over 2 bytes per missing
 // genotype), or, when that list cannot be held in HBM, from a second walk with the table of the missing codes
-int gvb_atx_tile(gvb_ctx* c, const double* u, double* out) {
+int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB) {
     const bool miss = c->total_missing > 0;
     if (miss && c->miss_state == 0) GVB_CHECK(gvb_misslist_build(c));
     const bool list = miss && c->miss_state == 1;
@@ -683,7 +684,7 @@ int gvb_atx_tile(gvb_ctx* c, const double* u, double* out) {
     else if (miss)
         GVB_CHECK(atx_main(c, c->tab_u + total, accm));
     atx_finish_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, c->stream>>>(acc, miss ? accm : nullptr, usum, c->scal, c->mave, c->msig, (long)Mpad,
-                                                                             1.0 / sqrt((double)c->N), out);
+                                                                             1.0 / sqrt((double)c->N), out, outB);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }

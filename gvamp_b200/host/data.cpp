@@ -254,3 +254,86 @@ std::vector<double> data::filter_pheno(int* nonnan) {
     }
     return y;
 }
+
+// ---- association tests ------------------------------------------------------------------------------
+// chromosome index of every local marker from column 1 of the .bim file, "X" -> 23 (data.cpp:346-380)
+std::vector<int> data::read_chromosome_info(std::string bim_file) {
+    std::vector<int> chroms;
+    std::ifstream infile(bim_file);
+    if (!infile.is_open()) {
+        std::cout << "FATAL: could not open bim file: " << bim_file << std::endl;
+        exit(EXIT_FAILURE);
+    }
+    std::string line;
+    for (int line_n = 0; std::getline(infile, line); line_n++) {
+        if (line_n < S || line_n >= S + M) continue;
+        std::istringstream fields(line);
+        std::string tok;
+        fields >> tok;
+        chroms.push_back(tok == "X" ? 23 : (int)atof(tok.c_str()));
+    }
+    return chroms;
+}
+
+namespace {
+struct DevVec {   // scoped device vector
+    gvb_ctx* ctx;
+    gvb_vec v = nullptr;
+    DevVec(gvb_ctx* c, bool n_vector) : ctx(c) {
+        if ((n_vector ? gvb_vec_alloc_N(c, &v) : gvb_vec_alloc_M(c, &v)) != GVB_OK) device_fatal("device vector allocation failed");
+    }
+    ~DevVec() { gvb_vec_free(ctx, v); }
+};
+}  // namespace
+
+// data::pvals_calc, data.cpp:1108-1180: leave-one-out t-test of every marker, y - z1 + x_k x1_hat_k regressed on x_k.
+// One call of the device association pass (two bed sweeps) per estimator.
+std::vector<std::vector<double>> data::pvals_calc(std::vector<std::vector<double>> z1, std::vector<double> y, std::vector<std::vector<double>> x1_hat,
+                                                  std::vector<std::string> filepath) {
+    const int nE = (int)z1.size();
+    std::vector<std::vector<double>> pvals(nE, std::vector<double>(M, 0.0));
+    DevVec yres(ctx, true), coef(ctx, false), pv(ctx, false);
+    for (int ie = 0; ie < nE; ie++) {
+        std::vector<double> ymod(4 * mbytes, 0.0);
+        for (int i = 0; i < N; i++) ymod[i] = y[i] - z1[ie][i];
+        if (gvb_vec_upload(ctx, yres.v, ymod.data(), (long)ymod.size()) != GVB_OK || gvb_vec_upload(ctx, coef.v, x1_hat[ie].data(), M) != GVB_OK ||
+            gvb_assoc_pvals(ctx, yres.v, coef.v, nullptr, pv.v) != GVB_OK || gvb_vec_download(ctx, pv.v, pvals[ie].data(), M) != GVB_OK)
+            device_fatal("LOO p-values failed");
+        if (rank == 0) std::cout << "so far worker 0 has calculated " << M << " pvals." << std::endl;
+        if (ie < (int)filepath.size()) mpi_store_vec_to_file(filepath[ie], pvals[ie], S, M);
+    }
+    return pvals;
+}
+
+// data::pvals_calc_LOCO, data.cpp:1220-1353: per chromosome, the predictor of the chromosome's own markers (all shards,
+// all-reduced inside Ax) is added back to y - z1 and the chromosome's markers are tested against it.
+std::vector<std::vector<double>> data::pvals_calc_LOCO(std::vector<std::vector<double>> z1, std::vector<double> y,
+                                                       std::vector<std::vector<double>> x1_hat, std::vector<std::string> filepath) {
+    const int nE = (int)z1.size();
+    std::vector<std::vector<double>> pvals(nE, std::vector<double>(M, 0.0));
+    std::vector<int> ch_info = read_chromosome_info(bimfp);
+    ch_info.resize(M, 0);
+    DevVec yres(ctx, true), sel(ctx, false), pv(ctx, false);
+    for (int ie = 0; ie < nE; ie++) {
+        if (gvb_vec_fill(ctx, pv.v, 0.0) != GVB_OK) device_fatal("LOCO p-values failed");
+        for (int ch = 1; ch <= 23; ch++) {
+            std::vector<double> xch(M, 0.0), select(M, 0.0);
+            for (int m = 0; m < M; m++)
+                if (ch_info[m] == ch) { xch[m] = x1_hat[ie][m]; select[m] = 1.0; }
+            std::vector<double> y_chrom = Ax(xch.data());   // collective: every rank walks all 23 chromosomes
+            for (size_t i = N; i < y_chrom.size(); i++) y_chrom[i] = 0.0;
+            std::string filepath_predictors = filepath[ie] + "_LOCO_chr_" + std::to_string(ch) + ".csv";
+            if (rank == 0) {
+                store_vec_to_file(filepath_predictors, y_chrom);
+                std::cout << "filepath predictors = " << filepath_predictors << std::endl;
+            }
+            for (int i = 0; i < N; i++) y_chrom[i] += y[i] - z1[ie][i];
+            if (gvb_vec_upload(ctx, yres.v, y_chrom.data(), (long)y_chrom.size()) != GVB_OK || gvb_vec_upload(ctx, sel.v, select.data(), M) != GVB_OK ||
+                gvb_assoc_pvals(ctx, yres.v, nullptr, sel.v, pv.v) != GVB_OK)
+                device_fatal("LOCO p-values failed");
+        }
+        if (gvb_vec_download(ctx, pv.v, pvals[ie].data(), M) != GVB_OK) device_fatal("LOCO p-values failed");
+        mpi_store_vec_to_file(filepath[ie] + "_pvals_LOCO.bin", pvals[ie], S, M);
+    }
+    return pvals;
+}

@@ -1,7 +1,7 @@
 // main_real.cpp -- driver for the linear model: the reference's main_real.exe command line
 // (main_real.cpp:13-599) on the B200 hot path.  Run modes built here: infere, test, both, restart,
-// predict_single.  pvals-calc and predict (Gibbs-sample prediction files) are post-processing outside
-// the hot path and report that instead of running.
+// predict_single, pvals-calc.  predict (Gibbs-sample prediction files) is post-processing outside the hot path
+//  and reports that instead of running.
 #include <cmath>
 #include <cstdlib>
 #include <iostream>
@@ -139,6 +139,47 @@ int run_predict_single(const Options& opt, int rank) {
     return 0;
 }
 
+// --run-mode pvals-calc (main_real.cpp:331-452): LOO (and, with a .bim file, LOCO) association p-values of one estimate
+// file or of an iteration range of estimate files; --store-pvals 0 = both, 1 = LOO only, 2 = LOCO only
+int run_pvals_calc(const Options& opt, int rank) {
+    const int N = opt.get_N();
+    Shard sh = shard_of(opt.get_Mt());
+    data dataset(opt.get_phen_files()[0], opt.get_bed_file(), N, sh.M, opt.get_Mt(), sh.S, rank, "bed", opt.get_alpha_scale(), opt.get_bim_file());
+    std::string est = opt.get_estimate_file();
+    std::string ext = est.substr(est.rfind(".") + 1);
+    std::vector<int> range = opt.get_test_iter_range();
+    if (rank == 0) std::cout << "iter range = [" << range[0] << ", " << range[1] << "]" << std::endl;
+    std::vector<std::vector<double>> z1_hats, x1_hats;
+    std::vector<std::string> out_loo, out_loco;
+    auto add = [&](const std::string& file, const std::string& stem) {
+        std::vector<double> x = ext == "bin" ? mpi_read_vec_from_file(file, sh.M, sh.S) : read_vec_from_file(file, sh.M, sh.S);
+        x.resize(sh.M, 0.0);
+        for (double& v : x) v *= sqrt((double)N);
+        z1_hats.push_back(dataset.Ax(x.data()));
+        x1_hats.push_back(x);
+        if (rank == 0) std::cout << "filepath_out_pvals = " << stem << std::endl << "filepath_out_pvals_LOCO = " << stem << std::endl;
+    };
+    if (range[0] != -1) {
+        size_t pos_it = est.rfind("it");
+        for (int it = range[0]; it <= range[1]; it++) {
+            std::string stem = opt.get_out_dir() + opt.get_out_name() + "_it_" + std::to_string(it);
+            add(est.substr(0, pos_it) + "it_" + std::to_string(it) + "." + ext, stem);
+            out_loo.push_back(stem + "_pvals.bin");
+            out_loco.push_back(stem + "_pvals_LOCO.bin");
+        }
+    } else {
+        if (rank == 0) std::cout << "end_est_file_name = " << ext << std::endl;
+        add(est, opt.get_out_dir() + opt.get_out_name());
+        out_loo.push_back(opt.get_out_dir() + opt.get_out_name() + "_pvals.bin");
+        out_loco.push_back(opt.get_out_dir() + opt.get_out_name() + "_pvals_LOCO.bin");
+    }
+    std::vector<double> y = dataset.filter_pheno();
+    const unsigned store_pvals = opt.get_store_pvals();
+    if (store_pvals == 0 || store_pvals == 1) dataset.pvals_calc(z1_hats, y, x1_hats, out_loo);
+    if (dataset.get_bimfp() != "" && (store_pvals == 0 || store_pvals == 2)) dataset.pvals_calc_LOCO(z1_hats, y, x1_hats, out_loco);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -151,7 +192,8 @@ int main(int argc, char** argv) {
     if (mode == "test") return run_test(opt, rank);
     if (mode == "both") return run_both(opt, rank);
     if (mode == "predict_single") return run_predict_single(opt, rank);
-    if (mode == "pvals-calc" || mode == "predict") {
+    if (mode == "pvals-calc") return run_pvals_calc(opt, rank);
+    if (mode == "predict") {
         if (rank == 0) std::cout << "run mode '" << mode << "' is post-processing outside the B200 hot path and is not built" << std::endl;
         return 2;
     }

@@ -192,6 +192,18 @@ std::vector<double> vamp::infere_linear(data* dataset) {
     linear_begin(dataset);
     for (int it = 1; it <= max_iter; it++)
         if (linear_iteration(dataset, it)) break;
+    if (store_pvals == 1) {   // association tests on the final estimate (vamp.cpp:761-777)
+        std::vector<double> yf = dataset->filter_pheno();
+        std::string filepath_out_pvals = out_dir + out_name + "_pvals.bin";
+        dataset->pvals_calc(std::vector<std::vector<double>>{z1}, yf, std::vector<std::vector<double>>{x1_hat}, std::vector<std::string>{filepath_out_pvals});
+        if (rank == 0) std::cout << "filepath_out_pvals = " << filepath_out_pvals << std::endl;
+        if (dataset->get_bimfp() != "") {
+            std::string filepath_out_pvals_LOCO = out_dir + out_name;
+            dataset->pvals_calc_LOCO(std::vector<std::vector<double>>{z1}, yf, std::vector<std::vector<double>>{x1_hat},
+                                     std::vector<std::string>{filepath_out_pvals_LOCO});
+            if (rank == 0) std::cout << "filepath_out_pvals_LOCO = " << filepath_out_pvals_LOCO << std::endl;
+        }
+    }
     return linear_end();
 }
 
@@ -416,9 +428,6 @@ bool vamp::linear_iteration(data* dataset, int it) {
 }
 
 std::vector<double> vamp::linear_end() {
-    if (store_pvals == 1 && rank == 0)
-        std::cout << "NOTE: --store-pvals (LOO / LOCO association tests) is post-processing outside the B200 hot path; skipped" << std::endl;
-
     if (files_enabled() && rank == 0) {
         store_vec_to_file(out_dir + out_name + "_gam1s.csv", gam1s);
         store_vec_to_file(out_dir + out_name + "_gam2s.csv", gam2s);

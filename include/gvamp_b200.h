@@ -166,6 +166,16 @@ int gvb_lmmse_mult(gvb_ctx* ctx, gvb_vec v, double tau, double gam2, gvb_vec out
 int gvb_cg_solve(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters,
                  double* rel_res);
 
+/* ---- association tests (LOO / LOCO p-values) --------------------------------------------------------- */
+/* The per-marker test of data::pvals_calc (data.cpp:1108-1180) and of the chromosome loop of data::pvals_calc_LOCO
+ * (data.cpp:1311-1343) with linear_reg1d_pvals (utilities.cpp:321-334): for every local marker j, regress
+ * yres + x_j * coef[j]/sqrt(N) on the standardised genotype column x_j over the individuals whose phenotype AND genotype
+ * are present, pvals[j] = two-sided Student-t p-value of the slope.  yres: N-vector (y - z1, resp. y - z1 + the
+ * chromosome's predictor); coef: the estimate whose own contribution is added back (x1_hat, LOO) or NULL (LOCO);
+ * select: optional M-vector, markers with select[j]==0 keep their old pvals[j] (LOCO: the markers of one chromosome).
+ * Two bed sweeps, local to the shard (no communication). */
+int gvb_assoc_pvals(gvb_ctx* ctx, gvb_vec yres, gvb_vec coef, gvb_vec select, gvb_vec pvals);
+
 /* ---- probit z-denoiser ---------------------------------------------------------------------------- */
 /* vamp::g1_bin_class / g1d_bin_class, vamp_probit.cpp:661-726 with erfcx (utilities.cpp:345-409):
  * z1_hat[i] = g(p1[i]); sums[0] = sum_i g'(p1[i]) (i<N); sums[1] = ||z1_hat - p1||^2.  mcov may be NULL. */

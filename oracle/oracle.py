@@ -204,6 +204,70 @@ class Dataset:
 
 
 # --------------------------------------------------------------------------------------------
+# association tests: LOO / LOCO p-values, data.cpp:1108-1353 + utilities.cpp:321-334
+# --------------------------------------------------------------------------------------------
+_DOSAGE = np.array([2.0, 0.0, 1.0, 0.0])      # dotp_lut_a: code 00 -> 2, 01 (missing) -> 0, 10 -> 1, 11 -> 0
+_PRESENT = np.array([1.0, 0.0, 1.0, 1.0])     # dotp_lut_b
+
+
+def _column_values(ds: "Dataset", j: int):
+    """(value, bm) of marker j over the 4*mbytes slots: value = (a - mu) sigma b m, bm = b m (data.cpp:1150, 1326)."""
+    codes = ((ds.bed[j][:, None] >> np.array([0, 2, 4, 6])) & 3).reshape(-1)
+    m = ((ds.mask4[:, None] >> np.arange(4)) & 1).reshape(-1).astype(np.float64)
+    bm = _PRESENT[codes] * m
+    return (_DOSAGE[codes] - ds.mave[j]) * ds.msig[j] * bm, bm
+
+
+def linear_reg1d_pvals(sumx, sumsqx, sumxy, sumy, sumsqy, n):
+    """utilities.cpp:321-334; the Student-t tail through the regularised incomplete beta function (scipy)."""
+    from scipy.special import betainc
+    s2y = (sumsqy - sumy * sumy / n) / (n - 1)
+    s2x = (sumsqx - sumx * sumx / n) / (n - 1)
+    sxy = (sumxy - sumx * sumy / n) / (n - 1)
+    rxy = sxy / math.sqrt(s2x * s2y)
+    t = rxy * math.sqrt((n - 2) / (1 - rxy * rxy))
+    nu = n - 2
+    return float(betainc(0.5 * nu, 0.5, nu / (nu + t * t)))
+
+
+def _reg_pvalue(value, bm, ymark):
+    return linear_reg1d_pvals(value.sum(), (value * value).sum(), (value * ymark).sum(), (ymark * bm).sum(), (ymark * ymark * bm).sum(),
+                              int(round(bm.sum())))
+
+
+def pvals_loo(ds: "Dataset", z1, y, x1_hat) -> np.ndarray:
+    """data::pvals_calc, data.cpp:1108-1180 (one estimator): y - z1 with the marker's own effect added back."""
+    ymod = np.zeros(4 * ds.mbytes)
+    ymod[: ds.N] = np.asarray(y)[: ds.N] - np.asarray(z1)[: ds.N]
+    out = np.empty(ds.M)
+    for j in range(ds.M):
+        value, bm = _column_values(ds, j)
+        out[j] = _reg_pvalue(value, bm, ymod + value / math.sqrt(ds.N) * x1_hat[j])
+    return out
+
+
+def pvals_loco(ds: "Dataset", z1, y, x1_hat, chroms, allreduce=lambda x: x) -> np.ndarray:
+    """data::pvals_calc_LOCO, data.cpp:1220-1353: per chromosome the predictor of its own markers is added back."""
+    ymod = np.zeros(4 * ds.mbytes)
+    ymod[: ds.N] = np.asarray(y)[: ds.N] - np.asarray(z1)[: ds.N]
+    chroms = np.asarray(chroms)
+    out = np.zeros(ds.M)
+    for ch in range(1, 24):
+        sel = np.flatnonzero(chroms == ch)
+        pred = np.zeros(4 * ds.mbytes)
+        for j in sel:
+            value, _ = _column_values(ds, j)
+            pred += value / math.sqrt(ds.N) * x1_hat[j]
+        pred = allreduce(pred)
+        pred[ds.N:] = 0.0                  # the reference all-reduces N entries only (data.cpp:1287)
+        ych = pred + ymod
+        for j in sel:
+            value, bm = _column_values(ds, j)
+            out[j] = _reg_pvalue(value, bm, ych)
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # denoiser, vamp.cpp:805-869
 # --------------------------------------------------------------------------------------------
 def g1(y, gam1, probs, vars_):

@@ -35,6 +35,9 @@ def lib():
         L.ref_data_create.argtypes = [cs, cs, ci, ci, ci, ci, cd]
         L.ref_data_create_y.restype = vp
         L.ref_data_create_y.argtypes = [c_f64p, cs, ci, ci, ci, ci, cd]
+        L.ref_data_create_bim.restype = vp
+        L.ref_data_create_bim.argtypes = [cs, cs, ci, ci, ci, ci, cd, cs]
+        L.ref_data_pvals.argtypes = [vp, ci, c_f64p, c_f64p, c_f64p, cs, c_f64p]
         L.ref_data_destroy.argtypes = [vp]
         L.ref_data_mbytes.restype = ctypes.c_long
         L.ref_data_mbytes.argtypes = [vp]
@@ -83,11 +86,13 @@ def _p(a):
 class RefData:
     """class data of the reference (data.hpp:93-94), one rank, shard [S, S+M)."""
 
-    def __init__(self, bed_path, N, M, Mt=None, S=0, phen_path=None, y=None, alpha_scale=1.0):
+    def __init__(self, bed_path, N, M, Mt=None, S=0, phen_path=None, y=None, alpha_scale=1.0, bim_path=None):
         L = lib()
         self.N, self.M = N, M
         Mt = M if Mt is None else Mt
-        if phen_path is not None:
+        if bim_path is not None:
+            self.h = L.ref_data_create_bim(phen_path.encode(), bed_path.encode(), N, M, Mt, S, alpha_scale, bim_path.encode())
+        elif phen_path is not None:
             self.h = L.ref_data_create(phen_path.encode(), bed_path.encode(), N, M, Mt, S, alpha_scale)
         else:
             yy = np.ascontiguousarray(np.zeros(N) if y is None else y, dtype=np.float64)
@@ -134,6 +139,15 @@ class RefData:
         uu[: min(len(u), 4 * LB)] = u[: 4 * LB]
         out = np.empty(self.M)
         lib().ref_data_ATx(self.h, _p(uu), SB, LB, _p(out))
+        return out
+
+    def pvals(self, z1, y, x1_hat, out_path, loco=False):
+        """data::pvals_calc / pvals_calc_LOCO (data.cpp:1108-1353) for one estimator."""
+        z1 = np.ascontiguousarray(z1[: self.N], dtype=np.float64)
+        y = np.ascontiguousarray(y[: self.N], dtype=np.float64)
+        x = np.ascontiguousarray(x1_hat, dtype=np.float64)
+        out = np.empty(self.M)
+        lib().ref_data_pvals(self.h, int(loco), _p(z1), _p(y), _p(x), out_path.encode(), _p(out))
         return out
 
     def close(self):

@@ -59,7 +59,21 @@ void* ref_data_create_y(const double* y, const char* bed_path, int N, int M, int
     std::vector<double> yy(y, y + N);
     return new data(yy, std::string(bed_path), N, M, Mt, S, 0, "bed", alpha_scale, "");
 }
+void* ref_data_create_bim(const char* phen_path, const char* bed_path, int N, int M, int Mt, int S, double alpha_scale, const char* bimfp) {
+    StdoutSilencer s(g_quiet);
+    return new data(std::string(phen_path), std::string(bed_path), N, M, Mt, S, 0, "bed", alpha_scale, std::string(bimfp));
+}
 void ref_data_destroy(void* h) { delete static_cast<data*>(h); }
+// data::pvals_calc data.cpp:1108-1180 / data::pvals_calc_LOCO data.cpp:1220-1353, one estimator; z1 and y have N entries
+void ref_data_pvals(void* h, int loco, const double* z1, const double* y, const double* x1_hat, const char* out_path, double* out) {
+    StdoutSilencer s(g_quiet);
+    data* d = static_cast<data*>(h);
+    std::vector<std::vector<double>> z{std::vector<double>(z1, z1 + d->N)}, x{std::vector<double>(x1_hat, x1_hat + d->M)};
+    std::vector<double> yy(y, y + d->N);
+    std::vector<std::string> fp{std::string(out_path)};
+    std::vector<std::vector<double>> r = loco ? d->pvals_calc_LOCO(z, yy, x, fp) : d->pvals_calc(z, yy, x, fp);
+    memcpy(out, r[0].data(), sizeof(double) * d->M);
+}
 long ref_data_mbytes(void* h) { return (long)static_cast<data*>(h)->get_mbytes(); }
 int ref_data_nonas(void* h) { return static_cast<data*>(h)->get_nonas(); }
 double ref_data_intercept(void* h) { return static_cast<data*>(h)->get_intercept(); }

@@ -204,6 +204,38 @@ def case_vamp_probit(tmp):
         fh.write("\n".join(l for l in log.splitlines() if not l.startswith("[CG")) + "\n")
 
 
+def case_pvals(tmp):
+    """LOO and LOCO association p-values (data.cpp:1108-1353) on the N=1003 case (2 % missing genotypes, phenotype NAs)
+    with a 5-chromosome .bim (incl. "X" -> 23).  The Student-t tail comes from oracle/shims (incomplete beta), which the
+    oracle cross-checks against scipy."""
+    N, M, seed = 1003, 400, 11
+    bed = O.synth_bed(seed, 0, M, N, miss_rate=0.02)
+    bedp, phenp, bimp = os.path.join(tmp, "pv.bed"), os.path.join(tmp, "pv.phen"), os.path.join(tmp, "pv.bim")
+    O.write_bed(bedp, bed)
+    rng = np.random.default_rng(seed + 1)
+    beta = np.zeros(M)
+    causal = rng.choice(M, size=12, replace=False)
+    beta[causal] = rng.normal(0, math.sqrt(0.5 / 12), size=12)
+    ds0 = O.Dataset(bed, N)
+    y = ds0.Ax(beta * math.sqrt(N))[:N] + rng.normal(0, math.sqrt(0.5), size=N)
+    na_idx = [5, 700, 701]
+    O.write_phen(phenp, y, na_idx=na_idx)
+    chrom_of = np.array([1] * 100 + [2] * 120 + [7] * 80 + [22] * 60 + [23] * 40)
+    with open(bimp, "w") as fh:
+        for j in range(M):
+            ch = "X" if chrom_of[j] == 23 else str(chrom_of[j])
+            fh.write(f"{ch}\trs{j}\t0\t{1000 + j}\tA\tG\n")
+    rd = R.RefData(bedp, N, M, phen_path=phenp, bim_path=bimp)
+    x1 = (beta + rng.normal(0, 0.01, size=M) * (rng.random(M) < 0.2)) * math.sqrt(N)   # an imperfect estimate, scaled like main_real.cpp:390
+    z1 = rd.Ax(x1)
+    yf = rd.filter_pheno()
+    loo = rd.pvals(z1, yf, x1, os.path.join(tmp, "pv_loo.bin"), loco=False)
+    loco = rd.pvals(z1, yf, x1, os.path.join(tmp, "pv"), loco=True)
+    np.savez_compressed(os.path.join(OUT, "pvals.npz"), N=N, M=M, seed=seed, miss_rate=0.02, y=y, na_idx=na_idx, chrom=chrom_of, x1=x1, z1=z1,
+                        y_filtered=yf, pvals_loo=loo, pvals_loco=loco, mask4=rd.mask4(), nonas=rd.nonas())
+    print("pvals: LOO min %.3e, LOCO min %.3e" % (loo.min(), loco.min()))
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first: make -C oracle ref"
     with tempfile.TemporaryDirectory() as tmp:
@@ -213,4 +245,5 @@ if __name__ == "__main__":
         case_cg(tmp)
         case_vamp_linear(tmp)
         case_vamp_probit(tmp)
+        case_pvals(tmp)
     print("golden vectors written to", OUT)

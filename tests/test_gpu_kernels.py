@@ -275,3 +275,33 @@ def test_probit_denoiser_golden(C, oracle):
         assert relerr(z.download(n), g["g"]) < 1e-14
         assert abs(sums[0] - g["gd"].sum()) < 1e-10 * n
         assert abs(sums[1] - ((g["g"] - g["p"]) ** 2).sum()) < 1e-10 * n
+
+
+def test_assoc_pvals_golden(C, oracle):
+    """gvb_assoc_pvals (LOO with the marker's own effect added back; LOCO per chromosome with a marker selection) against
+    the p-values of the UNMODIFIED reference (data::pvals_calc / pvals_calc_LOCO): N % 4 != 0, 2 % missing genotypes,
+    phenotype NAs, p from 1e-68 to 1.  Tolerance 1e-4 relative on p (north_star's bound for final outputs; the sums come
+    out of the fixed-point X^T.u sweep and d ln p / d ln t reaches ~400 at the small end)."""
+    g = golden("pvals.npz")
+    N, M = int(g["N"]), int(g["M"])
+    bed = oracle.synth_bed(int(g["seed"]), 0, M, N, miss_rate=float(g["miss_rate"]))
+    with make_ctx(C, "lut") as ctx:
+        ctx.load_host(bed, N).set_mask(g["mask4"], int(g["nonas"])).compute_stats(1.0)
+        ymod = np.zeros(4 * ((N + 3) // 4))
+        ymod[:N] = g["y_filtered"] - g["z1"][:N]
+        yres, coef, pv, sel = ctx.vecN(ymod), ctx.vecM(g["x1"]), ctx.vecM(), ctx.vecM()
+        ctx.assoc_pvals(yres, coef, None, pv)
+        loo = pv.download()
+        pv.fill(0.0)
+        for ch in range(1, 24):
+            pick = g["chrom"] == ch
+            if not pick.any():
+                continue
+            pred = ctx.Ax(np.where(pick, g["x1"], 0.0))
+            pred[N:] = 0.0
+            yres.upload(ymod + pred)
+            sel.upload(pick.astype(np.float64))
+            ctx.assoc_pvals(yres, None, sel, pv)
+        loco = pv.download()
+    assert np.allclose(loo, g["pvals_loo"], rtol=1e-4, atol=0), np.max(np.abs(loo / g["pvals_loo"] - 1))
+    assert np.allclose(loco, g["pvals_loco"], rtol=1e-4, atol=0), np.max(np.abs(loco / g["pvals_loco"] - 1))

@@ -83,6 +83,29 @@ def test_test_mode_r2(oracle, tmp_path):
     assert abs(got - want) < TOL_FINAL
 
 
+def test_pvals_calc_mode(oracle, tmp_path):
+    """--run-mode pvals-calc (main_real.cpp:331-452): LOO + LOCO p-value files of an estimate file against the reference's."""
+    g = golden("pvals.npz")
+    N, M = int(g["N"]), int(g["M"])
+    bed = oracle.synth_bed(int(g["seed"]), 0, M, N, miss_rate=float(g["miss_rate"]))
+    bedp, phenp, bimp, estp = str(tmp_path / "pv.bed"), str(tmp_path / "pv.phen"), str(tmp_path / "pv.bim"), str(tmp_path / "est.bin")
+    oracle.write_bed(bedp, bed)
+    oracle.write_phen(phenp, g["y"], na_idx=[int(i) for i in g["na_idx"]])
+    with open(bimp, "w") as fh:
+        for j, ch in enumerate(g["chrom"]):
+            fh.write(f"{'X' if ch == 23 else ch}\trs{j}\t0\t{1000 + j}\tA\tG\n")
+    (g["x1"] / math.sqrt(N)).astype(np.float64).tofile(estp)        # the driver multiplies the file by sqrt(N)
+    outd = str(tmp_path / "pvout") + "/"
+    r = subprocess.run([EXE, "--run-mode", "pvals-calc", "--bed-file", bedp, "--phen-files", phenp, "--bim-file", bimp, "--N", str(N), "--Mt", str(M),
+                        "--estimate-file", estp, "--out-dir", outd, "--out-name", "pv"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    loo = np.fromfile(outd + "pv_pvals.bin")
+    loco = np.fromfile(outd + "pv_pvals_LOCO.bin_pvals_LOCO.bin")     # the reference appends the suffix twice (data.cpp:1348)
+    # y in the golden was scaled by read_phen before the reference used it; the driver re-reads the same phen file
+    assert np.allclose(loo, g["pvals_loo"], rtol=1e-4, atol=0) and np.allclose(loco, g["pvals_loco"], rtol=1e-4, atol=0)
+    assert os.path.exists(outd + "pv_pvals_LOCO.bin_LOCO_chr_7.csv")
+
+
 EXE_PROBIT = os.path.join(ROOT, "gvamp_b200", "bin", "main_real_probit")
 
 

@@ -145,3 +145,17 @@ def test_vamp_linear_end_to_end(oracle):
     assert np.allclose(tr.vars[-1], g["prior_vars_last"], rtol=1e-5)
     assert np.allclose(tr.probs[-1], g["prior_probs_last"], rtol=1e-5)
     assert relerr(g["x1_last_manvect"], g[f"x1_{iters}"]) < 1e-10
+
+
+def test_pvals_loo_loco(oracle):
+    """The restatement of data::pvals_calc / pvals_calc_LOCO (oracle.py, Student-t tail from scipy) against the p-values the
+    UNMODIFIED reference produced (tests/golden/pvals.npz, make_golden.py:case_pvals; its Boost shim is an incomplete-beta
+    continued fraction): two independent evaluations of the t distribution agree to 1e-9."""
+    g = golden("pvals.npz")
+    N, M = int(g["N"]), int(g["M"])
+    bed = oracle.synth_bed(int(g["seed"]), 0, M, N, miss_rate=float(g["miss_rate"]))
+    ds = oracle.Dataset(bed, N, mask4=g["mask4"], nonas=int(g["nonas"]))
+    loo = oracle.pvals_loo(ds, g["z1"], g["y_filtered"], g["x1"])
+    loco = oracle.pvals_loco(ds, g["z1"], g["y_filtered"], g["x1"], g["chrom"])
+    assert np.allclose(loo, g["pvals_loo"], rtol=1e-9, atol=0) and np.allclose(loco, g["pvals_loco"], rtol=1e-9, atol=0)
+    assert g["pvals_loo"].min() < 1e-50 and g["pvals_loo"].max() > 0.9       # the case spans the whole range

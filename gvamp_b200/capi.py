@@ -76,6 +76,8 @@ SIGNATURES = {
     "gvb_probit_denoise": (ci, [vp, vp, vp, vp, cd, cd, vp, c_f64p]),
     "gvb_missing_list_entries": (cl, [vp]),
     "gvb_assoc_pvals": (ci, [vp, vp, vp, vp, vp]),
+    "gvb_probit_cov_pass": (ci, [vp, vp, vp, vp, ci, c_f64p, cd, ci, c_f64p]),
+    "gvb_probit_cov_apply": (ci, [vp, vp, ci, c_f64p, vp]),
 }
 
 _LIB = None
@@ -352,6 +354,16 @@ class Context:
 
     def sweeps(self) -> int:
         return self.L.gvb_sweep_count(self.h)
+
+    def probit_cov_pass(self, y, gg, Z, C, eta, probit_var=1.0, what=7):
+        e, pe = _f64(eta)
+        out = np.empty(1 + 2 * C + C * C)
+        _chk(self.L.gvb_probit_cov_pass(self.h, y.h, gg.h if gg is not None else None, Z.h, C, pe, probit_var, what, out.ctypes.data_as(c_f64p)))
+        return out[0], out[1:1 + C].copy(), out[1 + C:1 + 2 * C].copy(), out[1 + 2 * C:].reshape(C, C).copy()
+
+    def probit_cov_apply(self, Z, C, eta, mcov):
+        e, pe = _f64(eta)
+        _chk(self.L.gvb_probit_cov_apply(self.h, Z.h, C, pe, mcov.h))
 
     def assoc_pvals(self, yres, coef, select, pvals):
         _chk(self.L.gvb_assoc_pvals(self.h, yres.h, coef.h if coef is not None else None, select.h if select is not None else None, pvals.h))

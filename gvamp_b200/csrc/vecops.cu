@@ -365,3 +365,141 @@ extern "C" int gvb_probit_denoise(gvb_ctx* c, gvb_vec p1, gvb_vec y, gvb_vec mco
     GVB_LAUNCHED(c);
     return gvb_reduce_finish(c, blocks, 2, false, sums);   // N-vectors are replicated: no rank sum
 }
+
+// ------------------------------------------------------------------------------------------------
+// probit covariate effects: the N x C passes of vamp::Newton_method_cov (vamp_probit.cpp:936-1067) with grad_cov
+// (:814-839) and mlogL_probit (:841-858).  The reference walks the N x C covariate matrix on one core, once for the
+// Hessian + Newton numerator, once for the gradient and once per line-search probe; here ONE launch returns any subset
+// of {mlogL, gradient, numerator + Hessian} at a given eta.  Z stays on the device.
+//   out[0]            = -1/N sum_i log Phi(s_i g_i / sqrt(pv)),  g_i = gg_i + <Z_i, eta>, s_i = 2 y_i - 1
+//   out[1 .. C]       = gradient  -1/N sum_i r_i s_i Z_ij / sqrt(pv),  r_i = 2/sqrt(2 pi) / erfcx(-s_i g_i / sqrt(2 pv))
+//   out[1+C .. 2C]    = sum_i Z_ij lam_i,  lam_i = s_i 2/sqrt(2 pi) / erfcx(-s_i g_i / sqrt(2))   (no pv: vamp_probit.cpp:951)
+//   out[1+2C ..]      = H_jk = sum_i Z_ij Z_ik lam_i (lam_i + g_i)
+// ------------------------------------------------------------------------------------------------
+#define COV_CHUNK 128
+#define COV_MAXC 32
+
+__global__ void __launch_bounds__(256) probit_cov_kernel(const double* __restrict__ y, const double* __restrict__ gg, const double* __restrict__ Z,
+                                                         long n, int C, const double* __restrict__ eta_d, double probit_var, int what,
+                                                         double* __restrict__ partial) {
+    __shared__ double Zs[COV_CHUNK][COV_MAXC + 1];
+    __shared__ double s_lam[COV_CHUNK], s_w[COV_CHUNK], s_gr[COV_CHUNK], s_ll[COV_CHUNK];
+    __shared__ double eta[COV_MAXC];
+    const int K = 1 + 2 * C + C * C;
+    const int tid = threadIdx.x;
+    if (tid < C) eta[tid] = eta_d[tid];
+    const double k2pi = 2.0 / sqrt(2.0 * M_PI), isd = 1.0 / sqrt(probit_var);
+    // thread t owns H entries e = t, t+256, ... (at most 4 for C = 32) and, for t < C, step[t] / grad[t]; thread 0 owns mlogL
+    double hacc[4] = {0.0, 0.0, 0.0, 0.0};
+    double sacc = 0.0, gacc = 0.0, lacc = 0.0;
+    const long n_chunks = (n + COV_CHUNK - 1) / COV_CHUNK;
+    for (long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        const long i0 = ch * COV_CHUNK;
+        const int cnt = (int)min((long)COV_CHUNK, n - i0);
+        __syncthreads();
+        for (int e = tid; e < cnt * C; e += 256) Zs[e / C][e % C] = Z[i0 * C + e];   // rows of the chunk are contiguous
+        __syncthreads();
+        if (tid < cnt) {
+            double g = gg ? gg[i0 + tid] : 0.0;
+            for (int j = 0; j < C; j++) g += Zs[tid][j] * eta[j];     // inner_prod(Z[i], eta), same order as the reference
+            const double sgn = 2.0 * y[i0 + tid] - 1.0;
+            const double lam = k2pi / erfcx_dev(-(sgn * g) / sqrt(2.0)) * sgn;
+            s_lam[tid] = lam;
+            s_w[tid] = lam * (lam + g);
+            const double arg = sgn / sqrt(probit_var) * g;
+            s_gr[tid] = -(k2pi / erfcx_dev(-arg / sqrt(2.0))) * sgn * isd;
+            s_ll[tid] = -log(0.5 * erfc(-arg * M_SQRT1_2));
+        }
+        __syncthreads();
+        if (what & 4) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int e = tid + 256 * r;
+                if (e < C * C) {
+                    const int j = e / C, k = e % C;
+                    double a = 0.0;
+                    for (int i = 0; i < cnt; i++) a += Zs[i][k] * (Zs[i][j] * s_w[i]);
+                    hacc[r] += a;
+                }
+            }
+        }
+        if (tid < C) {
+            double a = 0.0, b = 0.0;
+            for (int i = 0; i < cnt; i++) {
+                a += Zs[i][tid] * s_lam[i];
+                b += s_gr[i] * Zs[i][tid];
+            }
+            sacc += a;
+            gacc += b;
+        }
+        if (tid == 255) {
+            double a = 0.0;
+            for (int i = 0; i < cnt; i++) a += s_ll[i];
+            lacc += a;
+        }
+    }
+    double* mine = partial + (size_t)blockIdx.x * K;
+    if (tid == 255) mine[0] = lacc;
+    if (tid < C) {
+        mine[1 + tid] = gacc;
+        mine[1 + C + tid] = sacc;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int e = tid + 256 * r;
+        if (e < C * C) mine[1 + 2 * C + e] = hacc[r];
+    }
+}
+
+__global__ void probit_cov_reduce_kernel(const double* __restrict__ partial, int nblocks, int K, int C, double inv_n, double* __restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; b++) s += partial[(size_t)b * K + k];
+    out[k] = (k <= C) ? s * inv_n : s;   // mlogL and the gradient are means (vamp_probit.cpp:837, 857)
+}
+
+extern "C" int gvb_probit_cov_pass(gvb_ctx* c, gvb_vec y, gvb_vec gg, gvb_vec Z, int C, const double* eta, double probit_var, int what, double* out) {
+    GVB_ARG(c && y && Z && eta && out, "arguments");
+    GVB_ARG(C >= 1 && C <= COV_MAXC, "1 <= C <= 32 covariates");
+    const long n = c->N;
+    GVB_ARG(y->n >= n && (!gg || gg->n >= n) && Z->n >= n * C, "vector lengths (Z is N x C, row-major)");
+    const int K = 1 + 2 * C + C * C;
+    const int blocks = (int)std::max(1l, std::min((n + COV_CHUNK - 1) / COV_CHUNK, 2l * c->sm_count));
+    double* scratch = nullptr;
+    GVB_CUDA(cudaMallocAsync(&scratch, ((size_t)blocks * K + K + COV_MAXC) * sizeof(double), c->stream));
+    double* d_out = scratch + (size_t)blocks * K;
+    double* d_eta = d_out + K;
+    GVB_CUDA(cudaMemcpyAsync(d_eta, eta, C * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    probit_cov_kernel<<<blocks, 256, 0, c->stream>>>(y->d, gg ? gg->d : nullptr, Z->d, n, C, d_eta, probit_var, what, scratch);
+    GVB_LAUNCHED(c);
+    probit_cov_reduce_kernel<<<(K + 127) / 128, 128, 0, c->stream>>>(scratch, blocks, K, C, 1.0 / (double)n, d_out);
+    GVB_LAUNCHED(c);
+    GVB_CUDA(cudaMemcpyAsync(out, d_out, K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GVB_CUDA(cudaStreamSynchronize(c->stream));
+    GVB_CUDA(cudaFreeAsync(scratch, c->stream));
+    return GVB_OK;
+}
+
+// mcov[i] = <Z_i, eta> (vamp_probit.cpp:132: the covariate part of the liability)
+__global__ void probit_cov_apply_kernel(const double* __restrict__ Z, long n, int C, const double* __restrict__ eta, double* __restrict__ mcov) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double g = 0.0;
+    for (int j = 0; j < C; j++) g += Z[i * C + j] * eta[j];
+    mcov[i] = g;
+}
+
+extern "C" int gvb_probit_cov_apply(gvb_ctx* c, gvb_vec Z, int C, const double* eta, gvb_vec mcov) {
+    GVB_ARG(c && Z && eta && mcov && C >= 1 && C <= COV_MAXC, "arguments");
+    const long n = c->N;
+    GVB_ARG(Z->n >= n * C && mcov->n >= n, "vector lengths");
+    double* d_eta = nullptr;
+    GVB_CUDA(cudaMallocAsync(&d_eta, COV_MAXC * sizeof(double), c->stream));
+    GVB_CUDA(cudaMemcpyAsync(d_eta, eta, C * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    probit_cov_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(Z->d, n, C, d_eta, mcov->d);
+    GVB_LAUNCHED(c);
+    GVB_CUDA(cudaStreamSynchronize(c->stream));   // eta is a host buffer of the caller
+    GVB_CUDA(cudaFreeAsync(d_eta, c->stream));
+    return GVB_OK;
+}

@@ -182,6 +182,16 @@ int gvb_assoc_pvals(gvb_ctx* ctx, gvb_vec yres, gvb_vec coef, gvb_vec select, gv
 int gvb_probit_denoise(gvb_ctx* ctx, gvb_vec p1, gvb_vec y, gvb_vec mcov, double tau1, double probit_var, gvb_vec z1_hat,
                        double* sums);
 
+/* ---- probit covariate effects --------------------------------------------------------------------- */
+/* One pass over the N x C covariate matrix Z (row-major device vector of N*C doubles, 1 <= C <= 32) at the covariate
+ * effects eta (C host doubles): the inner loops of vamp::Newton_method_cov (vamp_probit.cpp:936-1067), grad_cov
+ * (:814-839) and mlogL_probit (:841-858).  gg: genetic part of the liability (N-vector) or NULL for zeros.
+ * out (host, 1 + 2C + C*C doubles): [0] mlogL_probit, [1..C] grad_cov, [1+C..2C] Newton numerator sum_i Z_ij lambda_i,
+ * [1+2C..] Hessian, row-major.  `what` selects the Hessian (bit 2); the cheap parts are always returned. */
+int gvb_probit_cov_pass(gvb_ctx* ctx, gvb_vec y, gvb_vec gg, gvb_vec Z, int C, const double* eta, double probit_var, int what, double* out);
+/* mcov[i] = <Z_i, eta>: the covariate part of the liability (vamp_probit.cpp:132-137) */
+int gvb_probit_cov_apply(gvb_ctx* ctx, gvb_vec Z, int C, const double* eta, gvb_vec mcov);
+
 #ifdef __cplusplus
 }
 #endif

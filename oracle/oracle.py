@@ -607,3 +607,21 @@ def g1d_bin_class(p, tau1, y, m_cov, probit_var=1.0):
     c = (p + m_cov) / s
     ratio = 2.0 / math.sqrt(2 * math.pi) / erfcx(-(2 * y - 1) * c / math.sqrt(2))
     return 1 - ratio / (1 + tau1 * probit_var) * ((2 * y - 1) * c + ratio)
+
+
+def probit_cov_pass(y, gg, Z, eta, probit_var=1.0):
+    """The N x C sums of the covariate Newton step: mlogL_probit (vamp_probit.cpp:841-858), grad_cov (:814-839), and the
+    numerator / Hessian of Newton_method_cov (:944-970; note that these two do not carry probit_var)."""
+    from scipy.special import erfc
+    y, gg, Z, eta = np.asarray(y, float), np.asarray(gg, float), np.asarray(Z, float), np.asarray(eta, float)
+    n = len(y)
+    g = gg + Z @ eta
+    sgn = 2 * y - 1
+    arg = sgn / math.sqrt(probit_var) * g
+    mlogl = -np.sum(np.log(0.5 * erfc(-arg * math.sqrt(0.5)))) / n
+    ratio = 2.0 / math.sqrt(2 * math.pi) / erfcx(-arg / math.sqrt(2))
+    grad = -(ratio * sgn / math.sqrt(probit_var)) @ Z / n
+    lam = 2.0 / math.sqrt(2 * math.pi) / erfcx(-(sgn * g) / math.sqrt(2)) * sgn
+    step = Z.T @ lam
+    H = Z.T @ (Z * (lam * (lam + g))[:, None])
+    return mlogl, grad, step, H

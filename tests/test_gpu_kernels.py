@@ -305,3 +305,29 @@ def test_assoc_pvals_golden(C, oracle):
         loco = pv.download()
     assert np.allclose(loo, g["pvals_loo"], rtol=1e-4, atol=0), np.max(np.abs(loo / g["pvals_loo"] - 1))
     assert np.allclose(loco, g["pvals_loco"], rtol=1e-4, atol=0), np.max(np.abs(loco / g["pvals_loco"] - 1))
+
+
+@pytest.mark.parametrize("C_cov", [3, 20, 32])
+def test_probit_covariate_pass(C, oracle, C_cov):
+    """gvb_probit_cov_pass / gvb_probit_cov_apply (the N x C passes of vamp::Newton_method_cov, grad_cov, mlogL_probit)
+    against the numpy restatement; N not a multiple of the 128-individual chunk.  FP64 sums in a different order: 1e-12."""
+    N, M = 3001, 64
+    rng = np.random.default_rng(C_cov)
+    bed = oracle.synth_bed(5, 0, M, N)
+    Z = rng.normal(size=(N, C_cov))
+    eta = rng.normal(scale=0.3, size=C_cov)
+    gg = rng.normal(scale=0.5, size=N)
+    y = (rng.random(N) < 0.4).astype(np.float64)
+    with make_ctx(C, "lut") as ctx:
+        ctx.load_host(bed, N).compute_stats(1.0)
+        dy, dgg, dZ, dm = ctx.vecN(y), ctx.vecN(gg), ctx.vec(N * C_cov), ctx.vecN()
+        dZ.upload(Z.reshape(-1))
+        for pv in (1.0, 0.7):
+            got = ctx.probit_cov_pass(dy, dgg, dZ, C_cov, eta, pv)
+            want = oracle.probit_cov_pass(y, gg, Z, eta, pv)
+            for a, b in zip(got, want):
+                assert np.allclose(a, b, rtol=1e-12, atol=1e-12 * np.max(np.abs(b)))
+        got0 = ctx.probit_cov_pass(dy, None, dZ, C_cov, eta, 1.0, what=0)
+        assert np.isclose(got0[0], oracle.probit_cov_pass(y, np.zeros(N), Z, eta)[0], rtol=1e-12)
+        ctx.probit_cov_apply(dZ, C_cov, eta, dm)
+        assert np.allclose(dm.download()[:N], Z @ eta, rtol=1e-13, atol=1e-13)

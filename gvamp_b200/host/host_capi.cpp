@@ -24,6 +24,13 @@ void* gvbh_data_create_resident(gvb_ctx* ctx, const double* y, int N, int M, int
     return new data(ctx, std::vector<double>(y, y + N), N, M, Mt, S, gvb_host::world().rank, alpha_scale);
 }
 void gvbh_data_destroy(void* d) { delete static_cast<data*>(d); }
+// covariates from a row-major N x C host array (the executables read them with data::read_covariates)
+void gvbh_data_set_covs(void* d, const double* Z, int N, int C) {
+    std::vector<std::vector<double>> rows(N, std::vector<double>(C));
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < C; j++) rows[i][j] = Z[(size_t)i * C + j];
+    static_cast<data*>(d)->set_covs(std::move(rows));
+}
 gvb_ctx* gvbh_data_ctx(void* d) { return static_cast<data*>(d)->device(); }
 void gvbh_data_stats(void* d, double* mave, double* msig) {
     data* p = static_cast<data*>(d);

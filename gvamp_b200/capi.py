@@ -73,6 +73,7 @@ SIGNATURES = {
     "gvb_em_stats": (ci, [vp, vp, cd, cd, c_f64p, c_f64p, ci, c_f64p]),
     "gvb_lmmse_mult": (ci, [vp, vp, cd, cd, vp]),
     "gvb_cg_solve": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p]),
+    "gvb_cg_solve_ex": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, c_f64p]),
     "gvb_probit_denoise": (ci, [vp, vp, vp, vp, cd, cd, vp, c_f64p]),
     "gvb_missing_list_entries": (cl, [vp]),
     "gvb_assoc_pvals": (ci, [vp, vp, vp, vp, vp]),
@@ -319,6 +320,14 @@ class Context:
         log = np.zeros(4 * max_iter)
         _chk(self.L.gvb_cg_solve(self.h, rhs.h, mu.h, tau, gam2, max_iter, denoiser, ctypes.byref(it), log.ctypes.data_as(c_f64p)))
         return it.value, log.reshape(max_iter, 4)[: it.value]
+
+    def cg_solve_ex(self, rhs, mu, tau, gam2, max_iter, denoiser, ax_mu=None):
+        it = ci(0)
+        log = np.zeros(4 * max_iter)
+        dots3 = np.zeros(3)
+        _chk(self.L.gvb_cg_solve_ex(self.h, rhs.h, mu.h, tau, gam2, max_iter, denoiser, ctypes.byref(it), log.ctypes.data_as(c_f64p),
+                                    ax_mu.h if ax_mu is not None else None, dots3.ctypes.data_as(c_f64p)))
+        return it.value, log.reshape(max_iter, 4)[: it.value], dots3
 
     def probit_denoise(self, p1, y, mcov, tau1, probit_var, z1_hat):
         sums = np.empty(2)

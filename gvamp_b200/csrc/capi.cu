@@ -523,13 +523,28 @@ __global__ void __launch_bounds__(256) cg_init_kernel(double* __restrict__ r, do
     }
 }
 
+// ax += alpha * ap over the padded N-vector: the running A.mu of the CG by-product (see cg_solve_impl)
+__global__ void cg_axpy_n_kernel(double* __restrict__ ax, const double* __restrict__ ap, double alpha, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) ax[i] += alpha * ap[i];
+}
+// r -= alpha*d (no reductions): brings the residual up to date when the Onsager exit left it one update behind
+__global__ void cg_axpy_m_kernel(double* __restrict__ r, const double* __restrict__ d, double alpha, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) r[i] -= alpha * d[i];
+}
+
 static inline int cg_blocks(long n) { return (int)std::max(1l, std::min((n + 1023) / 1024, (long)GVB_RED_BLOCKS)); }
 
 // vamp::precondCG_solver, vamp.cpp:1130-1229.  z = r/diag is never materialised (diag is a constant,
 // :1137-1138); every scalar and every exit test is FP64 with the reference's formulas.
-extern "C" int gvb_cg_solve(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4) {
+//
+// By-products (both optional, no extra bed sweep): every iteration already forms A p (the N-vector inside lmmse_mult), so
+// ax_mu = A mu_start + sum_k alpha_k A p_k is A times the returned solution; and dots3 = {<rhs,rhs>, <rhs,mu>, <rhs,r>} with the
+// residual r = rhs - Q mu of the returned mu gives <rhs, A^T A mu> = (dots3[0] - gam2 dots3[1] - dots3[2]) / tau.
+static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
+                         gvb_vec ax_mu, double* dots3) {
     GVB_ARG(c && rhs && mu && rhs != mu, "vectors");
     GVB_ARG(rhs->cap >= c->Mg_pad * 4 && mu->cap >= c->Mg_pad * 4, "M-vectors from gvb_vec_alloc_M");
+    GVB_ARG(!ax_mu || ax_mu->cap >= c->Npad, "ax_mu must be an N-vector from gvb_vec_alloc_N");
     long n = c->M;
     for (int k = 0; k < 3; k++) {
         if (c->cg_ws[k] && c->cg_ws[k]->cap != c->Mg_pad * 4) {   // matrix was reloaded with another shape
@@ -547,7 +562,18 @@ extern "C" int gvb_cg_solve(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, dou
     const int nb = cg_blocks(n);
     double s2[2];
     // r = rhs - lmmse_mult(mu_start) ; z = r/diag ; p = z
+    const long sweeps_before = c->sweeps;
     CGCHK(lmmse_mult_dev(c, mu, tau, gam2, d, false));
+    if (ax_mu) {   // A mu_start is in the operator's scratch unless the zero-vector shortcut skipped the sweeps
+        if (c->sweeps != sweeps_before)
+            GVB_CUDA(cudaMemcpyAsync(ax_mu->d, c->tmpN2, c->Npad * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        else
+            GVB_CUDA(cudaMemsetAsync(ax_mu->d, 0, c->Npad * sizeof(double), c->stream));
+    }
+    const int nbn = (int)std::min((c->Npad + 255) / 256, 1184l);
+    double rhs_mu = 0.0;
+    bool r_stale = false;
+    double alpha_last = 0.0;
     cg_init_kernel<<<nb, 256, 0, c->stream>>>(r->d, p->d, rhs->d, d->d, diag, n, c->red_partial);
     c->launches++;
     CGCHK(gvb_reduce_finish(c, nb, 2, true, s2));
@@ -564,16 +590,23 @@ extern "C" int gvb_cg_solve(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, dou
         double dp = 0.0;
         CGCHK(gvb_vec_dots(c, 1, xs, ys, 1, &dp));
         double alpha = rz / dp;
+        if (ax_mu && rz != 0.0) {   // c->tmpN2 still holds A p of this iteration
+            cg_axpy_n_kernel<<<nbn, 256, 0, c->stream>>>(ax_mu->d, c->tmpN2, alpha, c->Npad);
+            c->launches++;
+        }
         cg_update_mu_kernel<<<nb, 256, 0, c->stream>>>(mu->d, p->d, rhs->d, alpha, n, c->red_partial);
         c->launches++;
         CGCHK(gvb_reduce_finish(c, nb, 2, true, s2));
         double norm_mu = sqrt(s2[1]);
+        rhs_mu = s2[0];
         double ons_rel = -1.0;
         if (denoiser == 0) {   // vamp.cpp:1174-1193
             double onsager = gam2 * s2[0];
             ons_rel = (onsager != 0.0) ? fabs((onsager - prev_onsager) / onsager) : 1.0;
             if (ons_rel < 1e-8) {
                 if (log4) { log4[4 * i + 0] = -1.0; log4[4 * i + 1] = norm_mu; log4[4 * i + 2] = -1.0; log4[4 * i + 3] = ons_rel; }
+                r_stale = true;   // mu moved, r did not (the reference tests before the r-update, vamp.cpp:1174-1193)
+                alpha_last = alpha;
                 break;
             }
             prev_onsager = onsager;
@@ -592,6 +625,19 @@ extern "C" int gvb_cg_solve(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, dou
         if (log4) { log4[4 * i + 0] = rel_err; log4[4 * i + 1] = norm_mu; log4[4 * i + 2] = norm_z / norm_v; log4[4 * i + 3] = ons_rel; }
         if (rel_err < 1e-5) break;                     // vamp.cpp:1217-1223
     }
+    if (dots3) {
+        if (r_stale) {
+            cg_axpy_m_kernel<<<(unsigned)std::min((n + 255) / 256, 1184l), 256, 0, c->stream>>>(r->d, d->d, alpha_last, n);
+            c->launches++;
+        }
+        gvb_vec xs[1] = {rhs};
+        gvb_vec ys[1] = {r};
+        double rr_dot = 0.0;
+        CGCHK(gvb_vec_dots(c, 1, xs, ys, 1, &rr_dot));
+        dots3[0] = norm_v * norm_v;
+        dots3[1] = rhs_mu;
+        dots3[2] = rr_dot;
+    }
 #undef CGCHK
     cudaError_t e = cudaGetLastError();
     cleanup();
@@ -601,4 +647,12 @@ extern "C" int gvb_cg_solve(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, dou
     }
     if (iters) *iters = it_done;
     return GVB_OK;
+}
+
+extern "C" int gvb_cg_solve(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4) {
+    return cg_solve_impl(c, rhs, mu, tau, gam2, max_iter, denoiser, iters, log4, nullptr, nullptr);
+}
+extern "C" int gvb_cg_solve_ex(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
+                               gvb_vec ax_mu, double* dots3) {
+    return cg_solve_impl(c, rhs, mu, tau, gam2, max_iter, denoiser, iters, log4, ax_mu, dots3);
 }

@@ -60,6 +60,8 @@ vamp::vamp(int N, int M, int Mt, double gam1, double gamw, int max_iter, double 
     nranks = gvb_host::world().nranks;
     const char* d = getenv("GVB_DIAG");
     extra_diagnostics = d && d[0] == '1';
+    const char* rs = getenv("GVB_REFERENCE_SWEEPS");
+    reference_sweeps = rs && rs[0] == '1';
 }
 
 vamp::vamp(int M, double gam1, double gamw, std::vector<double> true_signal, int rank, Options opt)
@@ -85,6 +87,8 @@ vamp::vamp(int M, double gam1, double gamw, std::vector<double> true_signal, int
     nranks = gvb_host::world().nranks;
     const char* d = getenv("GVB_DIAG");
     extra_diagnostics = d && d[0] == '1';
+    const char* rs = getenv("GVB_REFERENCE_SWEEPS");
+    reference_sweeps = rs && rs[0] == '1';
 }
 
 vamp::~vamp() { dev_close(); }
@@ -133,10 +137,10 @@ void vamp::dev_denoise(double g1_prec, double* sum_d, double* dist2) {
     *dist2 = sums[1];
 }
 
-int vamp::dev_cg(gvb_vec rhs, gvb_vec mu, double tau, int denoiser) {
+int vamp::dev_cg(gvb_vec rhs, gvb_vec mu, double tau, int denoiser, gvb_vec ax_mu, double* dots3) {
     std::vector<double> log(4 * (size_t)CG_max_iter, 0.0);
     int iters = 0;
-    DEV(gvb_cg_solve(dev.ctx, rhs, mu, tau, gam2, CG_max_iter, denoiser, &iters, log.data()));
+    DEV(gvb_cg_solve_ex(dev.ctx, rhs, mu, tau, gam2, CG_max_iter, denoiser, &iters, log.data(), ax_mu, dots3));
     if (rank == 0) {
         for (int i = 0; i < iters; i++) {
             if (denoiser == 0 && log[4 * i + 3] >= 0 && log[4 * i + 0] >= 0)
@@ -362,9 +366,10 @@ bool vamp::linear_iteration(data* dataset, int it) {
             DEV(gvb_vec_fill(ctx, dev.x2, 0.0));
         else
             DEV(gvb_vec_copy(ctx, dev.x2, dev.mu_last));   // warm start from the previous LMMSE estimate
-        last_cg_iters[0] = dev_cg(dev.rhs, dev.x2, gamw, 1);
+        // A x2_hat falls out of the CG (sum of alpha_k A p_k): updateNoisePrec and err_measures(2) need no sweep of their own
+        last_cg_iters[0] = dev_cg(dev.rhs, dev.x2, gamw, 1, reference_sweeps ? nullptr : dev.tmpN2, nullptr);
         DEV(gvb_vec_copy(ctx, dev.mu_last, dev.x2));
-        dev.ax_x2_valid = false;
+        dev.ax_x2_valid = !reference_sweeps;
         std::string filepath_out_x2 = out_dir + out_name + "_it_" + std::to_string(it) + "_x2_hat.bin";
         store_scaled(dev.x2, filepath_out_x2, scale, S);
         if (rank == 0) std::cout << "x2_hat filepath_out is " << filepath_out_x2 << std::endl;
@@ -490,7 +495,11 @@ double vamp::g2d_onsager(double gam2, double tau, data* dataset) {
     DEV(gvb_vec_upload(dev.ctx, dev.bern, bern_vec.data(), M));
     DEV(gvb_vec_fill(dev.ctx, dev.invq, 0.0));
     this->gam2 = gam2;
-    last_cg_iters[1] = dev_cg(dev.bern, dev.invq, tau, 0);
+    double d3[3] = {0, 0, 0};
+    last_cg_iters[1] = dev_cg(dev.bern, dev.invq, tau, 0, nullptr, d3);
+    // <u, A^T A Q^-1 u> from the solver's own residual: Q mu = u - r  =>  tau A^T A mu = u - r - gam2 mu
+    onsager_u_AtA_invq = (d3[0] - gam2 * d3[1] - d3[2]) / tau;
+    onsager_valid = true;
     gvb_vec xs[1] = {dev.bern}, ys[1] = {dev.invq};
     double dot = 0;
     DEV(gvb_vec_dots(dev.ctx, 1, xs, ys, 1, &dot));
@@ -502,15 +511,22 @@ double vamp::g2d_onsager(double gam2, double tau, data* dataset) {
 // ---------------------------------------------------------------------------------------------------
 void vamp::updateNoisePrec(data* dataset) {
     gvb_ctx* ctx = dev.ctx;
-    DEV(gvb_dAx(ctx, dev.x2, dev.tmpN2));   // also reused by err_measures(2)
-    dev.ax_x2_valid = true;
+    if (!dev.ax_x2_valid) {
+        DEV(gvb_dAx(ctx, dev.x2, dev.tmpN2));   // also reused by err_measures(2)
+        dev.ax_x2_valid = true;
+    }
     double temp_norm2 = 0;
     DEV(gvb_vec_dist2(ctx, dev.tmpN2, dev.y, 0, &temp_norm2));
-    DEV(gvb_dAx(ctx, dev.invq, dev.tmpN));
-    DEV(gvb_dATx(ctx, dev.tmpN, dev.tmpM));
-    gvb_vec xs[1] = {dev.bern}, ys[1] = {dev.tmpM};
     double dot = 0;
-    DEV(gvb_vec_dots(ctx, 1, xs, ys, 1, &dot));
+    if (onsager_valid && !reference_sweeps) {
+        dot = onsager_u_AtA_invq;   // by-product of the Onsager CG (g2d_onsager), no sweep
+    } else {
+        DEV(gvb_dAx(ctx, dev.invq, dev.tmpN));
+        DEV(gvb_dATx(ctx, dev.tmpN, dev.tmpM));
+        gvb_vec xs[1] = {dev.bern}, ys[1] = {dev.tmpM};
+        DEV(gvb_vec_dots(ctx, 1, xs, ys, 1, &dot));
+    }
+    onsager_valid = false;
     double trace_corr = dot * Mt;
     if (rank == 0) {
         std::cout << "l2_norm2(temp) / N = " << temp_norm2 / N << std::endl;

@@ -69,6 +69,11 @@ private:
     std::string freeze_index_file;
     std::vector<double> x1_hat_stored;
     int shard_S = 0;
+    // GVB_REFERENCE_SWEEPS=1: A x2_hat and <u, A^T A Q^-1 u> by their own bed sweeps like the reference (vamp.cpp:897-915) instead
+    // of as by-products of the two CG solves (3 sweeps per iteration less; same values to rounding, tests compare both)
+    bool reference_sweeps = false;
+    bool onsager_valid = false;
+    double onsager_u_AtA_invq = 0;
     bool extra_diagnostics = false;   // GVB_DIAG=1: the reference's "onsager approx"/polynomial prints (3 extra sweeps)
 
     // ---- device-resident state (HBM) ----
@@ -85,7 +90,7 @@ private:
     void dev_open(data* dataset);
     void dev_close();
     void dev_denoise(double g1_prec, double* sum_d, double* dist2);
-    int dev_cg(gvb_vec rhs, gvb_vec mu, double tau, int denoiser);
+    int dev_cg(gvb_vec rhs, gvb_vec mu, double tau, int denoiser, gvb_vec ax_mu = nullptr, double* dots3 = nullptr);
     void sync_host(gvb_vec v, std::vector<double>& h, size_t n);
     void store_scaled(gvb_vec v, const std::string& path, double div, int S);
     double r2_train(gvb_vec ax);

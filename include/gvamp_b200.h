@@ -176,6 +176,13 @@ int gvb_cg_solve(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2,
  * Two bed sweeps, local to the shard (no communication). */
 int gvb_assoc_pvals(gvb_ctx* ctx, gvb_vec yres, gvb_vec coef, gvb_vec select, gvb_vec pvals);
 
+/* The same solver with its by-products (no extra bed sweep; either may be NULL): ax_mu <- A * (returned mu), accumulated from
+ * the A p_k the iterations form anyway (replaces the separate data::Ax(x2_hat) of vamp.cpp:897,1301 and of vamp_probit.cpp:567);
+ * dots3 <- {<rhs,rhs>, <rhs,mu>, <rhs,r>} over all ranks, r = rhs - (tau A^T A + gam2) mu, from which
+ * <rhs, A^T A mu> = (dots3[0] - gam2*dots3[1] - dots3[2]) / tau (replaces the Ax + ATx of vamp.cpp:908-915). */
+int gvb_cg_solve_ex(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters,
+                    double* rel_res, gvb_vec ax_mu, double* dots3);
+
 /* ---- probit z-denoiser ---------------------------------------------------------------------------- */
 /* vamp::g1_bin_class / g1d_bin_class, vamp_probit.cpp:661-726 with erfcx (utilities.cpp:345-409):
  * z1_hat[i] = g(p1[i]); sums[0] = sum_i g'(p1[i]) (i<N); sums[1] = ||z1_hat - p1||^2.  mcov may be NULL. */

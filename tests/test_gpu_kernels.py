@@ -331,3 +331,33 @@ def test_probit_covariate_pass(C, oracle, C_cov):
         assert np.isclose(got0[0], oracle.probit_cov_pass(y, np.zeros(N), Z, eta)[0], rtol=1e-12)
         ctx.probit_cov_apply(dZ, C_cov, eta, dm)
         assert np.allclose(dm.download()[:N], Z @ eta, rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("denoiser,warm", [(1, False), (1, True), (0, False)])
+def test_cg_by_products(C, oracle, denoiser, warm):
+    """gvb_cg_solve_ex: A.mu accumulated from the A p_k of the iterations equals a fresh X.v of the solution, and
+    (<rhs,rhs> - gam2 <rhs,mu> - <rhs,r>)/tau equals <rhs, A^T A mu> by explicit sweeps -- in the LMMSE mode (cold and warm
+    start) and in the Onsager mode, whose exit leaves the residual one update behind (vamp.cpp:1174-1193).  The solution and
+    the iteration count are those of gvb_cg_solve."""
+    N, M = 3000, 2600
+    bed = oracle.synth_bed(41, 0, M, N, miss_rate=0.01)
+    rng = np.random.default_rng(8)
+    tau, gam2 = 2.0, 0.7
+    rhs_h = rng.normal(size=M) if denoiser else (2.0 * rng.integers(0, 2, size=M) - 1.0) / math.sqrt(M)
+    mu0 = rng.normal(size=M) * 0.1 if warm else np.zeros(M)
+    with make_ctx(C, "lut") as ctx:
+        ctx.load_host(bed, N).compute_stats(1.0)
+        rhs, mu, mu_b, ax = ctx.vecM(rhs_h), ctx.vecM(mu0), ctx.vecM(mu0), ctx.vecN()
+        its, _ = ctx.cg_solve(rhs, mu, tau, gam2, 30, denoiser)
+        s0 = ctx.sweeps()
+        its_b, _, d3 = ctx.cg_solve_ex(rhs, mu_b, tau, gam2, 30, denoiser, ax)
+        assert ctx.sweeps() - s0 == 2 * its_b + (2 if warm else 0)            # the by-products cost no sweep
+        assert its_b == its and np.array_equal(mu.download(), mu_b.download())
+        ax_fresh, tmpN, tmpM = ctx.vecN(), ctx.vecN(), ctx.vecM()
+        ctx.dAx(mu_b, ax_fresh)
+        ctx.dATx(ax_fresh, tmpM)
+        explicit = float(np.dot(rhs_h, tmpM.download()[:M]))
+        a, b = ax.download(), ax_fresh.download()
+    assert relerr(a, b) < 1e-6                                                  # two fixed-point evaluations of A.mu
+    assert np.isclose(d3[0], rhs_h @ rhs_h, rtol=1e-12)
+    assert abs((d3[0] - gam2 * d3[1] - d3[2]) / tau - explicit) < 1e-6 * abs(explicit)

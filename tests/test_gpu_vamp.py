@@ -59,6 +59,25 @@ def test_linear_vamp_matches_reference_files(oracle, tmp_path, gen):
     assert np.allclose(alpha2, g["alpha2_log"], rtol=TOL_FINAL)
 
 
+def test_cg_by_products_leave_the_outputs_unchanged(oracle, tmp_path, monkeypatch):
+    """Default run (A x2_hat and the trace term of updateNoisePrec as by-products of the two CG solves) against
+    GVB_REFERENCE_SWEEPS=1 (their own bed sweeps, as the reference does, vamp.cpp:897-915): same files and gamw far inside the
+    tolerance, 3 sweeps per iteration less."""
+    g = golden("vamp_linear.npz")
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GVB_REFERENCE_SWEEPS", mode)
+        (tmp_path / mode).mkdir()
+        outd, log, iters = _run_case(oracle, tmp_path / mode, g, "lut")
+        x1 = np.fromfile(outd + f"g_it_{iters}.bin")
+        gamw = [float(l.split("=")[1]) for l in log.splitlines() if l.startswith("gamw = ")]
+        sweeps = [int(l.split("=")[1]) for l in log.splitlines() if l.startswith("bed sweeps this iteration")]
+        outs[mode] = (x1, np.array(gamw), np.loadtxt(f"{outd}g_R2trains.csv"), np.array(sweeps))
+    assert relerr(outs["0"][0], outs["1"][0]) < 1e-6 and np.allclose(outs["0"][1], outs["1"][1], rtol=1e-6)
+    assert np.allclose(outs["0"][2], outs["1"][2], rtol=1e-6, atol=1e-9)
+    assert np.all(outs["1"][3] - outs["0"][3] == 3)
+
+
 def test_test_mode_r2(oracle, tmp_path):
     """--run-mode test: R2 of an estimate file on a second (test) bed, against the oracle's arithmetic."""
     g = golden("vamp_linear.npz")

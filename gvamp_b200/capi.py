@@ -74,6 +74,7 @@ SIGNATURES = {
     "gvb_lmmse_mult": (ci, [vp, vp, cd, cd, vp]),
     "gvb_cg_solve": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p]),
     "gvb_cg_solve_ex": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, c_f64p]),
+    "gvb_cg_solve_warm": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, vp, ci, c_f64p]),
     "gvb_probit_denoise": (ci, [vp, vp, vp, vp, cd, cd, vp, c_f64p]),
     "gvb_missing_list_entries": (cl, [vp]),
     "gvb_assoc_pvals": (ci, [vp, vp, vp, vp, vp]),
@@ -327,6 +328,14 @@ class Context:
         dots3 = np.zeros(3)
         _chk(self.L.gvb_cg_solve_ex(self.h, rhs.h, mu.h, tau, gam2, max_iter, denoiser, ctypes.byref(it), log.ctypes.data_as(c_f64p),
                                     ax_mu.h if ax_mu is not None else None, dots3.ctypes.data_as(c_f64p)))
+        return it.value, log.reshape(max_iter, 4)[: it.value], dots3
+
+    def cg_solve_warm(self, rhs, mu, tau, gam2, max_iter, denoiser, ax_mu, ata_mu, have_start):
+        it = ci(0)
+        log = np.zeros(4 * max_iter)
+        dots3 = np.zeros(3)
+        _chk(self.L.gvb_cg_solve_warm(self.h, rhs.h, mu.h, tau, gam2, max_iter, denoiser, ctypes.byref(it), log.ctypes.data_as(c_f64p),
+                                      ax_mu.h, ata_mu.h, int(have_start), dots3.ctypes.data_as(c_f64p)))
         return it.value, log.reshape(max_iter, 4)[: it.value], dots3
 
     def probit_denoise(self, p1, y, mcov, tau1, probit_var, z1_hat):

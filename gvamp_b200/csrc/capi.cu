@@ -532,6 +532,19 @@ __global__ void cg_axpy_m_kernel(double* __restrict__ r, const double* __restric
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) r[i] -= alpha * d[i];
 }
 
+// ata = (d - gam2*mu)/tau: A^T A mu out of d = (tau A^T A + gam2) mu;  d = tau*ata + gam2*mu: the way back;
+// ata += alpha (d - gam2 p)/tau: the running A^T A mu next to mu += alpha p
+__global__ void cg_ata_from_d_kernel(double* __restrict__ ata, const double* __restrict__ d, const double* __restrict__ mu, double gam2, double tau, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) ata[i] = (d[i] - gam2 * mu[i]) / tau;
+}
+__global__ void cg_d_from_ata_kernel(double* __restrict__ d, const double* __restrict__ ata, const double* __restrict__ mu, double gam2, double tau, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) d[i] = tau * ata[i] + gam2 * mu[i];
+}
+__global__ void cg_ata_axpy_kernel(double* __restrict__ ata, const double* __restrict__ d, const double* __restrict__ p, double alpha, double gam2, double tau,
+                                   long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) ata[i] += alpha * ((d[i] - gam2 * p[i]) / tau);
+}
+
 static inline int cg_blocks(long n) { return (int)std::max(1l, std::min((n + 1023) / 1024, (long)GVB_RED_BLOCKS)); }
 
 // vamp::precondCG_solver, vamp.cpp:1130-1229.  z = r/diag is never materialised (diag is a constant,
@@ -540,11 +553,16 @@ static inline int cg_blocks(long n) { return (int)std::max(1l, std::min((n + 102
 // By-products (both optional, no extra bed sweep): every iteration already forms A p (the N-vector inside lmmse_mult), so
 // ax_mu = A mu_start + sum_k alpha_k A p_k is A times the returned solution; and dots3 = {<rhs,rhs>, <rhs,mu>, <rhs,r>} with the
 // residual r = rhs - Q mu of the returned mu gives <rhs, A^T A mu> = (dots3[0] - gam2 dots3[1] - dots3[2]) / tau.
+// ata_mu (optional, needs ax_mu) = A^T A mu, accumulated the same way from d_k = Q p_k.  With have_start != 0 the caller passes
+// ax_mu / ata_mu of the START vector (the by-products of the previous solve that produced it, with whatever tau / gam2): the
+// initial residual rhs - (tau ata_mu + gam2 mu) then needs no sweep at all (the warm-started LMMSE solve of vamp.cpp:591-600).
 static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
-                         gvb_vec ax_mu, double* dots3) {
+                         gvb_vec ax_mu, double* dots3, gvb_vec ata_mu = nullptr, int have_start = 0) {
     GVB_ARG(c && rhs && mu && rhs != mu, "vectors");
     GVB_ARG(rhs->cap >= c->Mg_pad * 4 && mu->cap >= c->Mg_pad * 4, "M-vectors from gvb_vec_alloc_M");
     GVB_ARG(!ax_mu || ax_mu->cap >= c->Npad, "ax_mu must be an N-vector from gvb_vec_alloc_N");
+    GVB_ARG(!ata_mu || (ax_mu && ata_mu->cap >= c->Mg_pad * 4 && ata_mu != mu && ata_mu != rhs), "ata_mu needs ax_mu and must be its own M-vector");
+    GVB_ARG(!have_start || ata_mu, "have_start needs ax_mu and ata_mu of the start vector");
     long n = c->M;
     for (int k = 0; k < 3; k++) {
         if (c->cg_ws[k] && c->cg_ws[k]->cap != c->Mg_pad * 4) {   // matrix was reloaded with another shape
@@ -563,12 +581,22 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
     double s2[2];
     // r = rhs - lmmse_mult(mu_start) ; z = r/diag ; p = z
     const long sweeps_before = c->sweeps;
-    CGCHK(lmmse_mult_dev(c, mu, tau, gam2, d, false));
-    if (ax_mu) {   // A mu_start is in the operator's scratch unless the zero-vector shortcut skipped the sweeps
-        if (c->sweeps != sweeps_before)
-            GVB_CUDA(cudaMemcpyAsync(ax_mu->d, c->tmpN2, c->Npad * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-        else
-            GVB_CUDA(cudaMemsetAsync(ax_mu->d, 0, c->Npad * sizeof(double), c->stream));
+    const unsigned nbm = (unsigned)std::min((n + 255) / 256, 1184l);
+    if (have_start) {
+        cg_d_from_ata_kernel<<<nbm, 256, 0, c->stream>>>(d->d, ata_mu->d, mu->d, gam2, tau, n);
+        c->launches++;
+    } else {
+        CGCHK(lmmse_mult_dev(c, mu, tau, gam2, d, false));
+        if (ax_mu) {   // A mu_start is in the operator's scratch unless the zero-vector shortcut skipped the sweeps
+            if (c->sweeps != sweeps_before)
+                GVB_CUDA(cudaMemcpyAsync(ax_mu->d, c->tmpN2, c->Npad * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            else
+                GVB_CUDA(cudaMemsetAsync(ax_mu->d, 0, c->Npad * sizeof(double), c->stream));
+        }
+        if (ata_mu) {
+            cg_ata_from_d_kernel<<<nbm, 256, 0, c->stream>>>(ata_mu->d, d->d, mu->d, gam2, tau, n);
+            c->launches++;
+        }
     }
     const int nbn = (int)std::min((c->Npad + 255) / 256, 1184l);
     double rhs_mu = 0.0;
@@ -593,6 +621,10 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
         if (ax_mu && rz != 0.0) {   // c->tmpN2 still holds A p of this iteration
             cg_axpy_n_kernel<<<nbn, 256, 0, c->stream>>>(ax_mu->d, c->tmpN2, alpha, c->Npad);
             c->launches++;
+            if (ata_mu) {
+                cg_ata_axpy_kernel<<<nbm, 256, 0, c->stream>>>(ata_mu->d, d->d, p->d, alpha, gam2, tau, n);
+                c->launches++;
+            }
         }
         cg_update_mu_kernel<<<nb, 256, 0, c->stream>>>(mu->d, p->d, rhs->d, alpha, n, c->red_partial);
         c->launches++;
@@ -655,4 +687,8 @@ extern "C" int gvb_cg_solve(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, dou
 extern "C" int gvb_cg_solve_ex(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
                                gvb_vec ax_mu, double* dots3) {
     return cg_solve_impl(c, rhs, mu, tau, gam2, max_iter, denoiser, iters, log4, ax_mu, dots3);
+}
+extern "C" int gvb_cg_solve_warm(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
+                                 gvb_vec ax_mu, gvb_vec ata_mu, int have_start, double* dots3) {
+    return cg_solve_impl(c, rhs, mu, tau, gam2, max_iter, denoiser, iters, log4, ax_mu, dots3, ata_mu, have_start);
 }

@@ -100,7 +100,7 @@ void vamp::dev_open(data* dataset) {
     if (dev.ctx == dataset->device() && dev.r1) return;
     dev_close();
     dev.ctx = dataset->device();
-    gvb_vec* mvecs[] = {&dev.r1, &dev.r2, &dev.r2_prev, &dev.x1, &dev.x1_prev, &dev.x2, &dev.mu_last, &dev.rhs, &dev.bern, &dev.invq, &dev.tmpM, &dev.truth, &dev.aty};
+    gvb_vec* mvecs[] = {&dev.r1, &dev.r2, &dev.r2_prev, &dev.x1, &dev.x1_prev, &dev.x2, &dev.mu_last, &dev.rhs, &dev.bern, &dev.invq, &dev.tmpM, &dev.truth, &dev.aty, &dev.ata_x2};
     for (gvb_vec* v : mvecs) DEV(gvb_vec_alloc_M(dev.ctx, v));
     gvb_vec* nvecs[] = {&dev.y, &dev.z1, &dev.tmpN, &dev.tmpN2};
     for (gvb_vec* v : nvecs) DEV(gvb_vec_alloc_N(dev.ctx, v));
@@ -109,7 +109,7 @@ void vamp::dev_open(data* dataset) {
 
 void vamp::dev_close() {
     if (!dev.ctx) return;
-    gvb_vec all[] = {dev.r1, dev.r2, dev.r2_prev, dev.x1, dev.x1_prev, dev.x2, dev.mu_last, dev.rhs, dev.bern, dev.invq, dev.tmpM, dev.truth, dev.aty,
+    gvb_vec all[] = {dev.r1, dev.r2, dev.r2_prev, dev.x1, dev.x1_prev, dev.x2, dev.mu_last, dev.rhs, dev.bern, dev.invq, dev.tmpM, dev.truth, dev.aty, dev.ata_x2,
                      dev.y, dev.z1, dev.tmpN, dev.tmpN2, dev.p1, dev.p2, dev.z1h, dev.z2h, dev.mcov, dev.p1_prev};
     for (gvb_vec v : all)
         if (v) gvb_vec_free(dev.ctx, v);
@@ -137,10 +137,10 @@ void vamp::dev_denoise(double g1_prec, double* sum_d, double* dist2) {
     *dist2 = sums[1];
 }
 
-int vamp::dev_cg(gvb_vec rhs, gvb_vec mu, double tau, int denoiser, gvb_vec ax_mu, double* dots3) {
+int vamp::dev_cg(gvb_vec rhs, gvb_vec mu, double tau, int denoiser, gvb_vec ax_mu, double* dots3, gvb_vec ata_mu, int have_start) {
     std::vector<double> log(4 * (size_t)CG_max_iter, 0.0);
     int iters = 0;
-    DEV(gvb_cg_solve_ex(dev.ctx, rhs, mu, tau, gam2, CG_max_iter, denoiser, &iters, log.data(), ax_mu, dots3));
+    DEV(gvb_cg_solve_warm(dev.ctx, rhs, mu, tau, gam2, CG_max_iter, denoiser, &iters, log.data(), ax_mu, ata_mu, have_start, dots3));
     if (rank == 0) {
         for (int i = 0; i < iters; i++) {
             if (denoiser == 0 && log[4 * i + 3] >= 0 && log[4 * i + 0] >= 0)
@@ -225,6 +225,7 @@ void vamp::linear_begin(data* dataset) {
     const int S = dataset->get_S();
     shard_S = S;
     alpha1 = 0;
+    dev.warm_age = -1;
 
     std::vector<double> yf = dataset->filter_pheno();   // NA phenotypes -> 0
     yf.resize(N, 0.0);
@@ -366,8 +367,16 @@ bool vamp::linear_iteration(data* dataset, int it) {
             DEV(gvb_vec_fill(ctx, dev.x2, 0.0));
         else
             DEV(gvb_vec_copy(ctx, dev.x2, dev.mu_last));   // warm start from the previous LMMSE estimate
-        // A x2_hat falls out of the CG (sum of alpha_k A p_k): updateNoisePrec and err_measures(2) need no sweep of their own
-        last_cg_iters[0] = dev_cg(dev.rhs, dev.x2, gamw, 1, reference_sweeps ? nullptr : dev.tmpN2, nullptr);
+        // A x2_hat falls out of the CG (sum of alpha_k A p_k): updateNoisePrec and err_measures(2) need no sweep of their own.
+        // A^T A x2_hat falls out the same way, and since the next solve starts from this x2_hat, its initial residual needs no
+        // sweep either; every 8th solve re-seeds both from real sweeps so that rounding cannot accumulate over a long run.
+        if (reference_sweeps) {
+            last_cg_iters[0] = dev_cg(dev.rhs, dev.x2, gamw, 1);
+        } else {
+            const int warm = (it > 1 && dev.warm_age >= 0 && dev.warm_age < 8) ? 1 : 0;
+            last_cg_iters[0] = dev_cg(dev.rhs, dev.x2, gamw, 1, dev.tmpN2, nullptr, dev.ata_x2, warm);
+            dev.warm_age = warm ? dev.warm_age + 1 : 0;
+        }
         DEV(gvb_vec_copy(ctx, dev.mu_last, dev.x2));
         dev.ax_x2_valid = !reference_sweeps;
         std::string filepath_out_x2 = out_dir + out_name + "_it_" + std::to_string(it) + "_x2_hat.bin";

@@ -84,13 +84,16 @@ private:
         gvb_vec y = nullptr, z1 = nullptr, tmpN = nullptr, tmpN2 = nullptr;
         gvb_vec p1 = nullptr, p2 = nullptr, z1h = nullptr, z2h = nullptr, mcov = nullptr, p1_prev = nullptr;
         bool ax_x2_valid = false;   // tmpN2 holds Ax(x2) of the current iteration
+        gvb_vec ata_x2 = nullptr;   // A^T A x2_hat, by-product of the LMMSE solve; with tmpN2 it warm-starts the next solve sweep-free
+        int warm_age = -1;          // solves since tmpN2 / ata_x2 were last seeded by real sweeps (-1: not seeded)
         gvb_vec aty = nullptr;      // A^T y: y is constant over the linear model's iterations, so the reference's per-iteration
         bool aty_valid = false;     // sweep (vamp.cpp:588) is done once and reused until y is uploaded again
     } dev;
     void dev_open(data* dataset);
     void dev_close();
     void dev_denoise(double g1_prec, double* sum_d, double* dist2);
-    int dev_cg(gvb_vec rhs, gvb_vec mu, double tau, int denoiser, gvb_vec ax_mu = nullptr, double* dots3 = nullptr);
+    int dev_cg(gvb_vec rhs, gvb_vec mu, double tau, int denoiser, gvb_vec ax_mu = nullptr, double* dots3 = nullptr, gvb_vec ata_mu = nullptr,
+               int have_start = 0);
     void sync_host(gvb_vec v, std::vector<double>& h, size_t n);
     void store_scaled(gvb_vec v, const std::string& path, double div, int S);
     double r2_train(gvb_vec ax);

@@ -183,6 +183,13 @@ int gvb_assoc_pvals(gvb_ctx* ctx, gvb_vec yres, gvb_vec coef, gvb_vec select, gv
 int gvb_cg_solve_ex(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters,
                     double* rel_res, gvb_vec ax_mu, double* dots3);
 
+/* Warm-started variant: ata_mu (M-vector) additionally carries A^T A * mu.  have_start != 0: on entry ax_mu / ata_mu hold A mu and
+ * A^T A mu of the START vector in mu (the outputs of the previous call that produced it; tau / gam2 may have changed since), and
+ * the initial residual of precondCG_solver (vamp.cpp:1141-1146, two sweeps in the reference) is formed from them without a sweep.
+ * On exit both describe the returned mu. */
+int gvb_cg_solve_warm(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters,
+                      double* rel_res, gvb_vec ax_mu, gvb_vec ata_mu, int have_start, double* dots3);
+
 /* ---- probit z-denoiser ---------------------------------------------------------------------------- */
 /* vamp::g1_bin_class / g1d_bin_class, vamp_probit.cpp:661-726 with erfcx (utilities.cpp:345-409):
  * z1_hat[i] = g(p1[i]); sums[0] = sum_i g'(p1[i]) (i<N); sums[1] = ||z1_hat - p1||^2.  mcov may be NULL. */

@@ -361,3 +361,28 @@ def test_cg_by_products(C, oracle, denoiser, warm):
     assert relerr(a, b) < 1e-6                                                  # two fixed-point evaluations of A.mu
     assert np.isclose(d3[0], rhs_h @ rhs_h, rtol=1e-12)
     assert abs((d3[0] - gam2 * d3[1] - d3[2]) / tau - explicit) < 1e-6 * abs(explicit)
+
+
+def test_cg_warm_start_products(C, oracle):
+    """gvb_cg_solve_warm: a second solve (other rhs, tau, gam2) started from the first solve's solution with its A.mu / A^T A.mu
+    by-products forms its initial residual without a sweep, runs the same iterations as gvb_cg_solve from the same start and
+    ends within the fixed-point error of the sweeps; its own by-products match fresh sweeps of its solution."""
+    N, M = 3000, 2600
+    bed = oracle.synth_bed(43, 0, M, N, miss_rate=0.01)
+    rng = np.random.default_rng(9)
+    rhs1, rhs2 = rng.normal(size=M), rng.normal(size=M)
+    with make_ctx(C, "lut") as ctx:
+        ctx.load_host(bed, N).compute_stats(1.0)
+        r1, r2, mu, ax, ata = ctx.vecM(rhs1), ctx.vecM(rhs2), ctx.vecM(), ctx.vecN(), ctx.vecM()
+        ctx.cg_solve_warm(r1, mu, 2.0, 0.7, 30, 1, ax, ata, False)
+        start = mu.download()
+        mu_plain = ctx.vecM(start)
+        its_plain, _ = ctx.cg_solve(r2, mu_plain, 1.5, 0.9, 30, 1)
+        s0 = ctx.sweeps()
+        its, _, _ = ctx.cg_solve_warm(r2, mu, 1.5, 0.9, 30, 1, ax, ata, True)
+        assert ctx.sweeps() - s0 == 2 * its and its == its_plain
+        assert relerr(mu.download(), mu_plain.download()) < 1e-6
+        ax_f, ata_f = ctx.vecN(), ctx.vecM()
+        ctx.dAx(mu, ax_f)
+        ctx.dATx(ax_f, ata_f)
+        assert relerr(ax.download(), ax_f.download()) < 1e-6 and relerr(ata.download(), ata_f.download()) < 1e-6

@@ -62,7 +62,8 @@ def test_linear_vamp_matches_reference_files(oracle, tmp_path, gen):
 def test_cg_by_products_leave_the_outputs_unchanged(oracle, tmp_path, monkeypatch):
     """Default run (A x2_hat and the trace term of updateNoisePrec as by-products of the two CG solves) against
     GVB_REFERENCE_SWEEPS=1 (their own bed sweeps, as the reference does, vamp.cpp:897-915): same files and gamw far inside the
-    tolerance, 3 sweeps per iteration less."""
+    tolerance, 3 sweeps less in the cold-started first iteration and 5 less in the warm-started ones (their initial residual comes
+    from the previous solve's A^T A x2_hat)."""
     g = golden("vamp_linear.npz")
     outs = {}
     for mode in ("0", "1"):
@@ -75,7 +76,8 @@ def test_cg_by_products_leave_the_outputs_unchanged(oracle, tmp_path, monkeypatc
         outs[mode] = (x1, np.array(gamw), np.loadtxt(f"{outd}g_R2trains.csv"), np.array(sweeps))
     assert relerr(outs["0"][0], outs["1"][0]) < 1e-6 and np.allclose(outs["0"][1], outs["1"][1], rtol=1e-6)
     assert np.allclose(outs["0"][2], outs["1"][2], rtol=1e-6, atol=1e-9)
-    assert np.all(outs["1"][3] - outs["0"][3] == 3)
+    saved = outs["1"][3] - outs["0"][3]
+    assert saved[0] == 3 and np.all(saved[1:] == 5), saved
 
 
 def test_test_mode_r2(oracle, tmp_path):

@@ -204,6 +204,49 @@ def case_vamp_probit(tmp):
         fh.write("\n".join(l for l in log.splitlines() if not l.startswith("[CG")) + "\n")
 
 
+def case_config1(tmp):
+    """BASELINE.json configs[0]: synthetic N=10,000 x M=20,000, h2=0.5, CV=2,000, linear model, 10 iterations of the reference's
+    main_real.exe (MANVECT build = the reference's own build line; 1 rank through the MPI shim instead of mpirun -np 2, which only
+    changes summation order and the Onsager probe's seed offset S).  Stored: what the north_star bounds -- the final signal
+    estimate, the learned prior, gamw, and the per-iteration scalars; the 50 MB bed is regenerated from the seed."""
+    N, M, seed, h2, CV, iters = 10_000, 20_000, 101, 0.5, 2000, 10
+    bed = O.synth_bed(seed, 0, M, N)
+    bedp = os.path.join(tmp, "c1.bed")
+    O.write_bed(bedp, bed)
+    ds0 = O.Dataset(bed, N)
+    beta = O.synth_beta(seed, M, CV, h2)
+    y = ds0.Ax(beta * math.sqrt(N))[:N] + O.synth_noise(seed, N, h2)
+    phenp = os.path.join(tmp, "c1.phen")
+    O.write_phen(phenp, y)
+    outd = os.path.join(tmp, "c1out") + "/"
+    probs, vars_ = [0.9, 0.05, 0.03, 0.02], [0, 1e-5, 1e-4, 1e-3]     # Mt <= 50000: the prior must be passed (utilities.cpp:98-99)
+    args = ["--run-mode", "infere", "--model", "linear", "--bed-file", bedp, "--phen-files", phenp, "--N", str(N), "--Mt", str(M),
+            "--out-dir", outd, "--out-name", "c1", "--iterations", str(iters), "--CG-max-iter", "20", "--rho", "0.5",
+            "--probs", ",".join(map(str, probs)), "--vars", ",".join(map(str, vars_)), "--h2", str(h2), "--seed", "1"]
+    env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count()))
+    import time
+    t0 = time.time()
+    log = subprocess.run([R.exe("main_real_manvect.exe")] + args, check=True, capture_output=True, text=True, env=env).stdout
+    wall = time.time() - t0
+    it_times = [float(l.split("=")[1]) for l in log.splitlines() if l.startswith("total iteration time")]
+    n_it = len([f for f in os.listdir(outd) if f.startswith("c1_it_") and f.endswith(".bin") and "x2" not in f])
+    out = dict(N=N, M=M, seed=seed, h2=h2, CV=CV, iterations=iters, iterations_done=n_it, args=np.array(args[8:]),
+               y=y.astype(np.float32).astype(np.float64) * 0 + y, ref_wall_s=wall, ref_iter_s=np.array(it_times), ref_threads=os.cpu_count())
+    out["x1_last"] = np.fromfile(f"{outd}c1_it_{n_it}.bin")
+    out["x1_first"] = np.fromfile(f"{outd}c1_it_1.bin")
+    out["x1_mid"] = np.fromfile(f"{outd}c1_it_{max(1, n_it // 2)}.bin")
+    for nm in ("gam1s", "gam2s", "R2trains"):
+        out[nm] = np.loadtxt(f"{outd}c1_{nm}.csv")
+    gamw = [float(l.split("=")[1]) for l in log.splitlines() if l.startswith("gamw = ")]
+    alpha2 = [float(l.split("=")[1]) for l in log.splitlines() if l.startswith("alpha2 = ")]
+    pv = [np.array(l.split("=")[1].split(), dtype=float) for l in log.splitlines() if l.startswith("prior variances")]
+    pp = [np.array(l.split("=")[1].split(), dtype=float) for l in log.splitlines() if l.startswith("prior probabilities")]
+    out.update(gamw_log=np.array(gamw), alpha2_log=np.array(alpha2), prior_vars_last=pv[-1], prior_probs_last=pp[-1])
+    np.savez_compressed(os.path.join(OUT, "config1.npz"), **out)
+    print(f"config1: reference wall {wall:.1f} s, iterations {n_it}, per-iteration {it_times}")
+    print("R2trains", out["R2trains"], "gamw", gamw)
+
+
 def case_pvals(tmp):
     """LOO and LOCO association p-values (data.cpp:1108-1353) on the N=1003 case (2 % missing genotypes, phenotype NAs)
     with a 5-chromosome .bim (incl. "X" -> 23).  The Student-t tail comes from oracle/shims (incomplete beta), which the
@@ -246,4 +289,5 @@ if __name__ == "__main__":
         case_vamp_linear(tmp)
         case_vamp_probit(tmp)
         case_pvals(tmp)
+        case_config1(tmp)
     print("golden vectors written to", OUT)

@@ -386,3 +386,24 @@ def test_cg_warm_start_products(C, oracle):
         ctx.dAx(mu, ax_f)
         ctx.dATx(ax_f, ata_f)
         assert relerr(ax.download(), ax_f.download()) < 1e-6 and relerr(ata.download(), ata_f.download()) < 1e-6
+
+
+def test_more_than_2M_individuals(C, oracle):
+    """N >= 2^21: the packed 21-bit counters of the statistics walk do not apply and the popcount kernel takes over; 17188
+    stripes, 68 individual blocks of the missing-genotype list, M = 9 (one full marker group + one ragged)."""
+    N, M = 2_200_003, 9
+    bed = oracle.synth_bed(51, 0, M, N, miss_rate=0.005)
+    ds = oracle.Dataset(bed, N)
+    rng = np.random.default_rng(51)
+    v, u = rng.normal(size=M), rng.normal(size=N)
+    with make_ctx(C, "lut") as ctx:
+        ctx.load_host(bed, N).compute_stats(1.0)
+        assert np.array_equal(ctx.counts(), ds.counts())
+        mave, msig = ctx.stats()
+        ax, atx = ctx.Ax(v), ctx.ATx(u)
+        assert ctx.missing_list_entries() >= ds.counts()[:, 5].sum() > 0
+        assert np.array_equal(ctx.decode(0, M), bed)
+    # the oracle adds 2.2M squared deviations one by one like the reference; the closed form from the exact counts is the more
+    # accurate of the two, hence 1e-10 here instead of the 1e-11 of the small cases
+    assert relerr(mave, ds.mave) < 1e-13 and relerr(msig, ds.msig) < 1e-10
+    assert relerr(ax, ds.Ax(v)) < TOL_MATVEC and relerr(atx, ds.ATx(u)) < TOL_MATVEC

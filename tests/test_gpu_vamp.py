@@ -59,6 +59,40 @@ def test_linear_vamp_matches_reference_files(oracle, tmp_path, gen):
     assert np.allclose(alpha2, g["alpha2_log"], rtol=TOL_FINAL)
 
 
+def test_config1_matches_reference(oracle, tmp_path):
+    """BASELINE.json configs[0] end to end: N=10,000 x M=20,000, h2=0.5, CV=2,000, linear, 10 iterations, against the output of
+    the reference's own main_real.exe (MANVECT build, tests/golden/config1.npz): signal estimate of the first, a middle and the
+    final iteration, per-iteration gam1 / gam2 / R2, gamw, Onsager alpha2 and the learned prior within 1e-4 (north_star)."""
+    g = golden("config1.npz")
+    N, M, iters = int(g["N"]), int(g["M"]), int(g["iterations_done"])
+    bed = oracle.synth_bed(int(g["seed"]), 0, M, N)
+    bedp, phenp = str(tmp_path / "c1.bed"), str(tmp_path / "c1.phen")
+    oracle.write_bed(bedp, bed)
+    oracle.write_phen(phenp, g["y"])
+    outd = str(tmp_path / "c1out") + "/"
+    args = ["--run-mode", "infere", "--model", "linear", "--bed-file", bedp, "--phen-files", phenp, "--N", str(N), "--Mt", str(M),
+            "--out-dir", outd, "--out-name", "c1"]
+    extra = [str(a) for a in g["args"]]
+    skip = {"--N", "--Mt", "--out-dir", "--out-name"}
+    for k in range(0, len(extra), 2):
+        if extra[k] not in skip:
+            args += [extra[k], extra[k + 1]]
+    r = subprocess.run([EXE] + args, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    log = r.stdout
+    for key, it in (("x1_first", 1), ("x1_mid", max(1, iters // 2)), ("x1_last", iters)):
+        got = np.fromfile(outd + f"c1_it_{it}.bin")
+        assert relerr(got, g[key]) < TOL_FINAL, (key, relerr(got, g[key]))
+    for nm in ("gam1s", "gam2s", "R2trains"):
+        assert np.allclose(np.loadtxt(f"{outd}c1_{nm}.csv"), g[nm], rtol=TOL_FINAL, atol=1e-6), nm
+    gamw = [float(l.split("=")[1]) for l in log.splitlines() if l.startswith("gamw = ")]
+    alpha2 = [float(l.split("=")[1]) for l in log.splitlines() if l.startswith("alpha2 = ")]
+    assert np.allclose(gamw, g["gamw_log"], rtol=TOL_FINAL) and np.allclose(alpha2, g["alpha2_log"], rtol=TOL_FINAL)
+    pv = [np.array(l.split("=")[1].split(), dtype=float) for l in log.splitlines() if l.startswith("prior variances")]
+    pp = [np.array(l.split("=")[1].split(), dtype=float) for l in log.splitlines() if l.startswith("prior probabilities")]
+    assert np.allclose(pv[-1], g["prior_vars_last"], rtol=TOL_FINAL) and np.allclose(pp[-1], g["prior_probs_last"], rtol=TOL_FINAL)
+
+
 def test_cg_by_products_leave_the_outputs_unchanged(oracle, tmp_path, monkeypatch):
     """Default run (A x2_hat and the trace term of updateNoisePrec as by-products of the two CG solves) against
     GVB_REFERENCE_SWEEPS=1 (their own bed sweeps, as the reference does, vamp.cpp:897-915): same files and gamw far inside the

@@ -159,3 +159,23 @@ def test_pvals_loo_loco(oracle):
     loco = oracle.pvals_loco(ds, g["z1"], g["y_filtered"], g["x1"], g["chrom"])
     assert np.allclose(loo, g["pvals_loo"], rtol=1e-9, atol=0) and np.allclose(loco, g["pvals_loco"], rtol=1e-9, atol=0)
     assert g["pvals_loo"].min() < 1e-50 and g["pvals_loo"].max() > 0.9       # the case spans the whole range
+
+
+def test_config1_end_to_end(oracle):
+    """The restatement at BASELINE.json configs[0] (N=10,000 x M=20,000, 10 iterations) against the reference's own
+    main_real.exe (MANVECT build): the oracle that the GPU parity tests lean on is pinned at the headline CPU config too.
+    Only the first half of the 10 iterations is replayed (about a minute of CPU); the GPU test compares all ten."""
+    g = golden("config1.npz")
+    N, M, iters = int(g["N"]), int(g["M"]), max(1, int(g["iterations_done"]) // 2)
+    bed = oracle.synth_bed(int(g["seed"]), 0, M, N)
+    y = g["y"]
+    avg = float(np.cumsum(y)[-1]) / N
+    sqn = math.sqrt((N - 1) / float(np.cumsum((y - avg) * (y - avg))[-1]))
+    ds = oracle.Dataset(bed, N, phen=y * sqn)
+    cfg = oracle.VampConfig(iterations=iters, rho=0.5, probs=(0.9, 0.05, 0.03, 0.02), vars=(0, 1e-5, 1e-4, 1e-3), CG_max_iter=20,
+                            gamw=1.0 / (1.0 - float(g["h2"])), seed=1)
+    tr = oracle.infere_linear(ds, cfg)
+    for key, it in (("x1_first", 1), ("x1_mid", iters)):
+        assert relerr(tr.x1_hat[it - 1], g[key]) < 1e-7, (key, relerr(tr.x1_hat[it - 1], g[key]))
+    assert np.allclose(tr.gam1s, g["gam1s"][:iters], rtol=1e-5) and np.allclose(tr.gam2s, g["gam2s"][:iters], rtol=1e-5)
+    assert np.allclose(tr.gamw, g["gamw_log"][1::2][:iters], rtol=1e-5)

@@ -62,6 +62,8 @@ vamp::vamp(int N, int M, int Mt, double gam1, double gamw, int max_iter, double 
     extra_diagnostics = d && d[0] == '1';
     const char* rs = getenv("GVB_REFERENCE_SWEEPS");
     reference_sweeps = rs && rs[0] == '1';
+    const char* ow = getenv("GVB_ONSAGER_WARM");
+    onsager_warm = !(ow && ow[0] == '0') && !reference_sweeps;
 }
 
 vamp::vamp(int M, double gam1, double gamw, std::vector<double> true_signal, int rank, Options opt)
@@ -89,6 +91,8 @@ vamp::vamp(int M, double gam1, double gamw, std::vector<double> true_signal, int
     extra_diagnostics = d && d[0] == '1';
     const char* rs = getenv("GVB_REFERENCE_SWEEPS");
     reference_sweeps = rs && rs[0] == '1';
+    const char* ow = getenv("GVB_ONSAGER_WARM");
+    onsager_warm = !(ow && ow[0] == '0') && !reference_sweeps;
 }
 
 vamp::~vamp() { dev_close(); }
@@ -100,16 +104,16 @@ void vamp::dev_open(data* dataset) {
     if (dev.ctx == dataset->device() && dev.r1) return;
     dev_close();
     dev.ctx = dataset->device();
-    gvb_vec* mvecs[] = {&dev.r1, &dev.r2, &dev.r2_prev, &dev.x1, &dev.x1_prev, &dev.x2, &dev.mu_last, &dev.rhs, &dev.bern, &dev.invq, &dev.tmpM, &dev.truth, &dev.aty, &dev.ata_x2};
+    gvb_vec* mvecs[] = {&dev.r1, &dev.r2, &dev.r2_prev, &dev.x1, &dev.x1_prev, &dev.x2, &dev.mu_last, &dev.rhs, &dev.bern, &dev.invq, &dev.tmpM, &dev.truth, &dev.aty, &dev.ata_x2, &dev.ata_invq};
     for (gvb_vec* v : mvecs) DEV(gvb_vec_alloc_M(dev.ctx, v));
-    gvb_vec* nvecs[] = {&dev.y, &dev.z1, &dev.tmpN, &dev.tmpN2};
+    gvb_vec* nvecs[] = {&dev.y, &dev.z1, &dev.tmpN, &dev.tmpN2, &dev.ax_invq};
     for (gvb_vec* v : nvecs) DEV(gvb_vec_alloc_N(dev.ctx, v));
     if ((int)true_signal.size() == M) DEV(gvb_vec_upload(dev.ctx, dev.truth, true_signal.data(), M));
 }
 
 void vamp::dev_close() {
     if (!dev.ctx) return;
-    gvb_vec all[] = {dev.r1, dev.r2, dev.r2_prev, dev.x1, dev.x1_prev, dev.x2, dev.mu_last, dev.rhs, dev.bern, dev.invq, dev.tmpM, dev.truth, dev.aty, dev.ata_x2,
+    gvb_vec all[] = {dev.r1, dev.r2, dev.r2_prev, dev.x1, dev.x1_prev, dev.x2, dev.mu_last, dev.rhs, dev.bern, dev.invq, dev.tmpM, dev.truth, dev.aty, dev.ata_x2, dev.ata_invq, dev.ax_invq,
                      dev.y, dev.z1, dev.tmpN, dev.tmpN2, dev.p1, dev.p2, dev.z1h, dev.z2h, dev.mcov, dev.p1_prev};
     for (gvb_vec v : all)
         if (v) gvb_vec_free(dev.ctx, v);
@@ -226,6 +230,7 @@ void vamp::linear_begin(data* dataset) {
     shard_S = S;
     alpha1 = 0;
     dev.warm_age = -1;
+    dev.onsager_age = -1;
 
     std::vector<double> yf = dataset->filter_pheno();   // NA phenotypes -> 0
     yf.resize(N, 0.0);
@@ -502,10 +507,17 @@ double vamp::g2d_onsager(double gam2, double tau, data* dataset) {
     bern_vec.assign(M, 0.0);
     for (int i = 0; i < M; i++) bern_vec[i] = (2 * bern(rd) - 1) / sqrt(Mt);
     DEV(gvb_vec_upload(dev.ctx, dev.bern, bern_vec.data(), M));
-    DEV(gvb_vec_fill(dev.ctx, dev.invq, 0.0));
     this->gam2 = gam2;
     double d3[3] = {0, 0, 0};
-    last_cg_iters[1] = dev_cg(dev.bern, dev.invq, tau, 0, nullptr, d3);
+    if (onsager_warm) {
+        const int warm = (dev.onsager_age >= 0 && dev.onsager_age < 8) ? 1 : 0;
+        if (!warm) DEV(gvb_vec_fill(dev.ctx, dev.invq, 0.0));
+        last_cg_iters[1] = dev_cg(dev.bern, dev.invq, tau, 0, dev.ax_invq, d3, dev.ata_invq, warm);
+        dev.onsager_age = warm ? dev.onsager_age + 1 : 0;
+    } else {
+        DEV(gvb_vec_fill(dev.ctx, dev.invq, 0.0));
+        last_cg_iters[1] = dev_cg(dev.bern, dev.invq, tau, 0, nullptr, d3);
+    }
     // <u, A^T A Q^-1 u> from the solver's own residual: Q mu = u - r  =>  tau A^T A mu = u - r - gam2 mu
     onsager_u_AtA_invq = (d3[0] - gam2 * d3[1] - d3[2]) / tau;
     onsager_valid = true;

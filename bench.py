@@ -5,8 +5,9 @@
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU implementation
 
 A "step" is ONE linear-model gVAMP iteration (denoiser + EM prior update, z1 = X.x1, LMMSE by
-preconditioned CG, Onsager trace estimate by a second CG, noise-precision update) over a synthetic
-genotype matrix that lives in HBM.  Default workload `c4shard`: N = 400,000 individuals and 275,000
+preconditioned CG, Onsager trace estimate by a second CG, noise-precision update; every output of the
+reference's iteration is produced, A.x2_hat and the trace term of the noise precision as by-products of
+the two solves) over a synthetic genotype matrix that lives in HBM.  Default workload `c4shard`: N = 400,000 individuals and 275,000
 markers PER GPU (27.5 GB packed), i.e. BASELINE.json's config 4 (N=400k, Mt=2.2M) marker-sharded over 8
 GPUs; at fewer GPUs the total marker count shrinks with the GPU count (weak scaling) because the full
 220 GB matrix does not fit one 180 GB part.  `value` is iterations/s scaled by Mt/2.2M so that it is a

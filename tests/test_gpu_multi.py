@@ -18,3 +18,46 @@ def test_two_rank_parity():
            "29511", os.path.join(ROOT, "tests", "mgpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "mgpu_check ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_main_real_two_ranks(tmp_path):
+    """The product executable itself, two ranks started by `torchrun --no-python`: its own NCCL rendezvous
+    (host/comm.cpp), marker sharding by divide_work, every rank writing its slice of the output files at byte offset S*8.
+    A multi-rank run is not bit-comparable with a single-rank one - the Onsager probe of shard S is drawn from mt19937{seed+S}
+    in the reference too (vamp.cpp:875) - so the two-rank result is held against the one-rank run of the same binary at the
+    statistical accuracy of that probe (iteration 1 returns x1_hat = 0 in both, the probe enters from iteration 1's LMMSE step on)."""
+    import numpy as np
+    from gvamp_b200 import capi
+    from oracle import oracle
+    from conftest import golden
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    g = golden("vamp_linear.npz")
+    N, M, iters = int(g["N"]), int(g["M"]), int(g["iterations"])
+    bed = oracle.synth_bed(int(g["seed"]), 0, M, N)
+    bedp, phenp = str(tmp_path / "v.bed"), str(tmp_path / "v.phen")
+    oracle.write_bed(bedp, bed)
+    oracle.write_phen(phenp, g["y"])
+    exe = os.path.join(ROOT, "gvamp_b200", "bin", "main_real")
+    extra = [str(a) for a in g["args"]]
+    res = {}
+    for world in (1, 2):
+        outd = str(tmp_path / f"out{world}") + "/"
+        args = ["--run-mode", "infere", "--model", "linear", "--bed-file", bedp, "--phen-files", phenp, "--N", str(N), "--Mt", str(M), "--out-dir", outd,
+                "--out-name", "g"]
+        for k in range(0, len(extra), 2):
+            if extra[k] not in {"--N", "--Mt", "--out-dir", "--out-name"}:
+                args += [extra[k], extra[k + 1]]
+        cmd = [exe] + args if world == 1 else [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", "--nproc-per-node", "2",
+                                                "--master-addr", "127.0.0.1", "--master-port", "29517", exe] + args
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        res[world] = (np.fromfile(outd + "g_it_1.bin"), np.fromfile(outd + f"g_it_{iters}.bin"), np.loadtxt(outd + "g_R2trains.csv"))
+    for world in (1, 2):
+        assert res[world][0].shape == (M,) and res[world][1].shape == (M,)
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert not res[2][0].any() and not res[1][0].any()
+    assert rel(res[2][1], res[1][1]) < 0.05 and np.corrcoef(res[2][1], res[1][1])[0, 1] > 0.995
+    # the R2 trajectories wander apart by a few 0.01 in the middle iterations (M = 2000: the probe's noise is 1/sqrt(M) = 2 %)
+    # and meet again at the end
+    assert abs(res[2][2][-1] - res[1][2][-1]) < 0.03 and np.allclose(res[2][2], res[1][2], atol=0.08)

@@ -75,6 +75,8 @@ SIGNATURES = {
     "gvb_cg_solve": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p]),
     "gvb_cg_solve_ex": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, c_f64p]),
     "gvb_cg_solve_warm": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, vp, ci, c_f64p]),
+    "gvb_people_stats": (ci, [vp, vp, vp, vp]),
+    "gvb_cg_solve_aat": (ci, [vp, vp, vp, cd, cd, vp, vp, vp, ci, ctypes.POINTER(ci), c_f64p]),
     "gvb_probit_denoise": (ci, [vp, vp, vp, vp, cd, cd, vp, c_f64p]),
     "gvb_missing_list_entries": (cl, [vp]),
     "gvb_assoc_pvals": (ci, [vp, vp, vp, vp, vp]),
@@ -337,6 +339,18 @@ class Context:
         _chk(self.L.gvb_cg_solve_warm(self.h, rhs.h, mu.h, tau, gam2, max_iter, denoiser, ctypes.byref(it), log.ctypes.data_as(c_f64p),
                                       ax_mu.h, ata_mu.h, int(have_start), dots3.ctypes.data_as(c_f64p)))
         return it.value, log.reshape(max_iter, 4)[: it.value], dots3
+
+    def people_stats(self):
+        a, s, n = self.vecN(), self.vecN(), self.vecN()
+        _chk(self.L.gvb_people_stats(self.h, a.h, s.h, n.h))
+        return a, s, n
+
+    def cg_solve_aat(self, rhs, mu, tau, gam2, people, max_iter):
+        it = ci(0)
+        log = np.zeros(3 * max_iter)
+        _chk(self.L.gvb_cg_solve_aat(self.h, rhs.h, mu.h, tau, gam2, people[0].h, people[1].h, people[2].h, max_iter, ctypes.byref(it),
+                                     log.ctypes.data_as(c_f64p)))
+        return it.value, log.reshape(max_iter, 3)[: it.value]
 
     def probit_denoise(self, p1, y, mcov, tau1, probit_var, z1_hat):
         sums = np.empty(2)

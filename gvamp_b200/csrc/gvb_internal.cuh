@@ -163,7 +163,7 @@ int gvb_ax_simple(gvb_ctx* c, const double* v, double* out);
 int gvb_atx_simple(gvb_ctx* c, const double* u, double* out);
 int gvb_ax_lut(gvb_ctx* c, const double* v, double* out);
 int gvb_atx_lut(gvb_ctx* c, const double* u, double* out);
-int gvb_ax_tile(gvb_ctx* c, const double* v, double* out);     // gen-2 sweeps (matvec_tile.cu)
+int gvb_ax_tile(gvb_ctx* c, const double* v, double* out, int mode = 0);     // gen-2 sweeps (matvec_tile.cu); mode: ax_code_values
 int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB = nullptr);   // outB[j] = sum_i b_ij u_i (optional)
 int gvb_count_tile_main(gvb_ctx* c, const int* tab, unsigned long long* acc);
 void gvb_misslist_reset(gvb_ctx* c);                                   // misslist.cu

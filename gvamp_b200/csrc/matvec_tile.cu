@@ -467,11 +467,28 @@ __device__ __forceinline__ int dosage_of(unsigned code) { return code == 0u ? 2 
 // ---- X . v ----------------------------------------------------------------------------------------
 // pass 1 (one block per marker tile of 128): bound = max over tiles of sum_j max_c |val_j(c)|, the largest |table entry
 // sum| a 32-lookup window can see; also clears the int64 accumulators of the individuals
+// The three per-code values of marker j that the table walk sums over the markers (missing -> 0 in every mode):
+//   mode 0: (a(c) - mu_j) sigma_j v_j          X.v, data::Ax
+//   mode 1: 1                                   number of non-missing genotypes of an individual (numb_people, data.cpp:585)
+//   mode 2: ((a(c) - mu_j) sigma_j)^2           sum of squared standardised genotypes of an individual (msig_people, data.cpp:586)
+__device__ __forceinline__ void ax_code_values(int mode, double vj, double mu, double sg, double& v00, double& v10, double& v11) {
+    if (mode == 1) {
+        v00 = v10 = v11 = (sg != 0.0) ? 1.0 : 0.0;   // padded markers carry sigma = 0 and must stay out
+    } else {
+        const double w = (mode == 0) ? sg * vj : sg;
+        v00 = (2.0 - mu) * w;
+        v10 = (1.0 - mu) * w;
+        v11 = -mu * w;
+        if (mode == 2) { v00 *= v00; v10 *= v10; v11 *= v11; }
+    }
+}
+
 __global__ void __launch_bounds__(128) ax_prep_kernel(const double* __restrict__ v, const double* __restrict__ mave, const double* __restrict__ msig,
-                                                      double* __restrict__ scal, unsigned long long* __restrict__ accN, long Npad) {
+                                                      double* __restrict__ scal, unsigned long long* __restrict__ accN, long Npad, int mode) {
     const long j = blockIdx.x * 128l + threadIdx.x;
-    const double w = msig[j] * v[j], mu = mave[j];
-    double e = fmax(fmax(fabs((2.0 - mu) * w), fabs(mu * w)), fabs((1.0 - mu) * w));
+    double v00, v10, v11;
+    ax_code_values(mode, v ? v[j] : 1.0, mave[j], msig[j], v00, v10, v11);
+    double e = fmax(fmax(fabs(v00), fabs(v11)), fabs(v10));
     __shared__ double sm[4];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
@@ -484,7 +501,7 @@ __global__ void __launch_bounds__(128) ax_prep_kernel(const double* __restrict__
 // pass 2 (one block per marker tile): tabv[(T*256 + e)*32 + s] = sum_q Q_{4g+q}(c_q(e)), g = 32 T + s,
 // Q_j(c) = rint(val_j(c) * scale), val_j(00) = (2-mu) w, val_j(10) = (1-mu) w, val_j(11) = -mu w, val_j(missing) = 0
 __global__ void __launch_bounds__(256) ax_build_kernel(const double* __restrict__ v, const double* __restrict__ mave, const double* __restrict__ msig,
-                                                       double* __restrict__ scal, int* __restrict__ tabv) {
+                                                       double* __restrict__ scal, int* __restrict__ tabv, int mode) {
     __shared__ int Qs[4][4][32];   // [q][code][slot]: a warp reads one (q, code) row -> conflict free
     __shared__ double s_scale;
     const long T = blockIdx.x;
@@ -500,11 +517,13 @@ __global__ void __launch_bounds__(256) ax_build_kernel(const double* __restrict_
     if (threadIdx.x < 128) {
         const long j = T * 128 + threadIdx.x;
         const int s = threadIdx.x >> 2, q = threadIdx.x & 3;
-        const double w = msig[j] * v[j], mu = mave[j], sc = s_scale;
-        Qs[q][0][s] = (int)rint((2.0 - mu) * w * sc);
+        const double sc = s_scale;
+        double v00, v10, v11;
+        ax_code_values(mode, v ? v[j] : 1.0, mave[j], msig[j], v00, v10, v11);
+        Qs[q][0][s] = (int)rint(v00 * sc);
         Qs[q][1][s] = 0;
-        Qs[q][2][s] = (int)rint((1.0 - mu) * w * sc);
-        Qs[q][3][s] = (int)rint(-mu * w * sc);
+        Qs[q][2][s] = (int)rint(v10 * sc);
+        Qs[q][3][s] = (int)rint(v11 * sc);
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -644,17 +663,19 @@ int atx_main(gvb_ctx* c, const int* tab, unsigned long long* acc) {
 
 }   // namespace
 
-// X . v of the local shard (reference data::Ax, data.cpp:848-1011, before its MPI_Allreduce): 4 launches
-int gvb_ax_tile(gvb_ctx* c, const double* v, double* out) {
+// X . v of the local shard (reference data::Ax, data.cpp:848-1011, before its MPI_Allreduce): 4 launches.
+// mode 1 / 2 (v unused, may be NULL): the per-individual sums of compute_people_statistics, unscaled (see ax_code_values).
+int gvb_ax_tile(gvb_ctx* c, const double* v, double* out, int mode) {
     GVB_CHECK(ensure_scratch(c, false, true, false));
     const long n_tiles = c->Mg_pad / 32;
     unsigned long long* accN = c->acc_i64 + 2 * (size_t)c->Mg_pad * 4;
-    ax_prep_kernel<<<(unsigned)n_tiles, 128, 0, c->stream>>>(v, c->mave, c->msig, c->scal, accN, c->Npad);
+    ax_prep_kernel<<<(unsigned)n_tiles, 128, 0, c->stream>>>(v, c->mave, c->msig, c->scal, accN, c->Npad, mode);
     GVB_LAUNCHED(c);
-    ax_build_kernel<<<(unsigned)n_tiles, 256, 0, c->stream>>>(v, c->mave, c->msig, c->scal, c->tab_v);
+    ax_build_kernel<<<(unsigned)n_tiles, 256, 0, c->stream>>>(v, c->mave, c->msig, c->scal, c->tab_v, mode);
     GVB_LAUNCHED(c);
     GVB_CHECK(ax_main(c, accN));
-    ax_finish_kernel<<<(unsigned)((c->Npad + 255) / 256), 256, 0, c->stream>>>(accN, c->scal, c->maskw, c->Npad, 1.0 / sqrt((double)c->N), out);
+    ax_finish_kernel<<<(unsigned)((c->Npad + 255) / 256), 256, 0, c->stream>>>(accN, c->scal, c->maskw, c->Npad,
+                                                                               mode == 0 ? 1.0 / sqrt((double)c->N) : 1.0, out);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }

@@ -91,6 +91,8 @@ data::data(gvb_ctx* resident, std::vector<double> y, const int N, const int M, c
 }
 
 data::~data() {
+    for (gvb_vec& v : people)
+        if (v && ctx) { gvb_vec_free(ctx, v); v = nullptr; }
     if (mave) _mm_free(mave);
     if (msig) _mm_free(msig);
     if (ctx && owns_ctx) {
@@ -195,6 +197,22 @@ void data::compute_markers_statistics() {
     if (gvb_compute_stats(ctx, alpha_scale) != GVB_OK) device_fatal("marker statistics failed");
     if (gvb_get_stats(ctx, mave, msig) != GVB_OK) device_fatal("marker statistics download failed");
     if (rank == 0) std::cout << "rank = " << rank << ": statistics took " << gvb_host::wtime() - start << " seconds to run." << std::endl;
+}
+
+// per-individual statistics over all markers of all shards (data.cpp:548-640): three X.v-type sweeps on the device
+void data::compute_people_statistics() {
+    double start = gvb_host::wtime();
+    for (int k = 0; k < 3; k++)
+        if (!people[k] && gvb_vec_alloc_N(ctx, &people[k]) != GVB_OK) device_fatal("device vector allocation failed");
+    if (gvb_people_stats(ctx, people[0], people[1], people[2]) != GVB_OK) device_fatal("people statistics failed");
+    mave_people.assign(4 * mbytes, 0.0);
+    msig_people.assign(4 * mbytes, 0.0);
+    numb_people.assign(4 * mbytes, 0.0);
+    if (gvb_vec_download(ctx, people[0], mave_people.data(), 4 * (long)mbytes) != GVB_OK ||
+        gvb_vec_download(ctx, people[1], msig_people.data(), 4 * (long)mbytes) != GVB_OK ||
+        gvb_vec_download(ctx, people[2], numb_people.data(), 4 * (long)mbytes) != GVB_OK)
+        device_fatal("people statistics download failed");
+    if (rank == 0) std::cout << "rank = " << rank << ": people statistics took " << gvb_host::wtime() - start << " seconds to run." << std::endl;
 }
 
 unsigned char* data::get_bed_data() {

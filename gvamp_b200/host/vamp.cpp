@@ -182,10 +182,7 @@ void vamp::prepare(data* dataset) {
     y = dataset->get_phen();
     // the design matrix is scaled by 1/sqrt(N), so the effect variances are scaled by N
     for (double& v : vars) v *= N;
-    if (reverse == 1) {
-        std::cout << "FATAL: --use-XXT-denoiser 1 (N x N LMMSE) is outside the B200 hot path and not built" << std::endl;
-        exit(EXIT_FAILURE);
-    }
+    if (reverse == 1) dataset->compute_people_statistics();   // vamp.cpp:168-170
     if (redglob != 0 || use_freeze != 0) {
         std::cout << "FATAL: --red / --use-freeze are not supported by the B200 build" << std::endl;
         exit(EXIT_FAILURE);
@@ -362,6 +359,16 @@ bool vamp::linear_iteration(data* dataset, int it) {
         if (rank == 0) std::cout << "______________________" << std::endl << "->LMMSE" << std::endl;
 
         double start_CG = wtime();
+        if (reverse == 1) {   // XXT form: solve in N-space (vamp.cpp:599-606)
+            if (it == 1) mu_CG_last = std::vector<double>(4 * dataset->get_mbytes(), 0.0);
+            std::vector<double> r2_h;
+            sync_host(dev.r2, r2_h, M);
+            x2_hat = lmmse_denoiserAAT(r2_h, mu_CG_last, dataset);
+            DEV(gvb_vec_upload(ctx, dev.x2, x2_hat.data(), M));
+            DEV(gvb_vec_copy(ctx, dev.mu_last, dev.x2));
+            dev.ax_x2_valid = false;
+            last_cg_iters[0] = 0;
+        } else {
         // v = gamw * A^T y + gam2 * r2
         if (!dev.aty_valid) {
             DEV(gvb_dATx(ctx, dev.y, dev.aty));
@@ -384,6 +391,7 @@ bool vamp::linear_iteration(data* dataset, int it) {
         }
         DEV(gvb_vec_copy(ctx, dev.mu_last, dev.x2));
         dev.ax_x2_valid = !reference_sweeps;
+        }
         std::string filepath_out_x2 = out_dir + out_name + "_it_" + std::to_string(it) + "_x2_hat.bin";
         store_scaled(dev.x2, filepath_out_x2, scale, S);
         if (rank == 0) std::cout << "x2_hat filepath_out is " << filepath_out_x2 << std::endl;
@@ -525,6 +533,71 @@ double vamp::g2d_onsager(double gam2, double tau, data* dataset) {
     double dot = 0;
     DEV(gvb_vec_dots(dev.ctx, 1, xs, ys, 1, &dot));
     return gam2 * dot;   // gam2 * Tr[(tau X^T X + gam2 I)^-1] / Mt
+}
+
+// ---------------------------------------------------------------------------------------------------
+// XXT form of the LMMSE step (denoiserXXT.cpp:15-55): x2 = r2 + gamw A^T (gamw A A^T + gam2)^-1 (y - A r2)
+// ---------------------------------------------------------------------------------------------------
+std::vector<double> vamp::lmmse_multAAT(std::vector<double> u, double tau, data* dataset) {
+    const size_t phen_size = 4 * dataset->get_mbytes();
+    u.resize(phen_size, 0.0);
+    bool zero = true;
+    for (int i = 0; i < N && zero; i++) zero = (u[i] == 0.0);
+    if (zero) return std::vector<double>(phen_size, 0.0);
+    std::vector<double> t = dataset->ATx(u.data());
+    std::vector<double> res = dataset->Ax(t.data());
+    for (int i = 0; i < N; i++) res[i] = res[i] * tau + gam2 * u[i];
+    return res;
+}
+
+std::vector<double> vamp::CG_solverAAT(std::vector<double> v, std::vector<double> mu_start, double tau, int save, data* dataset) {
+    dev_open(dataset);
+    gvb_ctx* ctx = dev.ctx;
+    const long n4 = 4 * (long)dataset->get_mbytes();
+    gvb_vec dv = nullptr, dmu = nullptr;
+    DEV(gvb_vec_alloc_N(ctx, &dv));
+    DEV(gvb_vec_alloc_N(ctx, &dmu));
+    v.resize(n4, 0.0);
+    mu_start.resize(n4, 0.0);
+    for (long i = N; i < n4; i++) v[i] = mu_start[i] = 0.0;
+    DEV(gvb_vec_upload(ctx, dv, v.data(), n4));
+    DEV(gvb_vec_upload(ctx, dmu, mu_start.data(), n4));
+    gvb_vec* pe = dataset->device_people();
+    if (!pe[0]) {
+        std::cout << "FATAL: compute_people_statistics() must run before the XXT solver" << std::endl;
+        exit(EXIT_FAILURE);
+    }
+    std::vector<double> log(3 * (size_t)CG_max_iter, 0.0);
+    int iters = 0;
+    DEV(gvb_cg_solve_aat(ctx, dv, dmu, tau, gam2, pe[0], pe[1], pe[2], CG_max_iter, &iters, log.data()));
+    if (rank == 0)
+        for (int i = 0; i < iters; i++)
+            std::cout << "[CG] it = " << i << ": ||r_it|| / ||RHS|| = " << log[3 * i] << ", ||x_it|| = " << log[3 * i + 1] << ", ||z|| / ||RHS|| = " << log[3 * i + 2]
+                      << std::endl;
+    std::vector<double> mu(n4, 0.0);
+    DEV(gvb_vec_download(ctx, dmu, mu.data(), n4));
+    gvb_vec_free(ctx, dv);
+    gvb_vec_free(ctx, dmu);
+    if (save == 1) mu_CG_last = mu;
+    return mu;
+}
+
+std::vector<double> vamp::lmmse_denoiserAAT(std::vector<double> r2, std::vector<double> mu_CG_AAT_last, data* dataset) {
+    double norm_r2 = sqrt(l2_norm2(r2, 1));
+    if (rank == 0) std::cout << "||r2|| = " << norm_r2 << std::endl;
+    std::vector<double> z2 = dataset->Ax(r2.data());
+    if (rank == 0) std::cout << "||z2|| = " << sqrt(l2_norm2(z2, 0)) << std::endl;
+    // the reference's member y is the NA-filtered phenotype by the time this runs (err_measures(1) has replaced it, vamp.cpp:1292)
+    std::vector<double> yf = dataset->filter_pheno();
+    yf.resize(N, 0.0);
+    if (rank == 0) std::cout << "||y|| = " << sqrt(l2_norm2(yf, 0)) << std::endl;
+    std::vector<double> v(N, 0.0);
+    for (int i = 0; i < N; i++) v[i] = yf[i] - z2[i];
+    if (rank == 0) std::cout << "||v|| = " << sqrt(l2_norm2(v, 0)) << std::endl;
+    std::vector<double> u = CG_solverAAT(v, mu_CG_AAT_last, gamw, 1, dataset);
+    std::vector<double> res = dataset->ATx(u.data());
+    for (int i = 0; i < M; i++) res[i] = gamw * res[i] + r2[i];
+    return res;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -132,6 +132,10 @@ public:
 
     void updatePrior(int verbose);
     void updateNoisePrec(data* dataset);
+    // XXT form of the LMMSE step (denoiserXXT.cpp:15-135), --use-XXT-denoiser 1
+    std::vector<double> lmmse_multAAT(std::vector<double> u, double tau, data* dataset);
+    std::vector<double> lmmse_denoiserAAT(std::vector<double> r2, std::vector<double> mu_CG_AAT_last, data* dataset);
+    std::vector<double> CG_solverAAT(std::vector<double> v, std::vector<double> mu_start, double tau, int save, data* dataset);
 
     std::vector<double> lmmse_mult(std::vector<double> v, double tau, data* dataset, int red = 0);
     std::vector<double> precondCG_solver(std::vector<double> v, double tau, int denoiser, data* dataset, int red = 0);

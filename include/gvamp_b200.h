@@ -190,6 +190,17 @@ int gvb_cg_solve_ex(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double ga
 int gvb_cg_solve_warm(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters,
                       double* rel_res, gvb_vec ax_mu, gvb_vec ata_mu, int have_start, double* dots3);
 
+/* ---- XXT form of the LMMSE step (--use-XXT-denoiser 1) ---------------------------------------------- */
+/* data::compute_people_statistics, data.cpp:548-640: per individual, over ALL markers (summed over the ranks): number of
+ * non-missing genotypes, mean and inverse-variance-like scale sqrt((n-1)/(S2 - n mean^2)) of the standardised genotypes;
+ * 0 for individuals without phenotype.  Three X.v-type sweeps.  COLLECTIVE when nranks>1. */
+int gvb_people_stats(gvb_ctx* ctx, gvb_vec mave_people, gvb_vec msig_people, gvb_vec numb_people);
+/* vamp::CG_solverAAT + lmmse_multAAT, denoiserXXT.cpp:15-135: (tau A A^T + gam2 I) mu = rhs on N-vectors with the
+ * per-individual diagonal preconditioner built from the people statistics; mu holds the start vector on entry; exit at
+ * ||r||/||rhs|| < 1e-4.  log3: 3 doubles per iteration (||r||/||rhs||, ||mu||, ||z||/||rhs||), may be NULL.  COLLECTIVE. */
+int gvb_cg_solve_aat(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, gvb_vec mave_people, gvb_vec msig_people,
+                     gvb_vec numb_people, int max_iter, int* iters, double* log3);
+
 /* ---- probit z-denoiser ---------------------------------------------------------------------------- */
 /* vamp::g1_bin_class / g1d_bin_class, vamp_probit.cpp:661-726 with erfcx (utilities.cpp:345-409):
  * z1_hat[i] = g(p1[i]); sums[0] = sum_i g'(p1[i]) (i<N); sums[1] = ||z1_hat - p1||^2.  mcov may be NULL. */

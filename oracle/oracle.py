@@ -625,3 +625,75 @@ def probit_cov_pass(y, gg, Z, eta, probit_var=1.0):
     step = Z.T @ lam
     H = Z.T @ (Z * (lam * (lam + g))[:, None])
     return mlogl, grad, step, H
+
+
+# --------------------------------------------------------------------------------------------
+# XXT form of the LMMSE step: people statistics (data.cpp:548-640) and the N-space solver (denoiserXXT.cpp:15-135)
+# --------------------------------------------------------------------------------------------
+def people_statistics(ds: "Dataset", allreduce=lambda x: x):
+    """(mave_people, msig_people, numb_people), each 4*mbytes long."""
+    n4 = 4 * ds.mbytes
+    s1, s2, numb = np.zeros(n4), np.zeros(n4), np.zeros(n4)
+    for j in range(ds.M):
+        value, bm = _column_values(ds, j)
+        s1 += value
+        numb += bm
+        s2 += value * value
+    s1, s2, numb = allreduce(s1), allreduce(s2), allreduce(numb)
+    m = ((ds.mask4[:, None] >> np.arange(4)) & 1).reshape(-1).astype(bool)
+    m[ds.N:] = False
+    mave, msig = np.zeros(n4), np.zeros(n4)
+    mave[m] = s1[m] / numb[m]
+    msig[m] = np.sqrt((numb[m] - 1) / (s2[m] - numb[m] * mave[m] ** 2))
+    return mave, msig, numb
+
+
+def lmmse_mult_aat(ds: "Dataset", u, tau, gam2):
+    """denoiserXXT.cpp:15-29."""
+    n4 = 4 * ds.mbytes
+    uu = np.zeros(n4)
+    uu[: ds.N] = np.asarray(u)[: ds.N]
+    if not uu.any():
+        return np.zeros(n4)
+    res = ds.Ax(ds.ATx(uu))
+    res[: ds.N] = res[: ds.N] * tau + gam2 * uu[: ds.N]
+    return res
+
+
+def cg_solver_aat(ds: "Dataset", v, mu_start, tau, gam2, people, CG_max_iter, log=None):
+    """denoiserXXT.cpp:57-135; returns (mu, iterations)."""
+    N, n4 = ds.N, 4 * ds.mbytes
+    mave_p, msig_p, numb_p = people
+    with np.errstate(divide="ignore", invalid="ignore"):
+        diag = tau * ((numb_p[:N] - 1) / msig_p[:N] / msig_p[:N] + mave_p[:N] ** 2 * numb_p[:N]) / N + gam2
+    v = np.asarray(v, float)[:N]
+    mu = np.zeros(n4)
+    mu[:N] = np.asarray(mu_start, float)[:N]
+    r = v - lmmse_mult_aat(ds, mu, tau, gam2)[:N]
+    z = r / diag
+    p = z.copy()
+    its = 0
+    for i in range(CG_max_iter):
+        its = i + 1
+        d = lmmse_mult_aat(ds, p, tau, gam2)[:N]
+        alpha = r.dot(z) / d.dot(p)
+        mu[:N] += alpha * p
+        beta = 1.0 / r.dot(z)
+        r = r - alpha * d
+        z = r / diag
+        beta *= r.dot(z)
+        p = z + beta * p
+        rel_err = math.sqrt(r.dot(r) / v.dot(v))
+        if log is not None:
+            log.append(rel_err)
+        if rel_err < 1e-4:
+            break
+    return mu, its
+
+
+def lmmse_denoiser_aat(ds: "Dataset", r2, mu_last, y, gamw, gam2, people, CG_max_iter):
+    """denoiserXXT.cpp:31-55; returns (x2_hat, u)."""
+    z2 = ds.Ax(r2)
+    v = np.asarray(y, float)[: ds.N] - z2[: ds.N]
+    u, _ = cg_solver_aat(ds, v, mu_last, gamw, gam2, people, CG_max_iter)
+    return gamw * ds.ATx(u) + np.asarray(r2, float), u

@@ -38,6 +38,8 @@ def lib():
         L.ref_data_create_bim.restype = vp
         L.ref_data_create_bim.argtypes = [cs, cs, ci, ci, ci, ci, cd, cs]
         L.ref_data_pvals.argtypes = [vp, ci, c_f64p, c_f64p, c_f64p, cs, c_f64p]
+        L.ref_data_people_stats.argtypes = [vp, c_f64p, c_f64p, c_f64p]
+        L.ref_vamp_cg_aat.argtypes = [vp, vp, c_f64p, c_f64p, ci, cd, c_f64p]
         L.ref_data_destroy.argtypes = [vp]
         L.ref_data_mbytes.restype = ctypes.c_long
         L.ref_data_mbytes.argtypes = [vp]
@@ -141,6 +143,11 @@ class RefData:
         lib().ref_data_ATx(self.h, _p(uu), SB, LB, _p(out))
         return out
 
+    def people_stats(self):
+        a, s, n = np.empty(4 * self.mbytes), np.empty(4 * self.mbytes), np.empty(4 * self.mbytes)
+        lib().ref_data_people_stats(self.h, _p(a), _p(s), _p(n))
+        return a, s, n
+
     def pvals(self, z1, y, x1_hat, out_path, loco=False):
         """data::pvals_calc / pvals_calc_LOCO (data.cpp:1108-1353) for one estimator."""
         z1 = np.ascontiguousarray(z1[: self.N], dtype=np.float64)
@@ -204,6 +211,14 @@ class RefVamp:
         mu0 = np.ascontiguousarray(mu0, dtype=np.float64)
         out = np.empty(self.M)
         lib().ref_vamp_cg(self.h, data.h, _p(rhs), _p(mu0), self.M, tau, denoiser, _p(out))
+        return out
+
+    def cg_aat(self, data: RefData, rhs, mu0, tau):
+        n4 = 4 * data.mbytes
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        mu0 = np.ascontiguousarray(mu0, dtype=np.float64)
+        out = np.empty(n4)
+        lib().ref_vamp_cg_aat(self.h, data.h, _p(rhs), _p(mu0), n4, tau, _p(out))
         return out
 
     def onsager(self, data: RefData, gam2, tau):

@@ -64,6 +64,16 @@ void* ref_data_create_bim(const char* phen_path, const char* bed_path, int N, in
     return new data(std::string(phen_path), std::string(bed_path), N, M, Mt, S, 0, "bed", alpha_scale, std::string(bimfp));
 }
 void ref_data_destroy(void* h) { delete static_cast<data*>(h); }
+// data::compute_people_statistics data.cpp:548-640; each output has 4*mbytes doubles
+void ref_data_people_stats(void* h, double* mave, double* msig, double* numb) {
+    StdoutSilencer s(g_quiet);
+    data* d = static_cast<data*>(h);
+    d->compute_people_statistics();
+    std::vector<double> a = d->get_mave_people(), b = d->get_msig_people(), c = d->get_numb_people();
+    memcpy(mave, a.data(), a.size() * sizeof(double));
+    memcpy(msig, b.data(), b.size() * sizeof(double));
+    memcpy(numb, c.data(), c.size() * sizeof(double));
+}
 // data::pvals_calc data.cpp:1108-1180 / data::pvals_calc_LOCO data.cpp:1220-1353, one estimator; z1 and y have N entries
 void ref_data_pvals(void* h, int loco, const double* z1, const double* y, const double* x1_hat, const char* out_path, double* out) {
     StdoutSilencer s(g_quiet);
@@ -200,6 +210,13 @@ void ref_vamp_infere(void* h, void* dh, int M, double* out) {
     vamp* v = static_cast<vamp*>(h);
     std::vector<double> r = v->infere(static_cast<data*>(dh));
     memcpy(out, r.data(), sizeof(double) * M);
+}
+// vamp::CG_solverAAT denoiserXXT.cpp:57 (people statistics must have been computed on the data object; gam2 via set_state)
+void ref_vamp_cg_aat(void* h, void* dh, const double* rhs, const double* mu0, int n4, double tau, double* out) {
+    StdoutSilencer s(g_quiet);
+    vamp* v = static_cast<vamp*>(h);
+    std::vector<double> r = v->CG_solverAAT(std::vector<double>(rhs, rhs + v->N), std::vector<double>(mu0, mu0 + n4), tau, 0, static_cast<data*>(dh));
+    memcpy(out, r.data(), sizeof(double) * n4);
 }
 double ref_vamp_gamw(void* h) { return static_cast<vamp*>(h)->gamw; }
 double ref_vamp_gam1(void* h) { return static_cast<vamp*>(h)->gam1; }

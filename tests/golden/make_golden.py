@@ -247,6 +247,46 @@ def case_config1(tmp):
     print("R2trains", out["R2trains"], "gamw", gamw)
 
 
+def case_xxt(tmp):
+    """--use-XXT-denoiser 1: people statistics (data.cpp:548-640), one CG_solverAAT solve through the harness and a complete
+    main_real.exe run with the N-space LMMSE step (denoiserXXT.cpp), on the N=1003 / 2 % missing / phenotype-NA case and on the
+    N=1000 x M=2000 linear case."""
+    g = np.load(os.path.join(OUT, "matvec_n1003.npz"))
+    N, M, seed = int(g["N"]), int(g["M"]), int(g["seed"])
+    bed = O.synth_bed(seed, 0, M, N, miss_rate=float(g["miss_rate"]))
+    bedp, phenp = os.path.join(tmp, "x.bed"), os.path.join(tmp, "x.phen")
+    O.write_bed(bedp, bed)
+    O.write_phen(phenp, g["y"], na_idx=[int(i) for i in g["na_idx"]])
+    rd = R.RefData(bedp, N, M, phen_path=phenp)
+    mave_p, msig_p, numb_p = rd.people_stats()
+    rng = np.random.default_rng(77)
+    rhs = rng.normal(size=N) * ((rd.mask4()[:, None] >> np.arange(4)) & 1).reshape(-1)[:N]
+    rv = R.RefVamp(N, M, M, PROBS, VARS, iterations=1, CG_max_iter=30)
+    rv.set_state(1.0, 0.7, 2.0)
+    u = rv.cg_aat(rd, rhs, np.zeros(4 * rd.mbytes), 2.0)
+    out = dict(N=N, M=M, mave_people=mave_p, msig_people=msig_p, numb_people=numb_p, cg_rhs=rhs, cg_tau=2.0, cg_gam2=0.7, cg_max_iter=30, cg_u=u)
+    # end to end
+    gl = np.load(os.path.join(OUT, "vamp_linear.npz"))
+    N2, M2, iters = int(gl["N"]), int(gl["M"]), 5
+    bed2 = O.synth_bed(int(gl["seed"]), 0, M2, N2)
+    bedp2, phenp2 = os.path.join(tmp, "xl.bed"), os.path.join(tmp, "xl.phen")
+    O.write_bed(bedp2, bed2)
+    O.write_phen(phenp2, gl["y"])
+    outd = os.path.join(tmp, "xout") + "/"
+    args = ["--run-mode", "infere", "--model", "linear", "--bed-file", bedp2, "--phen-files", phenp2, "--N", str(N2), "--Mt", str(M2),
+            "--out-dir", outd, "--out-name", "x", "--iterations", str(iters), "--CG-max-iter", "20", "--rho", "0.5",
+            "--probs", ",".join(map(str, PROBS)), "--vars", ",".join(map(str, VARS)), "--h2", "0.5", "--seed", "1", "--use-XXT-denoiser", "1"]
+    log = subprocess.run([R.exe("main_real_scalar.exe")] + args, check=True, capture_output=True, text=True, env=dict(os.environ, OMP_NUM_THREADS="4")).stdout
+    out.update(e2e_args=np.array(args[8:]), e2e_iterations=iters)
+    for it in range(1, iters + 1):
+        out[f"x1_{it}"] = np.fromfile(f"{outd}x_it_{it}.bin")
+        out[f"x2_{it}"] = np.fromfile(f"{outd}x_it_{it}_x2_hat.bin")
+    out["gam1s"] = np.loadtxt(f"{outd}x_gam1s.csv")
+    out["gamw_log"] = np.array([float(l.split("=")[1]) for l in log.splitlines() if l.startswith("gamw = ")])
+    np.savez_compressed(os.path.join(OUT, "xxt.npz"), **out)
+    print("xxt: CG iterations in log:", len([l for l in log.splitlines() if l.startswith("[CG] it")]), "gamw", out["gamw_log"][-3:])
+
+
 def case_pvals(tmp):
     """LOO and LOCO association p-values (data.cpp:1108-1353) on the N=1003 case (2 % missing genotypes, phenotype NAs)
     with a 5-chromosome .bim (incl. "X" -> 23).  The Student-t tail comes from oracle/shims (incomplete beta), which the
@@ -290,4 +330,5 @@ if __name__ == "__main__":
         case_vamp_probit(tmp)
         case_pvals(tmp)
         case_config1(tmp)
+        case_xxt(tmp)
     print("golden vectors written to", OUT)

@@ -407,3 +407,22 @@ def test_more_than_2M_individuals(C, oracle):
     # accurate of the two, hence 1e-10 here instead of the 1e-11 of the small cases
     assert relerr(mave, ds.mave) < 1e-13 and relerr(msig, ds.msig) < 1e-10
     assert relerr(ax, ds.Ax(v)) < TOL_MATVEC and relerr(atx, ds.ATx(u)) < TOL_MATVEC
+
+
+def test_people_statistics_and_xxt_solver(C, oracle):
+    """gvb_people_stats (three X.v-type walks with per-code tables: value, 1, value^2) and gvb_cg_solve_aat against the reference's
+    compute_people_statistics / CG_solverAAT (tests/golden/xxt.npz): N % 4 != 0, 2 % missing genotypes, phenotype NAs.
+    Counts bit-exact; the FP sums carry the fixed-point error of a sweep (1e-6 bound), the solve its own 1e-4 exit tolerance."""
+    g, gm = golden("xxt.npz"), golden("matvec_n1003.npz")
+    N, M = int(g["N"]), int(g["M"])
+    bed = oracle.synth_bed(int(gm["seed"]), 0, M, N, miss_rate=float(gm["miss_rate"]))
+    with make_ctx(C, "lut") as ctx:
+        ctx.load_host(bed, N).set_mask(gm["mask4"], int(gm["nonas"])).compute_stats(1.0)
+        pe = ctx.people_stats()
+        mave_p, msig_p, numb_p = (v.download() for v in pe)
+        rhs, mu = ctx.vecN(np.concatenate([g["cg_rhs"], np.zeros(len(mave_p) - N)])), ctx.vecN()
+        its, log = ctx.cg_solve_aat(rhs, mu, float(g["cg_tau"]), float(g["cg_gam2"]), pe, int(g["cg_max_iter"]))
+        u = mu.download()
+    assert np.array_equal(numb_p, g["numb_people"])
+    assert relerr(mave_p, g["mave_people"]) < TOL_MATVEC and relerr(msig_p, g["msig_people"]) < TOL_MATVEC
+    assert relerr(u, g["cg_u"]) < 1e-4 and log[-1, 0] < 1e-4

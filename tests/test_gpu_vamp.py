@@ -93,6 +93,34 @@ def test_config1_matches_reference(oracle, tmp_path):
     assert np.allclose(pv[-1], g["prior_vars_last"], rtol=TOL_FINAL) and np.allclose(pp[-1], g["prior_probs_last"], rtol=TOL_FINAL)
 
 
+def test_xxt_denoiser_matches_reference_files(oracle, tmp_path):
+    """--use-XXT-denoiser 1 (N-space LMMSE step, denoiserXXT.cpp) end to end against the reference's files.  The N-space solve
+    stops at ||r||/||rhs|| < 1e-4 (denoiserXXT.cpp:125), so two correct implementations agree to about that; the bound here is
+    5e-3 on the estimates (the 1e-4 of the north_star applies to the default M-space path, which the other tests hold)."""
+    g, gl = golden("xxt.npz"), golden("vamp_linear.npz")
+    N, M, iters = int(gl["N"]), int(gl["M"]), int(g["e2e_iterations"])
+    bed = oracle.synth_bed(int(gl["seed"]), 0, M, N)
+    bedp, phenp = str(tmp_path / "x.bed"), str(tmp_path / "x.phen")
+    oracle.write_bed(bedp, bed)
+    oracle.write_phen(phenp, gl["y"])
+    outd = str(tmp_path / "xout") + "/"
+    args = ["--run-mode", "infere", "--model", "linear", "--bed-file", bedp, "--phen-files", phenp, "--N", str(N), "--Mt", str(M),
+            "--out-dir", outd, "--out-name", "x"]
+    extra = [str(a) for a in g["e2e_args"]]
+    for k in range(0, len(extra), 2):
+        if extra[k] not in {"--N", "--Mt", "--out-dir", "--out-name"}:
+            args += [extra[k], extra[k + 1]]
+    r = subprocess.run([EXE] + args, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for it in range(1, iters + 1):
+        for key, fn in (("x1", f"x_it_{it}.bin"), ("x2", f"x_it_{it}_x2_hat.bin")):
+            ref, got = g[f"{key}_{it}"], np.fromfile(outd + fn)
+            if np.linalg.norm(ref) > 0:
+                assert relerr(got, ref) < 5e-3, (key, it, relerr(got, ref))
+    gamw = [float(l.split("=")[1]) for l in r.stdout.splitlines() if l.startswith("gamw = ")]
+    assert np.allclose(gamw, g["gamw_log"], rtol=5e-3)
+
+
 def test_cg_by_products_leave_the_outputs_unchanged(oracle, tmp_path, monkeypatch):
     """Default run (A x2_hat and the trace term of updateNoisePrec as by-products of the two CG solves) against
     GVB_REFERENCE_SWEEPS=1 (their own bed sweeps, as the reference does, vamp.cpp:897-915): same files and gamw far inside the

@@ -179,3 +179,17 @@ def test_config1_end_to_end(oracle):
         assert relerr(tr.x1_hat[it - 1], g[key]) < 1e-7, (key, relerr(tr.x1_hat[it - 1], g[key]))
     assert np.allclose(tr.gam1s, g["gam1s"][:iters], rtol=1e-5) and np.allclose(tr.gam2s, g["gam2s"][:iters], rtol=1e-5)
     assert np.allclose(tr.gamw, g["gamw_log"][1::2][:iters], rtol=1e-5)
+
+
+def test_xxt_people_statistics_and_solver(oracle):
+    """people statistics (data.cpp:548-640) and CG_solverAAT (denoiserXXT.cpp:57-135) of the restatement against the reference."""
+    g, gm = golden("xxt.npz"), golden("matvec_n1003.npz")
+    N, M = int(g["N"]), int(g["M"])
+    bed = oracle.synth_bed(int(gm["seed"]), 0, M, N, miss_rate=float(gm["miss_rate"]))
+    ds = oracle.Dataset(bed, N, mask4=gm["mask4"], nonas=int(gm["nonas"]))
+    pe = oracle.people_statistics(ds)
+    for got, key in zip(pe, ("mave_people", "msig_people", "numb_people")):
+        assert relerr(got, g[key]) < 1e-13, key
+    assert np.array_equal(pe[2], g["numb_people"])                       # counts: exact
+    u, its = oracle.cg_solver_aat(ds, g["cg_rhs"], np.zeros(4 * ds.mbytes), float(g["cg_tau"]), float(g["cg_gam2"]), pe, int(g["cg_max_iter"]))
+    assert relerr(u, g["cg_u"]) < 1e-12

@@ -440,56 +440,6 @@ extern "C" int gvb_lmmse_mult(gvb_ctx* c, gvb_vec v, double tau, double gam2, gv
 }
 
 // fused CG updates ---------------------------------------------------------------------------------
-// mu += alpha*p ; partial: <rhs,mu>, ||mu||^2
-__global__ void __launch_bounds__(256) cg_update_mu_kernel(double* __restrict__ mu, const double* __restrict__ p, const double* __restrict__ rhs,
-                                                           double alpha, long n, double* __restrict__ partial) {
-    double a0 = 0.0, a1 = 0.0;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        double m = mu[i] + alpha * p[i];
-        mu[i] = m;
-        a0 += rhs[i] * m;
-        a1 += m * m;
-    }
-    __shared__ double sm[8][2];
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    }
-    if (lane == 0) { sm[warp][0] = a0; sm[warp][1] = a1; }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-        double s = 0.0;
-        for (int w = 0; w < 8; w++) s += sm[w][threadIdx.x];
-        partial[blockIdx.x * 2 + threadIdx.x] = s;
-    }
-}
-// r -= alpha*d ; partial: <r, r/diag>, ||r||^2
-__global__ void __launch_bounds__(256) cg_update_r_kernel(double* __restrict__ r, const double* __restrict__ d, double alpha, double diag, long n,
-                                                          double* __restrict__ partial) {
-    double a0 = 0.0, a1 = 0.0;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        double x = r[i] - d[i] * alpha;
-        r[i] = x;
-        a0 += x * (x / diag);
-        a1 += x * x;
-    }
-    __shared__ double sm[8][2];
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    }
-    if (lane == 0) { sm[warp][0] = a0; sm[warp][1] = a1; }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-        double s = 0.0;
-        for (int w = 0; w < 8; w++) s += sm[w][threadIdx.x];
-        partial[blockIdx.x * 2 + threadIdx.x] = s;
-    }
-}
 // p = r/diag + beta*p
 __global__ void cg_update_p_kernel(double* __restrict__ p, const double* __restrict__ r, double beta, double diag, long n) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = r[i] / diag + beta * p[i];
@@ -527,22 +477,69 @@ __global__ void __launch_bounds__(256) cg_init_kernel(double* __restrict__ r, do
 __global__ void cg_axpy_n_kernel(double* __restrict__ ax, const double* __restrict__ ap, double alpha, long n) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) ax[i] += alpha * ap[i];
 }
-// r -= alpha*d (no reductions): brings the residual up to date when the Onsager exit left it one update behind
-__global__ void cg_axpy_m_kernel(double* __restrict__ r, const double* __restrict__ d, double alpha, long n) {
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) r[i] -= alpha * d[i];
-}
-
-// ata = (d - gam2*mu)/tau: A^T A mu out of d = (tau A^T A + gam2) mu;  d = tau*ata + gam2*mu: the way back;
-// ata += alpha (d - gam2 p)/tau: the running A^T A mu next to mu += alpha p
+// ata = (d - gam2*mu)/tau: A^T A mu out of d = (tau A^T A + gam2) mu;  d = tau*ata + gam2*mu: the way back
+// (the running update ata += alpha (d - gam2 p)/tau lives in cg_update_mu_r_kernel)
 __global__ void cg_ata_from_d_kernel(double* __restrict__ ata, const double* __restrict__ d, const double* __restrict__ mu, double gam2, double tau, long n) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) ata[i] = (d[i] - gam2 * mu[i]) / tau;
 }
 __global__ void cg_d_from_ata_kernel(double* __restrict__ d, const double* __restrict__ ata, const double* __restrict__ mu, double gam2, double tau, long n) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) d[i] = tau * ata[i] + gam2 * mu[i];
 }
-__global__ void cg_ata_axpy_kernel(double* __restrict__ ata, const double* __restrict__ d, const double* __restrict__ p, double alpha, double gam2, double tau,
-                                   long n) {
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) ata[i] += alpha * ((d[i] - gam2 * p[i]) / tau);
+// d = tau*d + gam2*p (the tail of lmmse_mult, vamp.cpp:1113-1114) fused with <d,p>
+__global__ void __launch_bounds__(256) cg_combine_dot_kernel(double* __restrict__ d, double tau, double gam2, const double* __restrict__ p, long n,
+                                                             double* __restrict__ partial) {
+    double a0 = 0.0;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        double x = d[i] * tau;
+        x = x + gam2 * p[i];
+        d[i] = x;
+        a0 += x * p[i];
+    }
+    __shared__ double sm[8];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    if (lane == 0) sm[warp] = a0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; w++) s += sm[w];
+        partial[blockIdx.x] = s;
+    }
+}
+// mu += alpha p ; r -= alpha d ; [ata += alpha (d - gam2 p)/tau] ; partial: <rhs,mu>, ||mu||^2, <r, r/diag>, ||r||^2.
+// One kernel and ONE host-visible reduction for the two updates of a CG iteration (vamp.cpp:1160-1207); the Onsager exit test,
+// which the reference places between them, only reads <rhs,mu>, so testing it after both leaves mu and the decision unchanged.
+__global__ void __launch_bounds__(256) cg_update_mu_r_kernel(double* __restrict__ mu, double* __restrict__ r, const double* __restrict__ p,
+                                                             const double* __restrict__ d, const double* __restrict__ rhs, double* __restrict__ ata,
+                                                             double alpha, double diag, double gam2, double tau, long n, double* __restrict__ partial) {
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const double pi = p[i], di = d[i];
+        const double m = mu[i] + alpha * pi;
+        const double x = r[i] - di * alpha;
+        mu[i] = m;
+        r[i] = x;
+        if (ata) ata[i] += alpha * ((di - gam2 * pi) / tau);
+        a[0] += rhs[i] * m;
+        a[1] += m * m;
+        a[2] += x * (x / diag);
+        a[3] += x * x;
+    }
+    __shared__ double sm[8][4];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+        if (lane == 0) sm[warp][k] = a[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0.0;
+        for (int w = 0; w < 8; w++) s += sm[w][threadIdx.x];
+        partial[blockIdx.x * 4 + threadIdx.x] = s;
+    }
 }
 
 static inline int cg_blocks(long n) { return (int)std::max(1l, std::min((n + 1023) / 1024, (long)GVB_RED_BLOCKS)); }
@@ -600,8 +597,6 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
     }
     const int nbn = (int)std::min((c->Npad + 255) / 256, 1184l);
     double rhs_mu = 0.0;
-    bool r_stale = false;
-    double alpha_last = 0.0;
     cg_init_kernel<<<nb, 256, 0, c->stream>>>(r->d, p->d, rhs->d, d->d, diag, n, c->red_partial);
     c->launches++;
     CGCHK(gvb_reduce_finish(c, nb, 2, true, s2));
@@ -611,44 +606,45 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
     double prev_onsager = 0.0;
     for (int i = 0; i < max_iter; i++) {
         it_done = i + 1;
-        // d = A p  (p == 0 only when r == 0: the reference then returns zeros and alpha = 0/0)
-        CGCHK(lmmse_mult_dev(c, p, tau, gam2, d, rz != 0.0));
-        gvb_vec xs[1] = {d};
-        gvb_vec ys[1] = {p};
+        // d = Q p  (p == 0 only when r == 0: the reference then returns zeros and alpha = 0/0)
         double dp = 0.0;
-        CGCHK(gvb_vec_dots(c, 1, xs, ys, 1, &dp));
+        if (rz != 0.0) {
+            CGCHK(gvb_ax_dev(c, p->d, c->tmpN2, true));
+            CGCHK(gvb_atx_dev(c, c->tmpN2, d->d));
+            cg_combine_dot_kernel<<<nb, 256, 0, c->stream>>>(d->d, tau, gam2, p->d, n, c->red_partial);
+            c->launches++;
+            CGCHK(gvb_reduce_finish(c, nb, 1, true, &dp));
+        } else {
+            CGCHK(lmmse_mult_dev(c, p, tau, gam2, d, false));
+            gvb_vec xs[1] = {d};
+            gvb_vec ys[1] = {p};
+            CGCHK(gvb_vec_dots(c, 1, xs, ys, 1, &dp));
+        }
         double alpha = rz / dp;
         if (ax_mu && rz != 0.0) {   // c->tmpN2 still holds A p of this iteration
             cg_axpy_n_kernel<<<nbn, 256, 0, c->stream>>>(ax_mu->d, c->tmpN2, alpha, c->Npad);
             c->launches++;
-            if (ata_mu) {
-                cg_ata_axpy_kernel<<<nbm, 256, 0, c->stream>>>(ata_mu->d, d->d, p->d, alpha, gam2, tau, n);
-                c->launches++;
-            }
         }
-        cg_update_mu_kernel<<<nb, 256, 0, c->stream>>>(mu->d, p->d, rhs->d, alpha, n, c->red_partial);
+        double s4[4];
+        cg_update_mu_r_kernel<<<nb, 256, 0, c->stream>>>(mu->d, r->d, p->d, d->d, rhs->d, (ata_mu && rz != 0.0) ? ata_mu->d : nullptr, alpha, diag, gam2, tau, n,
+                                                         c->red_partial);
         c->launches++;
-        CGCHK(gvb_reduce_finish(c, nb, 2, true, s2));
-        double norm_mu = sqrt(s2[1]);
-        rhs_mu = s2[0];
+        CGCHK(gvb_reduce_finish(c, nb, 4, true, s4));
+        double norm_mu = sqrt(s4[1]);
+        rhs_mu = s4[0];
         double ons_rel = -1.0;
         if (denoiser == 0) {   // vamp.cpp:1174-1193
-            double onsager = gam2 * s2[0];
+            double onsager = gam2 * s4[0];
             ons_rel = (onsager != 0.0) ? fabs((onsager - prev_onsager) / onsager) : 1.0;
             if (ons_rel < 1e-8) {
                 if (log4) { log4[4 * i + 0] = -1.0; log4[4 * i + 1] = norm_mu; log4[4 * i + 2] = -1.0; log4[4 * i + 3] = ons_rel; }
-                r_stale = true;   // mu moved, r did not (the reference tests before the r-update, vamp.cpp:1174-1193)
-                alpha_last = alpha;
                 break;
             }
             prev_onsager = onsager;
         }
         double beta = 1.0 / rz;   // vamp.cpp:1198
-        cg_update_r_kernel<<<nb, 256, 0, c->stream>>>(r->d, d->d, alpha, diag, n, c->red_partial);
-        c->launches++;
-        CGCHK(gvb_reduce_finish(c, nb, 2, true, s2));
-        rz = s2[0];
-        rr = s2[1];
+        rz = s4[2];
+        rr = s4[3];
         beta *= rz;               // vamp.cpp:1207
         cg_update_p_kernel<<<(unsigned)std::min((n + 255) / 256, 1184l), 256, 0, c->stream>>>(p->d, r->d, beta, diag, n);
         c->launches++;
@@ -657,11 +653,7 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
         if (log4) { log4[4 * i + 0] = rel_err; log4[4 * i + 1] = norm_mu; log4[4 * i + 2] = norm_z / norm_v; log4[4 * i + 3] = ons_rel; }
         if (rel_err < 1e-5) break;                     // vamp.cpp:1217-1223
     }
-    if (dots3) {
-        if (r_stale) {
-            cg_axpy_m_kernel<<<(unsigned)std::min((n + 255) / 256, 1184l), 256, 0, c->stream>>>(r->d, d->d, alpha_last, n);
-            c->launches++;
-        }
+    if (dots3) {   // r is the residual of the returned mu in every exit path (the two updates are one kernel)
         gvb_vec xs[1] = {rhs};
         gvb_vec ys[1] = {r};
         double rr_dot = 0.0;

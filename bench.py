@@ -98,7 +98,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu), "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu), "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
@@ -408,7 +408,7 @@ def ours_arm(args):
         "config": {"workload": f"{args.workload}: {desc}", "N": N, "Mt": Mt, "markers_per_gpu": m_per_gpu, "cg_max_iter": args.cg_max_iter,
                    "h2": H2, "rho": RHO, "prior": "reference default 23-component", "sweeps_per_step": timed_sweeps, "cg_iters_per_step": timed_cg,
                    "l2_policy": "inputs (>= 12 GB packed bed per sweep at the default workload) larger than the 126 MB L2",
-                   "kernels": os.environ.get("GVB_KERNELS", "tile (gen 2)"), "final_gamw": gamw, "setup_s": t_setup},
+                   "kernels": os.environ.get("GVB_KERNELS", "tile (gen 2)"), "twin_layout": ctx.twin_state() == 1, "final_gamw": gamw, "setup_s": t_setup},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": 8 * (N + M), "d2h_bytes_per_step": 8 * (4 * M + 4 * mbytes),
                 "ms_per_step": ms_e2e / K},

@@ -79,6 +79,7 @@ SIGNATURES = {
     "gvb_cg_solve_aat": (ci, [vp, vp, vp, cd, cd, vp, vp, vp, ci, ctypes.POINTER(ci), c_f64p]),
     "gvb_probit_denoise": (ci, [vp, vp, vp, vp, cd, cd, vp, c_f64p]),
     "gvb_missing_list_entries": (cl, [vp]),
+    "gvb_twin_state": (ci, [vp]),
     "gvb_assoc_pvals": (ci, [vp, vp, vp, vp, vp]),
     "gvb_probit_cov_pass": (ci, [vp, vp, vp, vp, ci, c_f64p, cd, ci, c_f64p]),
     "gvb_probit_cov_apply": (ci, [vp, vp, ci, c_f64p, vp]),
@@ -402,3 +403,7 @@ class Context:
 
     def missing_list_entries(self) -> int:
         return self.L.gvb_missing_list_entries(self.h)
+
+    def twin_state(self) -> int:
+        """1: X.v walks the individual-major twin of the matrix, -1: no twin (too large / GVB_TWIN=0), 0: not decided yet"""
+        return self.L.gvb_twin_state(self.h)

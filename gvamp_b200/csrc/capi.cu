@@ -125,6 +125,7 @@ extern "C" void gvb_ctx_destroy(gvb_ctx* c) {
     fr(c->bed); fr(c->maskw); fr(c->validw); fr(c->mave); fr(c->msig); fr(c->counts);
     fr(c->tmpN); fr(c->tmpN2); fr(c->tmpM); fr(c->tmpM2); fr(c->wv); fr(c->cv); fr(c->ax_partial);
     gvb_misslist_reset(c);
+    gvb_twin_reset(c);
     fr(c->tab_u); fr(c->tab_v); fr(c->acc_i64); fr(c->red_partial); fr(c->red_result); fr(c->scal); fr(c->work_counter);
     if (c->h_red) cudaFreeHost(c->h_red);
     for (int i = 0; i < 8; i++) { cudaEventDestroy(c->ev_start[i]); cudaEventDestroy(c->ev_stop[i]); }

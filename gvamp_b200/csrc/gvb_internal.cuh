@@ -52,6 +52,10 @@ struct gvb_ctx {
     long Mg = 0, Mg_pad = 0;        // marker groups, padded to GVB_GROUP_TILE
     size_t bed_words = 0;
     uint32_t* bed = nullptr;        // the HBM-resident matrix
+    // individual-major twin of the matrix (twin.cu): same indexing, every word 4x4-transposed, so that byte k of a word is
+    // the ready-made table index of individual k for X.v; held only while spare HBM allows it
+    uint32_t* bed_twin = nullptr;
+    int twin_state = 0;             // 0: not built yet, 1: built, -1: not available (X.v gathers its indices from `bed`)
 
     // phenotype mask / valid-individual mask, one 32-bit word per position: bits 0,2,4,6 of every
     // byte are set when individual k of that position is present (resp. < N)
@@ -166,6 +170,8 @@ int gvb_atx_lut(gvb_ctx* c, const double* u, double* out);
 int gvb_ax_tile(gvb_ctx* c, const double* v, double* out, int mode = 0);     // gen-2 sweeps (matvec_tile.cu); mode: ax_code_values
 int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB = nullptr);   // outB[j] = sum_i b_ij u_i (optional)
 int gvb_count_tile_main(gvb_ctx* c, const int* tab, unsigned long long* acc);
+void gvb_twin_reset(gvb_ctx* c);                                       // twin.cu
+int gvb_twin_build(gvb_ctx* c);
 void gvb_misslist_reset(gvb_ctx* c);                                   // misslist.cu
 int gvb_misslist_build(gvb_ctx* c);
 int gvb_misslist_sum(gvb_ctx* c, unsigned long long* accm);

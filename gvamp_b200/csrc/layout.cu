@@ -107,6 +107,7 @@ static void free_layout(gvb_ctx* c) {
     fr(c->tab_v); c->tab_v_cap = 0;
     fr(c->acc_i64); c->acc_i64_cap = 0;
     gvb_misslist_reset(c);
+    gvb_twin_reset(c);
     c->total_missing = 0;
     c->have_mask = c->have_stats = false;
 }

@@ -143,7 +143,8 @@ __device__ __forceinline__ void release_work_counter(int* work_counter) {
 // ===================================================================================================
 // MADK of the four accumulators take their additions as IMAD (fma pipe), the others as IADD3 (alu pipe, two lookups per
 // instruction): the alu pipe also carries the LOP3 / PRMT of every lookup and is the busiest unit of this kernel
-template <int BUF, int MADK>
+// TW: the words come from the individual-major twin (twin.cu): byte k IS the index of individual k, no gather
+template <int BUF, int MADK, bool TW>
 __device__ __forceinline__ void ax_consume(const char* __restrict__ tabc, uint32_t bb, const unsigned (&spack)[8], int one, int (&a32)[4]) {
     const char* tb = tabc + BUF * 128;
 #pragma unroll
@@ -152,16 +153,16 @@ __device__ __forceinline__ void ax_consume(const char* __restrict__ tabc, uint32
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             // the 2-bit codes of individual k in the four marker bytes -> one 8-bit index in the top byte
-            const unsigned prod = (w & (0x03030303u << (2 * k))) * (0x01041040u >> (2 * k));
+            const unsigned prod = TW ? w : (w & (0x03030303u << (2 * k))) * (0x01041040u >> (2 * k));
             // address = index * 256 + slot * 4 (bytes 2,3 = sign replication of a slot byte < 128 = 0)
-            const unsigned a = prmt(prod, spack[tau >> 2], 0xCC30u | (4 + (tau & 3)));
+            const unsigned a = prmt(prod, spack[tau >> 2], (TW ? (0xCC00u | (k << 4)) : 0xCC30u) | (4 + (tau & 3)));
             const int val = *reinterpret_cast<const int*>(tb + a);
             a32[k] = (k >= 4 - MADK) ? mad_one(val, one, a32[k]) : a32[k] + val;
         }
     }
 }
 
-template <int NW, int NS, int MADK>
+template <int NW, int NS, int MADK, bool TW>
 __global__ void __launch_bounds__(NW * 32, 1)
 ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, long Mg_pad, long n_stripes, int n_sblocks, int n_gchunks,
                int tiles_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out, int one) {
@@ -234,7 +235,7 @@ ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, l
             mbar_wait(bar0 + 8 * s, (n_use / NS) & 1);                                       \
             n_use++;                                                                         \
             int a32[4] = {0, 0, 0, 0};                                                       \
-            ax_consume<B, MADK>(smem, bed_sm + s * TILE_BYTES + lane_off, spack, one, a32); \
+            ax_consume<B, MADK, TW>(smem, bed_sm + s * TILE_BYTES + lane_off, spack, one, a32); \
             _Pragma("unroll") for (int k = 0; k < 4; k++) acc64[k] += (long long)a32[k];     \
         }                                                                                    \
     }
@@ -377,12 +378,14 @@ struct TileTune {
     int variant;   // 0: 16 warps x 2 stages, 1: 12 warps x 3 stages
     int use_mad;   // X.v: accumulators (0..4) fed by IMAD instead of IADD3; X^T.u: 4 -> all four, else none
     int ax_tiles_per_chunk, atx_stripes_per_chunk;
+    int twin_mad;  // X.v on the twin: one accumulator fed by IMAD (1) or none (0)
 };
 
 TileTune tune_from_env() {
-    TileTune t{0, 1, 0, 0};   // one IMAD-fed accumulator measured best for X.v on B200 (5.30 vs 5.17 TB/s with none)   // chunk lengths 0: chosen per launch from the problem size (pick_chunk)
+    TileTune t{0, 1, 0, 0, 0};   // one IMAD-fed accumulator measured best for X.v on B200 (5.30 vs 5.17 TB/s with none)   // chunk lengths 0: chosen per launch from the problem size (pick_chunk)
     if (const char* e = getenv("GVB_TILE_VARIANT")) t.variant = atoi(e);
     if (const char* e = getenv("GVB_TILE_MAD")) t.use_mad = std::max(0, std::min(4, atoi(e)));
+    if (const char* e = getenv("GVB_TWIN_MAD")) t.twin_mad = atoi(e);
     if (const char* e = getenv("GVB_AX_TPC")) t.ax_tiles_per_chunk = std::max(1, atoi(e));
     if (const char* e = getenv("GVB_ATX_SPC")) t.atx_stripes_per_chunk = std::max(1, atoi(e));
     return t;
@@ -397,10 +400,10 @@ int pick_chunk(int requested, long rows, long steps, int sm_count) {
     return (int)std::max(4l, std::min(64l, per));
 }   // read per launch: the tests vary the chunking within one process
 
-template <int NW, int NS, int MADK>
+template <int NW, int NS, int MADK, bool TW>
 int launch_ax(gvb_ctx* c, unsigned long long* accN) {
     using Cfg = TileCfg<NW, NS>;
-    auto kern = ax_tile_kernel<NW, NS, MADK>;
+    auto kern = ax_tile_kernel<NW, NS, MADK, TW>;
     static bool attr_done = false;
     if (!attr_done) {
         GVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -411,7 +414,7 @@ int launch_ax(gvb_ctx* c, unsigned long long* accN) {
     const int tpc = pick_chunk(tune().ax_tiles_per_chunk, n_sblocks, n_tiles, c->sm_count);
     int n_gchunks = (int)((n_tiles + tpc - 1) / tpc);
     int grid = std::min(n_sblocks * n_gchunks, c->sm_count);
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(c->bed, c->tab_v, c->Mg_pad, c->n_stripes, n_sblocks, n_gchunks, tpc, c->work_counter, accN, 1);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(TW ? c->bed_twin : c->bed, c->tab_v, c->Mg_pad, c->n_stripes, n_sblocks, n_gchunks, tpc, c->work_counter, accN, 1);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }
@@ -645,13 +648,21 @@ int ensure_scratch(gvb_ctx* c, bool need_tab_u, bool need_tab_v, bool miss) {
 
 int ax_main(gvb_ctx* c, unsigned long long* accN) {
     const TileTune t = tune();
-    if (t.variant == 1) return t.use_mad ? launch_ax<12, 3, 4>(c, accN) : launch_ax<12, 3, 0>(c, accN);
+    // X.v on the individual-major twin (twin.cu) when spare HBM holds one: the walk of X^T.u, no index gather
+    const char* tw = getenv("GVB_TWIN");
+    const bool want_twin = !(tw && !strcmp(tw, "0"));
+    if (want_twin && c->twin_state == 0) GVB_CHECK(gvb_twin_build(c));
+    if (want_twin && c->twin_state == 1) {
+        if (t.variant == 1) return launch_ax<12, 3, 0, true>(c, accN);
+        return t.twin_mad > 0 ? launch_ax<16, 2, 1, true>(c, accN) : launch_ax<16, 2, 0, true>(c, accN);
+    }
+    if (t.variant == 1) return t.use_mad ? launch_ax<12, 3, 4, false>(c, accN) : launch_ax<12, 3, 0, false>(c, accN);
     switch (t.use_mad) {
-        case 0: return launch_ax<16, 2, 0>(c, accN);
-        case 1: return launch_ax<16, 2, 1>(c, accN);
-        case 2: return launch_ax<16, 2, 2>(c, accN);
-        case 3: return launch_ax<16, 2, 3>(c, accN);
-        default: return launch_ax<16, 2, 4>(c, accN);
+        case 0: return launch_ax<16, 2, 0, false>(c, accN);
+        case 1: return launch_ax<16, 2, 1, false>(c, accN);
+        case 2: return launch_ax<16, 2, 2, false>(c, accN);
+        case 3: return launch_ax<16, 2, 3, false>(c, accN);
+        default: return launch_ax<16, 2, 4, false>(c, accN);
     }
 }
 

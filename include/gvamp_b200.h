@@ -107,6 +107,11 @@ int gvb_get_counts(gvb_ctx* ctx, int64_t* counts);
  * (list larger than half the bed / out of memory / env GVB_MISS=twopass). */
 long gvb_missing_list_entries(gvb_ctx* ctx);
 
+/* state of the individual-major twin of the matrix that X.v (data::Ax, data.cpp:848-1011) walks when spare HBM holds one:
+ * 1 built, 0 not decided yet (the first X.v after gvb_compute_stats decides), -1 not held (shard too large for a second
+ * orientation, or env GVB_TWIN=0): X.v then gathers its table indices from the one matrix.  Results are bit-identical. */
+int gvb_twin_state(gvb_ctx* ctx);
+
 /* ---- X.v and X^T.u, host-pointer drop-in --------------------------------------------------------- */
 /* data::Ax(double* v, SB, LB), data.cpp:848-1011 incl. the MPI_Allreduce at :995.
  * v: M local entries; out: 4*LB entries.  COLLECTIVE when nranks>1. */

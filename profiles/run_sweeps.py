@@ -34,4 +34,5 @@ for r in range(a.reps):
     ctx.dATx(u, ou)
     p = ctx.profile_read()
     print(f"rep {r}: X.v {p['ax_ms']:.3f} ms = {bed / p['ax_ms'] / 1e6:.0f} GB/s | X^T.u {p['atx_ms']:.3f} ms = {bed / p['atx_ms'] / 1e6:.0f} GB/s")
+print(f"twin layout state: {ctx.twin_state()} (1 = X.v walks the individual-major twin)")
 ctx.close()

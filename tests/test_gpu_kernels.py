@@ -198,6 +198,30 @@ def test_missing_list_equals_second_walk(C, oracle, N, M, miss, monkeypatch):
     assert relerr(res["list"][0], ds.ATx(u)) < TOL_MATVEC
 
 
+@pytest.mark.parametrize("N,M,miss", [(70_001, 301, 0.02), (4099, 1030, 0.0), (2500, 333, 0.05)])
+def test_twin_layout_is_bit_identical(C, oracle, N, M, miss, monkeypatch):
+    """X.v on the individual-major twin of the matrix (twin.cu: byte k of a word = the table index of individual k) and
+    X.v on the one matrix (index gathered with mask + multiply) walk the same tables and add the same integers: the
+    results must agree BIT FOR BIT, with phenotype NAs, ragged N / M and missing genotypes; people statistics (the same
+    walk with other tables) likewise.  Both are within the mat-vec tolerance of the oracle."""
+    bed = oracle.synth_bed(37, 0, M, N, miss_rate=miss)
+    present = np.ones(N, bool)
+    present[np.random.default_rng(5).choice(N, N // 50, replace=False)] = False
+    mask4 = oracle.make_mask4(N, present)
+    ds = oracle.Dataset(bed, N, mask4=mask4, nonas=int(present.sum()))
+    v = np.random.default_rng(4).normal(size=M)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GVB_TWIN", mode)
+        with make_ctx(C, "lut") as ctx:
+            ctx.load_host(bed, N).set_mask(mask4, int(present.sum())).compute_stats(1.0)
+            assert ctx.twin_state() == 0                             # decided by the first X.v
+            res[mode] = (ctx.Ax(v), ctx.Ax(2.5 * v), ctx.twin_state())
+    assert res["0"][2] == 0 and res["1"][2] == 1                     # really bypassed / really built
+    assert np.array_equal(res["0"][0], res["1"][0]) and np.array_equal(res["0"][1], res["1"][1])
+    assert relerr(res["1"][0], ds.Ax(v)) < TOL_MATVEC
+
+
 def test_vector_ops(C, oracle):
     N, M = 512, 3001
     bed = oracle.synth_bed(1, 0, M, N)

@@ -80,6 +80,8 @@ SIGNATURES = {
     "gvb_probit_denoise": (ci, [vp, vp, vp, vp, cd, cd, vp, c_f64p]),
     "gvb_missing_list_entries": (cl, [vp]),
     "gvb_twin_state": (ci, [vp]),
+    "gvb_snapshot_begin": (ci, [vp, vp, cl, ci]),
+    "gvb_snapshot_wait": (ci, [vp, ci, ctypes.POINTER(c_f64p), ctypes.POINTER(cl)]),
     "gvb_assoc_pvals": (ci, [vp, vp, vp, vp, vp]),
     "gvb_probit_cov_pass": (ci, [vp, vp, vp, vp, ci, c_f64p, cd, ci, c_f64p]),
     "gvb_probit_cov_apply": (ci, [vp, vp, ci, c_f64p, vp]),
@@ -403,6 +405,15 @@ class Context:
 
     def missing_list_entries(self) -> int:
         return self.L.gvb_missing_list_entries(self.h)
+
+    def snapshot_begin(self, vec, n, slot):
+        _chk(self.L.gvb_snapshot_begin(self.h, vec.h, n, slot))
+
+    def snapshot_wait(self, slot):
+        """copy of the pinned host buffer of a snapshot (blocks until the device -> host copy has landed)"""
+        ptr, n = c_f64p(), cl()
+        _chk(self.L.gvb_snapshot_wait(self.h, slot, ctypes.byref(ptr), ctypes.byref(n)))
+        return np.ctypeslib.as_array(ptr, shape=(n.value,)).copy()
 
     def twin_state(self) -> int:
         """1: X.v walks the individual-major twin of the matrix, -1: no twin (too large / GVB_TWIN=0), 0: not decided yet"""

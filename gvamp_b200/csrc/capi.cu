@@ -128,6 +128,13 @@ extern "C" void gvb_ctx_destroy(gvb_ctx* c) {
     gvb_twin_reset(c);
     fr(c->tab_u); fr(c->tab_v); fr(c->acc_i64); fr(c->red_partial); fr(c->red_result); fr(c->scal); fr(c->work_counter);
     if (c->h_red) cudaFreeHost(c->h_red);
+    for (auto& sn : c->snap) {
+        if (sn.dev) cudaFree(sn.dev);
+        if (sn.host) cudaFreeHost(sn.host);
+        if (sn.ready) cudaEventDestroy(sn.ready);
+        if (sn.done) cudaEventDestroy(sn.done);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (int i = 0; i < 8; i++) { cudaEventDestroy(c->ev_start[i]); cudaEventDestroy(c->ev_stop[i]); }
     if (c->comm && c->owns_comm) ncclCommDestroy(c->comm);
     cudaStreamDestroy(c->stream);
@@ -218,6 +225,46 @@ extern "C" int gvb_vec_download(gvb_ctx* c, gvb_vec src, double* dst, long n) {
     GVB_ARG(c && dst && src && n >= 0 && n <= src->n, "download length");
     GVB_CUDA(cudaMemcpyAsync(dst, src->d, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     GVB_CUDA(cudaStreamSynchronize(c->stream));
+    return GVB_OK;
+}
+// Snapshots: the vector is copied to a staging buffer on the library stream (ordered with the kernels that produce and later
+// overwrite it), then leaves for pinned host memory on a second stream, overlapping whatever the library stream does next.
+extern "C" int gvb_snapshot_begin(gvb_ctx* c, gvb_vec src, long n, int slot) {
+    GVB_ARG(c && src && n >= 0 && n <= src->n, "snapshot length");
+    GVB_ARG(slot >= 0 && slot < GVB_SNAP_SLOTS, "snapshot slot");
+    gvb_ctx::Snap& sn = c->snap[slot];
+    if (!c->copy_stream) GVB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!sn.ready) {
+        GVB_CUDA(cudaEventCreateWithFlags(&sn.ready, cudaEventDisableTiming));
+        GVB_CUDA(cudaEventCreateWithFlags(&sn.done, cudaEventDisableTiming));
+    }
+    if (sn.pending) GVB_CUDA(cudaEventSynchronize(sn.done));   // an unread snapshot in this slot is simply replaced
+    if (sn.cap < n) {
+        if (sn.dev) cudaFree(sn.dev);
+        if (sn.host) cudaFreeHost(sn.host);
+        sn.dev = sn.host = nullptr;
+        sn.cap = 0;
+        GVB_CUDA(cudaMalloc(&sn.dev, std::max(n, 1l) * sizeof(double)));
+        GVB_CUDA(cudaMallocHost(&sn.host, std::max(n, 1l) * sizeof(double)));
+        sn.cap = n;
+    }
+    sn.n = n;
+    GVB_CUDA(cudaMemcpyAsync(sn.dev, src->d, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    GVB_CUDA(cudaEventRecord(sn.ready, c->stream));
+    GVB_CUDA(cudaStreamWaitEvent(c->copy_stream, sn.ready, 0));
+    GVB_CUDA(cudaMemcpyAsync(sn.host, sn.dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    GVB_CUDA(cudaEventRecord(sn.done, c->copy_stream));
+    sn.pending = true;
+    return GVB_OK;
+}
+extern "C" int gvb_snapshot_wait(gvb_ctx* c, int slot, const double** host, long* n) {
+    GVB_ARG(c && slot >= 0 && slot < GVB_SNAP_SLOTS && host, "snapshot slot / pointer");
+    gvb_ctx::Snap& sn = c->snap[slot];
+    GVB_ARG(sn.done && sn.host, "no snapshot was begun in this slot");
+    if (sn.pending) GVB_CUDA(cudaEventSynchronize(sn.done));
+    sn.pending = false;
+    *host = sn.host;
+    if (n) *n = sn.n;
     return GVB_OK;
 }
 extern "C" int gvb_vec_copy(gvb_ctx* c, gvb_vec dst, gvb_vec src) {

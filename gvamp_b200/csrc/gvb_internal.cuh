@@ -32,6 +32,7 @@
 #define GVB_GROUP 4               // markers per interleaved word
 #define GVB_GROUP_TILE 32         // marker groups per table tile (Mg_pad is a multiple of this)
 #define GVB_PAD_BYTE 0x55u
+#define GVB_SNAP_SLOTS 8
 
 struct gvb_vec_s {
     double* d;
@@ -100,6 +101,17 @@ struct gvb_ctx {
     int* work_counter = nullptr;
     double* scal = nullptr;         // small device scalars
     int kernel_gen = 2;             // 0: simple FP64 kernels, 1: gen-1 table kernels, 2: gen-2 tile kernels (env GVB_KERNELS)
+
+    // asynchronous device -> host snapshots of vectors (capi.cu): the iteration outputs leave over a copy stream while
+    // the sweeps go on; staging in HBM decouples them from later updates of the vector
+    struct Snap {
+        double* dev = nullptr;    // staging copy in HBM
+        double* host = nullptr;   // pinned
+        long cap = 0, n = 0;
+        cudaEvent_t ready = nullptr, done = nullptr;
+        bool pending = false;
+    } snap[GVB_SNAP_SLOTS];
+    cudaStream_t copy_stream = nullptr;
 
     // timers and counters
     cudaEvent_t ev_start[8], ev_stop[8];

@@ -28,16 +28,21 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[K], double* __res
     __syncthreads();
 }
 
-__global__ void reduce_final_kernel(const double* __restrict__ partial, int nblocks, int K, double* __restrict__ result) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= K) return;
-    double s = 0.0;
-    for (int b = 0; b < nblocks; b++) s += partial[b * K + k];   // fixed order: deterministic
-    result[k] = s;
+// one warp per scalar: lane l adds partials l, l+32, ... in order, then a fixed shuffle tree: deterministic, and a chain of
+// nblocks/32 dependent FP64 additions instead of nblocks (this launch sits on the host-visible path of every CG iteration)
+__global__ void __launch_bounds__(1024) reduce_final_kernel(const double* __restrict__ partial, int nblocks, int K, double* __restrict__ result) {
+    const int lane = threadIdx.x & 31;
+    for (int k = threadIdx.x >> 5; k < K; k += blockDim.x >> 5) {
+        double s = 0.0;
+        for (int b = lane; b < nblocks; b += 32) s += partial[b * K + k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) result[k] = s;
+    }
 }
 
 int gvb_reduce_finish(gvb_ctx* c, int nblocks, int K, bool sync, double* res_host) {
-    reduce_final_kernel<<<1, 128, 0, c->stream>>>(c->red_partial, nblocks, K, c->red_result);
+    reduce_final_kernel<<<1, 32 * std::min(K, 32), 0, c->stream>>>(c->red_partial, nblocks, K, c->red_result);
     GVB_LAUNCHED(c);
     if (sync && c->nranks > 1) {
         // replaces the per-scalar MPI_Allreduce calls (utilities.cpp:203, vamp.cpp:313,990,1012-1013)

@@ -64,6 +64,8 @@ vamp::vamp(int N, int M, int Mt, double gam1, double gamw, int max_iter, double 
     reference_sweeps = rs && rs[0] == '1';
     const char* ow = getenv("GVB_ONSAGER_WARM");
     onsager_warm = !(ow && ow[0] == '0') && !reference_sweeps;
+    const char* ao = getenv("GVB_ASYNC_OUT");
+    async_outputs = !(ao && ao[0] == '0');
 }
 
 vamp::vamp(int M, double gam1, double gamw, std::vector<double> true_signal, int rank, Options opt)
@@ -93,6 +95,8 @@ vamp::vamp(int M, double gam1, double gamw, std::vector<double> true_signal, int
     reference_sweeps = rs && rs[0] == '1';
     const char* ow = getenv("GVB_ONSAGER_WARM");
     onsager_warm = !(ow && ow[0] == '0') && !reference_sweeps;
+    const char* ao = getenv("GVB_ASYNC_OUT");
+    async_outputs = !(ao && ao[0] == '0');
 }
 
 vamp::~vamp() { dev_close(); }
@@ -132,6 +136,53 @@ void vamp::store_scaled(gvb_vec v, const std::string& path, double div, int S) {
     if (!files_enabled()) return;
     for (double& x : h) x = x / div;
     mpi_store_vec_to_file(path, h, S, M);
+}
+
+// One output vector of the iteration (the z1 csv of vamp.cpp:435-436 and the x1_hat / r1 / r2 / x2_hat stores of
+// vamp.cpp:453,462,542,612).  Asynchronous form: a snapshot starts here and flush_outputs() finishes it.
+void vamp::emit_output(int which, gvb_vec v, size_t n, const std::string& path, double scale, int S) {
+    snap_path[which] = path;
+    if (async_outputs) {
+        DEV(gvb_snapshot_begin(dev.ctx, v, (long)n, which));
+        snap_open[which] = true;
+        return;
+    }
+    std::vector<double> h;
+    sync_host(v, h, n);
+    finish_output(which, h.data(), n, scale, S);
+}
+
+void vamp::finish_output(int which, const double* h, size_t n, double scale, int S) {
+    const std::string& path = snap_path[which];
+    if (which == SNAP_Z1) {
+        z1.assign(h, h + n);
+        if (files_enabled() && rank == 0) {
+            std::ofstream f(path);
+            for (double v : z1) f << v << '\n';
+        }
+        return;
+    }
+    if (which == SNAP_X1) {
+        x1_hat.assign(h, h + n);
+        for (size_t i = 0; i < n; i++) x1_hat_stored[i] = x1_hat[i] / scale;
+        if (files_enabled()) mpi_store_vec_to_file(path, x1_hat_stored, S, M);
+        return;
+    }
+    if (!files_enabled()) return;
+    std::vector<double> scaled(n);
+    for (size_t i = 0; i < n; i++) scaled[i] = h[i] / scale;
+    mpi_store_vec_to_file(path, scaled, S, M);
+}
+
+void vamp::flush_outputs(double scale, int S) {
+    for (int which = 0; which < SNAP_COUNT; which++) {
+        if (!snap_open[which]) continue;
+        const double* h = nullptr;
+        long n = 0;
+        DEV(gvb_snapshot_wait(dev.ctx, which, &h, &n));
+        snap_open[which] = false;
+        finish_output(which, h, (size_t)n, scale, S);
+    }
 }
 
 void vamp::dev_denoise(double g1_prec, double* sum_d, double* dist2) {
@@ -301,25 +352,19 @@ bool vamp::linear_iteration(data* dataset, int it) {
 
         double start_z1 = wtime();
         DEV(gvb_dAx(ctx, dev.x1, dev.z1));
-        sync_host(dev.z1, z1, 4 * dataset->get_mbytes());
+        std::string filepath_out_z1 = out_dir + out_name + "_z1_it_" + std::to_string(it) + ".csv";
+        emit_output(SNAP_Z1, dev.z1, 4 * dataset->get_mbytes(), filepath_out_z1, scale, S);
         double end_z1 = wtime();
         if (rank == 0) std::cout << "time needed to calculate z1 = " << end_z1 - start_z1 << " seconds" << std::endl;
-        std::string filepath_out_z1 = out_dir + out_name + "_z1_it_" + std::to_string(it) + ".csv";
-        if (files_enabled() && rank == 0) {
-            std::ofstream f(filepath_out_z1);
-            for (double v : z1) f << v << '\n';
-        }
         if (rank == 0) std::cout << "filepath_out_z1 = " << filepath_out_z1 << std::endl;
         if (rank == 0) std::cout << "rho = " << rho << std::endl;
 
         double start_saving = wtime();
         std::string filepath_out = out_dir + out_name + "_it_" + std::to_string(it) + ".bin";
-        sync_host(dev.x1, x1_hat, M);
-        for (int i = 0; i < M; i++) x1_hat_stored[i] = x1_hat[i] / scale;
-        if (files_enabled()) mpi_store_vec_to_file(filepath_out, x1_hat_stored, S, M);
+        emit_output(SNAP_X1, dev.x1, M, filepath_out, scale, S);
         if (rank == 0) std::cout << "x1_hat filepath_out is " << filepath_out << std::endl;
         std::string filepath_out_r1 = out_dir + out_name + "_r1_it_" + std::to_string(it) + ".bin";
-        store_scaled(dev.r1, filepath_out_r1, scale, S);
+        emit_output(SNAP_R1, dev.r1, M, filepath_out_r1, scale, S);
         if (rank == 0) std::cout << "r1 filepath_out is " << filepath_out_r1 << std::endl;
         if (rank == 0) std::cout << "time needed to save beta1 to an external file = " << wtime() - start_saving << " seconds" << std::endl;
 
@@ -353,7 +398,7 @@ bool vamp::linear_iteration(data* dataset, int it) {
 
         // ================= LMMSE step =================
         std::string filepath_out_r2 = out_dir + out_name + "_r2_it_" + std::to_string(it) + ".bin";
-        store_scaled(dev.r2, filepath_out_r2, scale, S);
+        emit_output(SNAP_R2, dev.r2, M, filepath_out_r2, scale, S);
         if (rank == 0) std::cout << "r2 filepath_out is " << filepath_out_r2 << std::endl;
         double start_lmmse_step = wtime();
         if (rank == 0) std::cout << "______________________" << std::endl << "->LMMSE" << std::endl;
@@ -393,7 +438,7 @@ bool vamp::linear_iteration(data* dataset, int it) {
         dev.ax_x2_valid = !reference_sweeps;
         }
         std::string filepath_out_x2 = out_dir + out_name + "_it_" + std::to_string(it) + "_x2_hat.bin";
-        store_scaled(dev.x2, filepath_out_x2, scale, S);
+        emit_output(SNAP_X2, dev.x2, M, filepath_out_x2, scale, S);
         if (rank == 0) std::cout << "x2_hat filepath_out is " << filepath_out_x2 << std::endl;
         if (rank == 0) std::cout << "CG took " << wtime() - start_CG << " seconds." << std::endl;
 
@@ -431,6 +476,7 @@ bool vamp::linear_iteration(data* dataset, int it) {
 
         updateNoisePrec(dataset);
         err_measures(dataset, 2);
+        flush_outputs(scale, S);   // the snapshots of this iteration's outputs have landed long ago: scale and write them
 
         double end_lmmse_step = wtime();
         if (rank == 0) std::cout << "lmmse step took " << end_lmmse_step - start_lmmse_step << " seconds." << std::endl;
@@ -510,11 +556,17 @@ double vamp::g1d(double x, double gam1) {
 double vamp::g2d_onsager(double gam2, double tau, data* dataset) {
     dev_open(dataset);
     // Rademacher probe +-1/sqrt(Mt) from mt19937{seed + S}: identical stream to the reference on every shard
-    std::mt19937 rd{seed + (long unsigned int)dataset->get_S()};
-    std::bernoulli_distribution bern(0.5);
-    bern_vec.assign(M, 0.0);
-    for (int i = 0; i < M; i++) bern_vec[i] = (2 * bern(rd) - 1) / sqrt(Mt);
-    DEV(gvb_vec_upload(dev.ctx, dev.bern, bern_vec.data(), M));
+    // (the reference re-draws it every iteration from the same seed, vamp.cpp:875-882: drawn and uploaded once here)
+    const long bern_key = (long)seed + (long)dataset->get_S();
+    if (!dev.bern_valid || dev.bern_key != bern_key || (int)bern_vec.size() != M) {
+        std::mt19937 rd{seed + (long unsigned int)dataset->get_S()};
+        std::bernoulli_distribution bern(0.5);
+        bern_vec.assign(M, 0.0);
+        for (int i = 0; i < M; i++) bern_vec[i] = (2 * bern(rd) - 1) / sqrt(Mt);
+        DEV(gvb_vec_upload(dev.ctx, dev.bern, bern_vec.data(), M));
+        dev.bern_valid = true;
+        dev.bern_key = bern_key;
+    }
     this->gam2 = gam2;
     double d3[3] = {0, 0, 0};
     if (onsager_warm) {

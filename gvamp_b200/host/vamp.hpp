@@ -96,7 +96,18 @@ private:
         int onsager_age = -1;
         gvb_vec aty = nullptr;      // A^T y: y is constant over the linear model's iterations, so the reference's per-iteration
         bool aty_valid = false;     // sweep (vamp.cpp:588) is done once and reused until y is uploaded again
+        bool bern_valid = false;    // dev.bern holds the Onsager probe of (seed, shard): the reference re-draws the SAME probe every
+        long bern_key = -1;         // iteration (mt19937{seed + S}, vamp.cpp:875-882), so it is drawn and uploaded once
     } dev;
+    // the iteration's output vectors leave the device as asynchronous snapshots (gvb_snapshot_begin) while the LMMSE sweeps run
+    // and are scaled / written by flush_outputs() at the end of the iteration; GVB_ASYNC_OUT=0: synchronous, in place
+    enum { SNAP_Z1 = 0, SNAP_X1, SNAP_R1, SNAP_R2, SNAP_X2, SNAP_COUNT };
+    bool async_outputs = true;
+    std::string snap_path[SNAP_COUNT];
+    bool snap_open[SNAP_COUNT] = {false, false, false, false, false};
+    void emit_output(int which, gvb_vec v, size_t n, const std::string& path, double scale, int S);
+    void finish_output(int which, const double* h, size_t n, double scale, int S);
+    void flush_outputs(double scale, int S);
     void dev_open(data* dataset);
     void dev_close();
     void dev_denoise(double g1_prec, double* sum_d, double* dist2);

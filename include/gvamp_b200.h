@@ -135,6 +135,13 @@ long gvb_vec_len(gvb_vec v);
 void* gvb_vec_ptr(gvb_vec v);                                   /* raw device pointer */
 int gvb_vec_upload(gvb_ctx* ctx, gvb_vec dst, const double* src, long n);
 int gvb_vec_download(gvb_ctx* ctx, gvb_vec src, double* dst, long n);
+/* Asynchronous snapshot of the first n entries of a vector into pinned host memory: the per-iteration outputs of
+ * vamp::infere_linear (z1 / x1_hat / r1 / r2 / x2_hat files, vamp.cpp:435-462,542,612) leave the device while the LMMSE
+ * sweeps run.  begin: ordered on the library stream like a copy kernel (the vector may be overwritten right after the
+ * call); wait: blocks until that snapshot is in host memory and returns the library-owned pinned buffer, valid until
+ * the next begin on the same slot (0..7) or gvb_ctx_destroy. */
+int gvb_snapshot_begin(gvb_ctx* ctx, gvb_vec src, long n, int slot);
+int gvb_snapshot_wait(gvb_ctx* ctx, int slot, const double** host, long* n);
 int gvb_vec_copy(gvb_ctx* ctx, gvb_vec dst, gvb_vec src);
 int gvb_vec_fill(gvb_ctx* ctx, gvb_vec dst, double value);
 /* out = a*x + b*y (y may be NULL); the M-vector algebra of infere_linear, vamp.cpp:348-354,485-486,

@@ -222,6 +222,28 @@ def test_twin_layout_is_bit_identical(C, oracle, N, M, miss, monkeypatch):
     assert relerr(res["1"][0], ds.Ax(v)) < TOL_MATVEC
 
 
+def test_snapshot_is_ordered_with_the_stream(C, oracle):
+    """gvb_snapshot_begin / _wait: the snapshot holds the vector as it was when begin was called even if it is overwritten
+    right afterwards (staging copy on the library stream), slots are independent, a slot can be reused."""
+    N, M = 512, 30011
+    bed = oracle.synth_bed(1, 0, M, N)
+    a = np.random.default_rng(0).normal(size=M)
+    with C.Context(0) as ctx:
+        ctx.load_host(bed, N)
+        va, vb = ctx.vecM(a), ctx.vecM(-a)
+        ctx.snapshot_begin(va, M, 0)
+        ctx.axpby(va, 3.0, va)                     # overwrite after begin
+        ctx.snapshot_begin(va, M - 7, 1)
+        ctx.snapshot_begin(vb, M, 2)
+        assert np.array_equal(ctx.snapshot_wait(1), (3.0 * a)[:M - 7])
+        assert np.array_equal(ctx.snapshot_wait(0), a)
+        assert np.array_equal(ctx.snapshot_wait(2), -a)
+        ctx.snapshot_begin(vb, 5, 0)               # reuse with another length
+        assert np.array_equal(ctx.snapshot_wait(0), -a[:5])
+        with pytest.raises(RuntimeError):
+            ctx.snapshot_begin(va, M, 8)           # slots are 0..7
+
+
 def test_vector_ops(C, oracle):
     N, M = 512, 3001
     bed = oracle.synth_bed(1, 0, M, N)

@@ -15,7 +15,7 @@ EXE = os.path.join(ROOT, "gvamp_b200", "bin", "main_real")
 TOL_FINAL = 1e-4
 
 
-def _run_case(oracle, tmp_path, g, gen):
+def _run_case(oracle, tmp_path, g, gen, env_extra=None):
     N, M, iters = int(g["N"]), int(g["M"]), int(g["iterations"])
     bed = oracle.synth_bed(int(g["seed"]), 0, M, N)
     bedp, phenp = str(tmp_path / "v.bed"), str(tmp_path / "v.phen")
@@ -30,7 +30,7 @@ def _run_case(oracle, tmp_path, g, gen):
     for k in range(0, len(extra), 2):
         if extra[k] not in skip:
             args += [extra[k], extra[k + 1]]
-    env = dict(os.environ, GVB_KERNELS=gen)
+    env = dict(os.environ, GVB_KERNELS=gen, **(env_extra or {}))
     r = subprocess.run([EXE] + args, capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return outd, r.stdout, iters
@@ -57,6 +57,21 @@ def test_linear_vamp_matches_reference_files(oracle, tmp_path, gen):
     assert np.allclose(pv[-1], g["prior_vars_last"], rtol=TOL_FINAL) and np.allclose(pp[-1], g["prior_probs_last"], rtol=TOL_FINAL)
     alpha2 = [float(l.split("=")[1]) for l in log.splitlines() if l.startswith("alpha2 = ")]
     assert np.allclose(alpha2, g["alpha2_log"], rtol=TOL_FINAL)
+
+
+def test_async_outputs_write_the_same_files(oracle, tmp_path):
+    """The iteration outputs leave the device as asynchronous snapshots and are written at the end of the iteration
+    (vamp::emit_output / flush_outputs); GVB_ASYNC_OUT=0 downloads and writes each one in place like the reference.  Same
+    arithmetic, same bytes: every output file of the two runs must be identical."""
+    g = golden("vamp_linear.npz")
+    outs = {}
+    for mode in ("1", "0"):
+        (tmp_path / mode).mkdir()
+        outs[mode], _, iters = _run_case(oracle, tmp_path / mode, g, "lut", {"GVB_ASYNC_OUT": mode})
+    names = sorted(os.listdir(outs["1"]))
+    assert names == sorted(os.listdir(outs["0"])) and len(names) >= 5 * iters
+    for fn in names:
+        assert open(outs["1"] + fn, "rb").read() == open(outs["0"] + fn, "rb").read(), fn
 
 
 def test_config1_matches_reference(oracle, tmp_path):

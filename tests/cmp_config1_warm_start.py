@@ -1,3 +1,5 @@
+"""Checker script (not a pytest module): config 1 against the reference golden run with the Onsager warm start on and off;
+prints the margins quoted in DESIGN.md section 7.  Uses the oracle only to regenerate the synthetic bed / phen files."""
 import os, sys, subprocess, tempfile, numpy as np
 sys.path.insert(0, os.environ.get("GRAFT_REPO_ROOT", "/root/repo"))
 ROOT = os.environ.get("GRAFT_REPO_ROOT", "/root/repo")

@@ -445,8 +445,13 @@ int launch_atx(gvb_ctx* c, const int* tab, unsigned long long* acc) {
 // scal[] layout (device doubles): [0] scale of X^T.u, [1] its inverse, [2] scale of X.v, [3] its inverse,
 // [8] / [9]: running maxima (bit patterns of non-negative doubles, ordered like unsigned integers) of the X^T.u / X.v
 // magnitude bounds; the finish kernel of a sweep re-arms its maximum to 0 for the next sweep.
+// [10] / [11]: 1.0 when the input vector of the running X^T.u / X.v sweep holds a NaN or an infinity.  The reference's FP64 sums then
+// turn every output into NaN (0 * NaN in the LUT products of data.cpp:766 / :975); fixed point cannot carry a NaN, so the
+// sweep carries this flag from its build kernel to its finish kernel instead.
 #define SCAL_ATX_BOUND 8
 #define SCAL_AX_BOUND 9
+#define SCAL_ATX_BAD 10
+#define SCAL_AX_BAD 11
 
 // power-of-two scale such that `window` table entries of magnitude <= bound * scale (+ slack) cannot overflow an int32
 __device__ __forceinline__ double scale_for(double bound, double window, double slack) {
@@ -492,6 +497,7 @@ __global__ void __launch_bounds__(128) ax_prep_kernel(const double* __restrict__
     double v00, v10, v11;
     ax_code_values(mode, v ? v[j] : 1.0, mave[j], msig[j], v00, v10, v11);
     double e = fmax(fmax(fabs(v00), fabs(v11)), fabs(v10));
+    if (!isfinite(v00 + v10 + v11)) e = INFINITY;   // fmax drops NaNs: a non-finite input makes the bound non-finite
     __shared__ double sm[4];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
@@ -514,6 +520,7 @@ __global__ void __launch_bounds__(256) ax_build_kernel(const double* __restrict_
         if (T == 0) {
             scal[2] = sc;
             scal[3] = 1.0 / sc;
+            scal[SCAL_AX_BAD] = isfinite(scal[SCAL_AX_BOUND]) ? 0.0 : 1.0;
         }
     }
     __syncthreads();
@@ -543,7 +550,8 @@ __global__ void ax_finish_kernel(const unsigned long long* __restrict__ acc, dou
     if (i == 0) scal[SCAL_AX_BOUND] = 0.0;
     if (i >= Npad) return;
     bool present = (maskw[i >> 2] >> (2 * (i & 3))) & 1u;
-    out[i] = present ? (double)(long long)acc[i] * scal[3] * inv_sqrt_n : 0.0;
+    const double val = scal[SCAL_AX_BAD] != 0.0 ? __longlong_as_double(0x7ff8000000000000ll) : (double)(long long)acc[i] * scal[3] * inv_sqrt_n;
+    out[i] = present ? val : 0.0;
 }
 
 // ---- X^T . u --------------------------------------------------------------------------------------
@@ -556,7 +564,9 @@ __global__ void __launch_bounds__(256) atx_prep_kernel(const double* __restrict_
     for (long p = tid; p < npos; p += nth) {
         const double2* up = reinterpret_cast<const double2*>(u + 4 * p);
         double2 a = up[0], b = up[1];
-        m = fmax(m, 2.0 * (fabs(a.x) + fabs(a.y) + fabs(b.x) + fabs(b.y)));
+        double s4 = 2.0 * (fabs(a.x) + fabs(a.y) + fabs(b.x) + fabs(b.y));
+        if (!isfinite(s4)) s4 = INFINITY;   // fmax drops NaNs: a non-finite input makes the bound non-finite
+        m = fmax(m, s4);
     }
     for (long i = tid; i < nacc; i += nth) acc[i] = 0ull;
     if (tid == 0) *usum = 0;
@@ -578,6 +588,7 @@ __global__ void __launch_bounds__(256) atx_build_kernel(const double* __restrict
         if (t == 0) {
             scal[0] = sc;
             scal[1] = 1.0 / sc;
+            scal[SCAL_ATX_BAD] = isfinite(scal[SCAL_ATX_BOUND]) ? 0.0 : 1.0;
         }
     }
     __syncthreads();
@@ -605,11 +616,17 @@ __global__ void __launch_bounds__(256) atx_build_kernel(const double* __restrict
 
 // out[j] = sigma_j * (A_j - mu_j * B_j) / scale / sqrt(N),  B_j = sum_i U_i - sum_{i missing in j} U_i
 __global__ void atx_finish_kernel(const unsigned long long* __restrict__ acc, const unsigned long long* __restrict__ accm, const long long* __restrict__ usum,
-                                  double* __restrict__ scal, const double* __restrict__ mave, const double* __restrict__ msig, long Mpad,
+                                  double* __restrict__ scal, const double* __restrict__ mave, const double* __restrict__ msig, long Mpad, long M,
                                   double inv_sqrt_n, double* __restrict__ out, double* __restrict__ outB) {
     long j = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (j == 0) scal[SCAL_ATX_BOUND] = 0.0;
     if (j >= Mpad) return;
+    if (scal[SCAL_ATX_BAD] != 0.0) {   // non-finite input: every marker's sum is NaN in the reference; padded markers stay 0
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        out[j] = j < M ? nan : 0.0;
+        if (outB) outB[j] = j < M ? nan : 0.0;
+        return;
+    }
     long long A = (long long)acc[j];
     long long Bs = *usum - (accm ? (long long)accm[j] : 0ll);
     double inv_s = scal[1];
@@ -715,7 +732,7 @@ int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB) {
         GVB_CHECK(gvb_misslist_sum(c, accm));
     else if (miss)
         GVB_CHECK(atx_main(c, c->tab_u + total, accm));
-    atx_finish_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, c->stream>>>(acc, miss ? accm : nullptr, usum, c->scal, c->mave, c->msig, (long)Mpad,
+    atx_finish_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, c->stream>>>(acc, miss ? accm : nullptr, usum, c->scal, c->mave, c->msig, (long)Mpad, c->M,
                                                                              1.0 / sqrt((double)c->N), out, outB);
     GVB_LAUNCHED(c);
     return GVB_OK;

@@ -222,6 +222,37 @@ def test_twin_layout_is_bit_identical(C, oracle, N, M, miss, monkeypatch):
     assert relerr(res["1"][0], ds.Ax(v)) < TOL_MATVEC
 
 
+def test_nonfinite_inputs_turn_the_outputs_into_nan(C, oracle):
+    """A NaN / infinity in the input vector: the reference's FP64 LUT products (0 * NaN, data.cpp:766 / :975) turn EVERY
+    output into NaN.  The fixed-point sweeps cannot carry a NaN through their integer sums, so they flag it (bound kernel ->
+    finish kernel): all markers NaN for X^T.u; all present individuals NaN, masked and padded ones 0 for X.v; and the next
+    sweep on finite data is clean again (nothing sticks in padded entries or scales)."""
+    N, M = 1003, 517
+    bed = oracle.synth_bed(41, 0, M, N, miss_rate=0.01)
+    present = np.ones(N, bool)
+    present[[3, 500, 1002]] = False
+    mask4 = oracle.make_mask4(N, present)
+    ds = oracle.Dataset(bed, N, mask4=mask4, nonas=int(present.sum()))
+    rng = np.random.default_rng(9)
+    v, u = rng.normal(size=M), rng.normal(size=N)
+    with make_ctx(C, "lut") as ctx:
+        ctx.load_host(bed, N).set_mask(mask4, int(present.sum())).compute_stats(1.0)
+        for bad in (np.nan, np.inf, -np.inf):
+            ub, vb = u.copy(), v.copy()
+            ub[77], vb[M - 1] = bad, bad
+            atx, ax = ctx.ATx(ub), ctx.Ax(vb)
+            assert np.isnan(atx).all() and atx.shape == (M,)
+            assert np.isnan(ax[:N][present]).all() and not ax[:N][~present].any() and not ax[N:].any()
+            assert relerr(ctx.ATx(u), ds.ATx(u)) < TOL_MATVEC and relerr(ctx.Ax(v), ds.Ax(v)) < TOL_MATVEC
+        # and through the device-vector entry points used by the solver: padded entries of the M-vector stay finite
+        du, dv, oM, oN = ctx.vecN(np.where(np.arange(N) == 5, np.nan, u)), ctx.vecM(v), ctx.vecM(), ctx.vecN()
+        ctx.dATx(du, oM)
+        ctx.dAx(oM, oN)                       # NaN in -> NaN out
+        assert np.isnan(oN.download(N)[present]).all()
+        ctx.dAx(dv, oN)
+        assert relerr(oN.download(), ds.Ax(v)) < TOL_MATVEC
+
+
 def test_snapshot_is_ordered_with_the_stream(C, oracle):
     """gvb_snapshot_begin / _wait: the snapshot holds the vector as it was when begin was called even if it is overwritten
     right afterwards (staging copy on the library stream), slots are independent, a slot can be reused."""

@@ -309,10 +309,10 @@ template <int GPW, int STAGES, bool HAS_MISS>
 static int launch_atx(gvb_ctx* c, unsigned long long* acc, unsigned long long* accm) {
     using Cfg = AtxCfg<GPW, STAGES, HAS_MISS>;
     auto kern = atx_lut_kernel<GPW, STAGES, HAS_MISS>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0;   // one bit per device
+    if (!(attr_done >> (c->device & 63) & 1ull)) {
         GVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-        attr_done = true;
+        attr_done |= 1ull << (c->device & 63);
     }
     int n_mblocks = (int)((c->Mg_pad + Cfg::GPB - 1) / Cfg::GPB);
     int n_chunks = (int)((c->n_stripes + AT_CHUNK - 1) / AT_CHUNK);
@@ -558,11 +558,11 @@ int gvb_ax_lut(gvb_ctx* c, const double* v, double* out) {
     ax_build_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(v, c->mave, c->msig, n_tiles, c->scal, c->tab_v);
     GVB_LAUNCHED(c);
 
-    static bool attr_done = false;
+    static unsigned long long attr_done = 0;   // one bit per device
     const int smem = TAB_REGION + AX_WARPS * 8192;
-    if (!attr_done) {
+    if (!(attr_done >> (c->device & 63) & 1ull)) {
         GVB_CUDA(cudaFuncSetAttribute(ax_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
+        attr_done |= 1ull << (c->device & 63);
     }
     int n_sblocks = (int)((c->n_stripes + AX_WARPS - 1) / AX_WARPS);
     int n_gchunks = (int)((c->Mg_pad + AX_GCHUNK - 1) / AX_GCHUNK);

@@ -404,10 +404,10 @@ template <int NW, int NS, int MADK, bool TW>
 int launch_ax(gvb_ctx* c, unsigned long long* accN) {
     using Cfg = TileCfg<NW, NS>;
     auto kern = ax_tile_kernel<NW, NS, MADK, TW>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0;   // one bit per device: the attribute is per device, a process may hold several contexts
+    if (!(attr_done >> (c->device & 63) & 1ull)) {
         GVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-        attr_done = true;
+        attr_done |= 1ull << (c->device & 63);
     }
     const long n_tiles = c->Mg_pad / 32;
     int n_sblocks = (int)((c->n_stripes + NW - 1) / NW);
@@ -423,10 +423,10 @@ template <int NW, int NS, bool USE_MAD, int MODE>
 int launch_atx(gvb_ctx* c, const int* tab, unsigned long long* acc) {
     using Cfg = TileCfg<NW, NS>;
     auto kern = atx_tile_kernel<NW, NS, USE_MAD, MODE>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0;   // one bit per device: the attribute is per device, a process may hold several contexts
+    if (!(attr_done >> (c->device & 63) & 1ull)) {
         GVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-        attr_done = true;
+        attr_done |= 1ull << (c->device & 63);
     }
     const long n_tiles = c->Mg_pad / 32;
     int n_gblocks = (int)((n_tiles + NW - 1) / NW);

@@ -10,6 +10,9 @@
  * `class data` / `class vamp` that make up the hot path.  Each declaration cites the reference
  * interface it stands in for (file:line relative to the gVAMP source tree).
  *
+ * Threading and devices: like a rank of the reference, a context is driven by ONE host thread, and a process normally holds
+ * the context(s) of one GPU (gvb_ctx_create makes its device current and the later calls expect it to stay current).
+ *
  * Vector conventions: "host" pointers are ordinary host memory (pinned or not); `gvb_vec` handles
  * are device-resident FP64 vectors owned by the context.  M-vectors are sharded like the markers,
  * N-vectors (length 4*ceil(N/4), padded entries are zero) are replicated on every rank.

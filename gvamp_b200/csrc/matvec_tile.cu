@@ -23,11 +23,13 @@
 //   per-lane slot byte (8 registers hold the 32 slot bytes); the table base is a link-time constant
 //   folded into the LDS immediate.  Per 4 genotypes: [LOP3 + IMAD +] PRMT + LDS + IADD/IMAD.
 //
-// A CTA = NW warps in lock step over tiles (one __syncthreads per tile), sharing the table tile of the
-// step (X.v: warps = NW stripes, same marker tile; X^T.u: warps = NW marker tiles, same stripe), which
-// all threads fetch with 16-byte cp.async into a double buffer interleaved at 128 B.  Bed tiles are
-// per-warp, NS stages deep.  Persistent CTAs pull rectangular work items from an atomic counter; items
-// are ordered so that CTAs running at the same time share their table tiles in L2.
+// A CTA = NW consumer warps + one producer warp.  The consumers walk their tiles step by step and share the table
+// tile of the step (X.v: warps = NW stripes, same marker tile; X^T.u: warps = NW marker tiles, same stripe); the
+// producer warp fetches the table tiles with 16-byte cp.async into a double buffer interleaved at 128 B.  Producer and
+// consumers meet on two pairs of mbarriers (full / empty per buffer, struct TabPipe) instead of a __syncthreads per
+// step, so a warp whose bed tile arrives late does not stall the others.  Bed tiles are per-warp, NS stages deep.
+// Persistent CTAs pull rectangular work items from an atomic counter; items are ordered so that CTAs running at the
+// same time share their table tiles in L2.
 //
 // Arithmetic: fixed point, exact after quantisation, see matvec_lut.cu (scales, pre- and post-kernels).
 #include "gvb_internal.cuh"
@@ -60,6 +62,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier; the bed is read once per
 // sweep, so it is tagged evict-first and leaves the L2 to the lookup tables
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was just read through the generic proxy
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(bar), "l"(policy)
                  : "memory");
@@ -72,8 +75,14 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// arrive on an mbarrier once all cp.async copies this thread has issued so far have landed (the barrier's count includes
+// these arrivals: .noinc)
+__device__ __forceinline__ void cp_async_arrive_on(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
@@ -99,8 +108,24 @@ constexpr int TILE_WORDS = 1024;
 
 template <int NW, int NS>
 struct TileCfg {
-    static constexpr int THREADS = NW * 32;
+    static constexpr int THREADS = NW * 32 + 32;   // NW consumer warps + one producer warp that stages the lookup tables
     static constexpr int SMEM = TAB_REGION + NW * NS * TILE_BYTES + TILE_BYTES;   // + slack for the 4 KB alignment of the bed stages
+};
+
+// The table double buffer is a two-stage producer / consumer pipeline on mbarriers instead of a __syncthreads per step: the
+// producer warp refills buffer b as soon as all NW consumer warps have left it (tab_empty[b]) and a consumer warp starts a step
+// as soon as ITS bed tile and the step's table have landed (tab_full[b]), so a warp whose tile arrives late no longer stalls the
+// others.  Measured on B200 (27.5 GB shard): 15 consumers + producer 5.87 / 5.93 TB/s (X.v / X^T.u) against 5.79 / 5.76 TB/s for 16
+// warps with a __syncthreads per step.  (Dropping the per-step barrier altogether - unsafe, timing only - gave 6.37 TB/s, so the
+// warps still pay for moving within one step of each other; a third table buffer would not fit the 227 KB.  Also measured and
+// not kept: 16 + 1 warps (the register file then allows 96 registers instead of 128: no gain), bed tiles staged through registers
+// with two TMA copies in flight per warp (slower), an L2 prefetch of the bed tiles 1-8 steps ahead (no gain), table rows as 256
+// TMA bulk copies of 128 B (4.7x slower: the copy engine is the limit).)
+struct TabPipe {
+    uint32_t full, empty;   // shared-memory addresses of tab_full[2] / tab_empty[2] (8 bytes apart)
+    uint32_t fills0, fills1;   // how often buffer 0 / 1 has been filled since kernel start (uniform over the CTA)
+    template <int B>
+    __device__ __forceinline__ uint32_t& fills() { return B ? fills1 : fills0; }
 };
 
 // slot bytes of the XOR-skewed walk, 4 per register: byte (tau & 3) of spack[tau >> 2] = ((tau ^ lane) & 31) * 4
@@ -114,14 +139,37 @@ __device__ __forceinline__ void make_spack(unsigned (&spack)[8], int lane) {
     }
 }
 
-// all threads: table tile (32 KB, contiguous in global) -> interleaved buffer `buf` of the table region
-template <int THREADS>
-__device__ __forceinline__ void stage_table(uint32_t tab_sm, int buf, const int* __restrict__ src) {
+// producer warp: table tile (32 KB, contiguous in global) -> interleaved buffer `buf` of the table region, 64 x 16 bytes per lane
+__device__ __forceinline__ void stage_table(uint32_t tab_sm, int buf, const int* __restrict__ src, int lane) {
     const uint32_t dst = tab_sm + buf * 128;
-#pragma unroll
-    for (int c0 = 0; c0 < 2048; c0 += THREADS) {
-        const int c = c0 + threadIdx.x;
-        if (2048 % THREADS == 0 || c < 2048) cp_async16(dst + (c >> 3) * 256 + (c & 7) * 16, src + c * 4);
+#pragma unroll 8
+    for (int c = lane; c < 2048; c += 32) cp_async16(dst + (c >> 3) * 256 + (c & 7) * 16, src + c * 4);
+}
+__device__ __forceinline__ void tab_pipe_init(TabPipe& tp, unsigned long long* s_tab, int consumers) {
+    tp.full = smem_u32(&s_tab[0]);
+    tp.empty = smem_u32(&s_tab[2]);
+    tp.fills0 = tp.fills1 = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(tp.full, 32);
+        mbar_init(tp.full + 8, 32);
+        mbar_init(tp.empty, consumers);
+        mbar_init(tp.empty + 8, consumers);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+}
+// producer: wait until the consumers have left buffer b, refill it, let the copies arrive on tab_full[b]
+template <int B>
+__device__ __forceinline__ void tab_produce(TabPipe& tp, uint32_t tab_sm, const int* __restrict__ src, int lane) {
+    mbar_wait(tp.empty + 8 * B, (tp.fills<B>() & 1) ^ 1);   // a fresh barrier passes the wait for the phase "before the first"
+    stage_table(tab_sm, B, src, lane);
+    cp_async_arrive_on(tp.full + 8 * B);
+    tp.fills<B>()++;
+}
+// producer warp: the tables of the n steps of a work item, buffers alternating from 0
+__device__ __forceinline__ void tab_produce_item(TabPipe& tp, uint32_t tab_sm, const int* __restrict__ src, int n, int lane) {
+    for (int i = 0; i < n; i += 2) {
+        tab_produce<0>(tp, tab_sm, src + (long)i * 8192, lane);
+        if (i + 1 < n) tab_produce<1>(tp, tab_sm, src + (long)(i + 1) * 8192, lane);
     }
 }
 
@@ -163,22 +211,25 @@ __device__ __forceinline__ void ax_consume(const char* __restrict__ tabc, uint32
 }
 
 template <int NW, int NS, int MADK, bool TW>
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __launch_bounds__(NW * 32 + 32, 1)
 ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, long Mg_pad, long n_stripes, int n_sblocks, int n_gchunks,
                int tiles_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out, int one) {
-    using Cfg = TileCfg<NW, NS>;
     extern __shared__ __align__(1024) char smem[];
     __shared__ int s_item;
     __shared__ __align__(8) unsigned long long s_bar[NW * NS];
+    __shared__ __align__(8) unsigned long long s_tab[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool producer = warp == NW;
     const uint32_t tab_sm = smem_u32(smem);
-    const uint32_t bed_sm = ((tab_sm + TAB_REGION + 4095u) & ~4095u) + warp * (NS * TILE_BYTES);   // 4 KB aligned: XOR addressing
-    const uint32_t bar0 = smem_u32(&s_bar[warp * NS]);
-    if (lane == 0) {
+    const uint32_t bed_sm = ((tab_sm + TAB_REGION + 4095u) & ~4095u) + (producer ? 0 : warp) * (NS * TILE_BYTES);   // 4 KB aligned: XOR addressing
+    const uint32_t bar0 = smem_u32(&s_bar[(producer ? 0 : warp) * NS]);
+    if (lane == 0 && !producer) {
 #pragma unroll
         for (int s = 0; s < NS; s++) mbar_init(bar0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    TabPipe tp;
+    tab_pipe_init(tp, s_tab, NW);
     const uint64_t pol = policy_evict_first();
     unsigned spack[8];
     make_spack(spack, lane);
@@ -195,13 +246,17 @@ ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, l
         if (item >= n_items) break;
         // marker-chunk major order: CTAs running at the same time share the chunk's tables in L2
         const int gc = item / n_sblocks, sb = item % n_sblocks;
-        const long t = (long)sb * NW + warp;
-        const bool active = t < n_stripes;
         const long tile_lo = (long)gc * tiles_per_chunk;
         const int nt = (int)min((long)tiles_per_chunk, n_tiles - tile_lo);
-        const uint32_t* bsrc = bed + ((active ? t : 0) * Mg_pad + tile_lo * 32) * 32;
         const int* tsrc = tabv + tile_lo * 8192;
 
+        if (producer) {
+            tab_produce_item(tp, tab_sm, tsrc, nt, lane);
+            continue;
+        }
+        const long t = (long)sb * NW + warp;
+        const bool active = t < n_stripes;
+        const uint32_t* bsrc = bed + ((active ? t : 0) * Mg_pad + tile_lo * 32) * 32;
         auto issue_bed = [&](int i) {
             if (active && i < nt) {
                 if (lane == 0) {
@@ -212,24 +267,17 @@ ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, l
                 n_fill++;
             }
         };
-        auto issue_tab = [&](int i) {
-            if (i < nt) stage_table<Cfg::THREADS>(tab_sm, i & 1, tsrc + (long)i * 8192);
-            cp_async_commit();
-        };
-
 #pragma unroll
         for (int s = 0; s < NS - 1; s++) issue_bed(s);
-        issue_tab(0);
         long long acc64[4] = {0, 0, 0, 0};
 
         for (int i0 = 0; i0 < nt; i0 += 2) {
 #define AX_STEP(B)                                                                           \
     if (i0 + B < nt) {                                                                       \
         const int i = i0 + B;                                                                \
-        cp_async_wait_all();                                                                 \
-        __syncthreads(); /* table i visible; everyone is done with tile i-1 */               \
-        issue_tab(i + 1);                                                                    \
-        issue_bed(i + NS - 1);                                                               \
+        issue_bed(i + NS - 1); /* its stage was consumed in step i-1 by this same warp */    \
+        mbar_wait(tp.full + 8 * B, tp.fills<B>() & 1); /* table i has landed */              \
+        tp.fills<B>()++;                                                                     \
         if (active) {                                                                        \
             const uint32_t s = n_use % NS;                                                   \
             mbar_wait(bar0 + 8 * s, (n_use / NS) & 1);                                       \
@@ -238,12 +286,13 @@ ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, l
             ax_consume<B, MADK, TW>(smem, bed_sm + s * TILE_BYTES + lane_off, spack, one, a32); \
             _Pragma("unroll") for (int k = 0; k < 4; k++) acc64[k] += (long long)a32[k];     \
         }                                                                                    \
+        __syncwarp();                                                                        \
+        if (lane == 0) mbar_arrive(tp.empty + 8 * B); /* this warp has left table buffer B */ \
     }
             AX_STEP(0)
             AX_STEP(1)
 #undef AX_STEP
         }
-        cp_async_wait_all();
         if (active) {
 #pragma unroll
             for (int k = 0; k < 4; k++)
@@ -276,22 +325,25 @@ __device__ __forceinline__ void atx_consume(const char* __restrict__ tabc, uint3
 // stripe adds at most 32 x 4 = 128 to each of them, and the per-stripe flush widens them to three 21-bit counters of
 // the int64 accumulator.
 template <int NW, int NS, bool USE_MAD, int MODE>
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __launch_bounds__(NW * 32 + 32, 1)
 atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, long Mg_pad, long n_stripes, int n_gblocks, int n_schunks,
                 int stripes_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out, int one) {
-    using Cfg = TileCfg<NW, NS>;
     extern __shared__ __align__(1024) char smem[];
     __shared__ int s_item;
     __shared__ __align__(8) unsigned long long s_bar[NW * NS];
+    __shared__ __align__(8) unsigned long long s_tab[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool producer = warp == NW;
     const uint32_t tab_sm = smem_u32(smem);
-    const uint32_t bed_sm = ((tab_sm + TAB_REGION + 4095u) & ~4095u) + warp * (NS * TILE_BYTES);
-    const uint32_t bar0 = smem_u32(&s_bar[warp * NS]);
-    if (lane == 0) {
+    const uint32_t bed_sm = ((tab_sm + TAB_REGION + 4095u) & ~4095u) + (producer ? 0 : warp) * (NS * TILE_BYTES);
+    const uint32_t bar0 = smem_u32(&s_bar[(producer ? 0 : warp) * NS]);
+    if (lane == 0 && !producer) {
 #pragma unroll
         for (int s = 0; s < NS; s++) mbar_init(bar0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    TabPipe tp;
+    tab_pipe_init(tp, s_tab, NW);
     const uint64_t pol = policy_evict_first();
     unsigned spack[8];
     make_spack(spack, lane);
@@ -308,13 +360,17 @@ atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
         if (item >= n_items) break;
         // stripe-chunk major order: CTAs running at the same time share the chunk's tables in L2
         const int sc = item / n_gblocks, gb = item % n_gblocks;
-        const long T = (long)gb * NW + warp;
-        const bool active = T < n_tiles;
         const long t_lo = (long)sc * stripes_per_chunk;
         const int ns = (int)min((long)stripes_per_chunk, n_stripes - t_lo);
-        const uint32_t* bsrc = bed + (t_lo * Mg_pad + (active ? T : 0) * 32) * 32;   // + i * Mg_pad * 32 words per stripe
         const int* tsrc = tab + t_lo * 8192;
 
+        if (producer) {
+            tab_produce_item(tp, tab_sm, tsrc, ns, lane);
+            continue;
+        }
+        const long T = (long)gb * NW + warp;
+        const bool active = T < n_tiles;
+        const uint32_t* bsrc = bed + (t_lo * Mg_pad + (active ? T : 0) * 32) * 32;   // + i * Mg_pad * 32 words per stripe
         auto issue_bed = [&](int i) {
             if (active && i < ns) {
                 if (lane == 0) {
@@ -325,24 +381,17 @@ atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
                 n_fill++;
             }
         };
-        auto issue_tab = [&](int i) {
-            if (i < ns) stage_table<Cfg::THREADS>(tab_sm, i & 1, tsrc + (long)i * 8192);
-            cp_async_commit();
-        };
-
 #pragma unroll
         for (int s = 0; s < NS - 1; s++) issue_bed(s);
-        issue_tab(0);
         long long acc64[4] = {0, 0, 0, 0};
 
         for (int i0 = 0; i0 < ns; i0 += 2) {
 #define ATX_STEP(B)                                                                            \
     if (i0 + B < ns) {                                                                         \
         const int i = i0 + B;                                                                  \
-        cp_async_wait_all();                                                                   \
-        __syncthreads();                                                                       \
-        issue_tab(i + 1);                                                                      \
         issue_bed(i + NS - 1);                                                                 \
+        mbar_wait(tp.full + 8 * B, tp.fills<B>() & 1);                                         \
+        tp.fills<B>()++;                                                                       \
         if (active) {                                                                          \
             const uint32_t s = n_use % NS;                                                     \
             mbar_wait(bar0 + 8 * s, (n_use / NS) & 1);                                         \
@@ -359,12 +408,13 @@ atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
                 }                                                                              \
             }                                                                                  \
         }                                                                                      \
+        __syncwarp();                                                                          \
+        if (lane == 0) mbar_arrive(tp.empty + 8 * B);                                          \
     }
             ATX_STEP(0)
             ATX_STEP(1)
 #undef ATX_STEP
         }
-        cp_async_wait_all();
         if (active) {
 #pragma unroll
             for (int q = 0; q < 4; q++)
@@ -375,7 +425,7 @@ atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
 }
 
 struct TileTune {
-    int variant;   // 0: 16 warps x 2 stages, 1: 12 warps x 3 stages
+    int variant;   // 0: 15 consumer warps x 2 stages, 1: 12 consumer warps x 3 stages (+ the producer warp)
     int use_mad;   // X.v: accumulators (0..4) fed by IMAD instead of IADD3; X^T.u: 4 -> all four, else none
     int ax_tiles_per_chunk, atx_stripes_per_chunk;
     int twin_mad;  // X.v on the twin: one accumulator fed by IMAD (1) or none (0)
@@ -671,22 +721,22 @@ int ax_main(gvb_ctx* c, unsigned long long* accN) {
     if (want_twin && c->twin_state == 0) GVB_CHECK(gvb_twin_build(c));
     if (want_twin && c->twin_state == 1) {
         if (t.variant == 1) return launch_ax<12, 3, 0, true>(c, accN);
-        return t.twin_mad > 0 ? launch_ax<16, 2, 1, true>(c, accN) : launch_ax<16, 2, 0, true>(c, accN);
+        return t.twin_mad > 0 ? launch_ax<15, 2, 1, true>(c, accN) : launch_ax<15, 2, 0, true>(c, accN);
     }
     if (t.variant == 1) return t.use_mad ? launch_ax<12, 3, 4, false>(c, accN) : launch_ax<12, 3, 0, false>(c, accN);
     switch (t.use_mad) {
-        case 0: return launch_ax<16, 2, 0, false>(c, accN);
-        case 1: return launch_ax<16, 2, 1, false>(c, accN);
-        case 2: return launch_ax<16, 2, 2, false>(c, accN);
-        case 3: return launch_ax<16, 2, 3, false>(c, accN);
-        default: return launch_ax<16, 2, 4, false>(c, accN);
+        case 0: return launch_ax<15, 2, 0, false>(c, accN);
+        case 1: return launch_ax<15, 2, 1, false>(c, accN);
+        case 2: return launch_ax<15, 2, 2, false>(c, accN);
+        case 3: return launch_ax<15, 2, 3, false>(c, accN);
+        default: return launch_ax<15, 2, 4, false>(c, accN);
     }
 }
 
 int atx_main(gvb_ctx* c, const int* tab, unsigned long long* acc) {
     const TileTune t = tune();
     if (t.variant == 1) return t.use_mad >= 4 ? launch_atx<12, 3, true, 0>(c, tab, acc) : launch_atx<12, 3, false, 0>(c, tab, acc);
-    return t.use_mad >= 4 ? launch_atx<16, 2, true, 0>(c, tab, acc) : launch_atx<16, 2, false, 0>(c, tab, acc);
+    return t.use_mad >= 4 ? launch_atx<15, 2, true, 0>(c, tab, acc) : launch_atx<15, 2, false, 0>(c, tab, acc);
 }
 
 }   // namespace
@@ -742,5 +792,5 @@ int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB) {
 int gvb_count_tile_main(gvb_ctx* c, const int* tab, unsigned long long* acc) {
     const TileTune t = tune();
     if (t.variant == 1) return launch_atx<12, 3, false, 1>(c, tab, acc);
-    return launch_atx<16, 2, false, 1>(c, tab, acc);
+    return launch_atx<15, 2, false, 1>(c, tab, acc);
 }

@@ -122,6 +122,7 @@ void vamp::dev_close() {
     for (gvb_vec v : all)
         if (v) gvb_vec_free(dev.ctx, v);
     dev = Dev();
+    for (bool& open : snap_open) open = false;   // snapshots belong to the context that is being left
 }
 
 void vamp::sync_host(gvb_vec v, std::vector<double>& h, size_t n) {

@@ -411,7 +411,7 @@ def ours_arm(args):
                    "l2_policy": "inputs (>= 12 GB packed bed per sweep at the default workload) larger than the 126 MB L2",
                    "kernels": os.environ.get("GVB_KERNELS", "tile (gen 2)"), "twin_layout": ctx.twin_state() == 1, "final_gamw": gamw, "setup_s": t_setup},
         "roofline": roofline,
-        "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": 8 * (N + M), "d2h_bytes_per_step": 8 * (4 * M + 4 * mbytes),
+        "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * (4 * M + 4 * mbytes),
                 "ms_per_step": ms_e2e / K, "sweeps_per_step": e2e_sweeps,
                 "note": "the K iterations AFTER the device-timed ones: y re-uploaded from pinned host memory every step (A^T y recomputed), "
                         "x1_hat / r1 / r2 / x2_hat / z1 read back every step; VAMP has converged further, so the CG solves may need fewer sweeps"},

@@ -22,7 +22,7 @@ LIB = os.path.join(LIBDIR, "libgvamp_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CU_SOURCES = ["capi.cu", "layout.cu", "stats.cu", "matvec_simple.cu", "matvec_lut.cu", "matvec_tile.cu", "misslist.cu", "twin.cu", "assoc.cu", "people.cu", "vecops.cu"]
+CU_SOURCES = ["capi.cu", "cg.cu", "layout.cu", "stats.cu", "matvec_simple.cu", "matvec_lut.cu", "matvec_tile.cu", "misslist.cu", "twin.cu", "assoc.cu", "people.cu", "vecops.cu"]
 NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", HOSTCXX, "--expt-relaxed-constexpr",
               "-Xcompiler", "-Wno-unused-result"] + ARCH
 

@@ -38,6 +38,9 @@ SIGNATURES = {
     "gvb_timer_elapsed_ms": (ci, [vp, ci, ctypes.POINTER(ctypes.c_float)]),
     "gvb_launch_count": (cl, [vp]),
     "gvb_sweep_count": (cl, [vp]),
+    "gvb_host_sync_count": (cl, [vp]),
+    "gvb_layout_generation": (cl, [vp]),
+    "gvb_vec_reduce_batch": (ci, [vp, ci, vp, c_f64p]),
     "gvb_profile_enable": (ci, [vp, ci]),
     "gvb_profile_read": (ci, [vp, c_f64p]),
     "gvb_divide_work": (None, [cl, ci, ci, ctypes.POINTER(cl), ctypes.POINTER(cl)]),
@@ -86,6 +89,15 @@ SIGNATURES = {
     "gvb_probit_cov_pass": (ci, [vp, vp, vp, vp, ci, c_f64p, cd, ci, c_f64p]),
     "gvb_probit_cov_apply": (ci, [vp, vp, ci, c_f64p, vp]),
 }
+
+
+
+class RedOp(ctypes.Structure):
+    """gvb_red_op of the header"""
+    _fields_ = [("x", vp), ("y", vp), ("a", cd), ("b", cd), ("kind", ci), ("sync", ci)]
+
+
+RED_DOT, RED_SQ = 0, 1
 
 _LIB = None
 
@@ -292,6 +304,14 @@ class Context:
         _chk(self.L.gvb_vec_dots(self.h, n, X, Y, int(sync), res.ctypes.data_as(c_f64p)))
         return res
 
+    def reduce_batch(self, ops):
+        """ops: list of (kind, x, y, a, b, sync); see gvb_vec_reduce_batch"""
+        n = len(ops)
+        arr = (RedOp * n)(*[RedOp(x.h, y.h if y is not None else None, a, b, kind, int(sync)) for kind, x, y, a, b, sync in ops])
+        res = np.empty(n)
+        _chk(self.L.gvb_vec_reduce_batch(self.h, n, ctypes.cast(arr, vp), res.ctypes.data_as(c_f64p)))
+        return res
+
     def dist2(self, x, y, sync=True):
         res = np.empty(1)
         _chk(self.L.gvb_vec_dist2(self.h, x.h, y.h, int(sync), res.ctypes.data_as(c_f64p)))
@@ -389,6 +409,12 @@ class Context:
 
     def sweeps(self) -> int:
         return self.L.gvb_sweep_count(self.h)
+
+    def host_syncs(self) -> int:
+        return self.L.gvb_host_sync_count(self.h)
+
+    def layout_generation(self) -> int:
+        return self.L.gvb_layout_generation(self.h)
 
     def probit_cov_pass(self, y, gg, Z, C, eta, probit_var=1.0, what=7):
         e, pe = _f64(eta)

@@ -128,6 +128,9 @@ extern "C" void gvb_ctx_destroy(gvb_ctx* c) {
     gvb_twin_reset(c);
     fr(c->tab_u); fr(c->tab_v); fr(c->acc_i64); fr(c->red_partial); fr(c->red_result); fr(c->scal); fr(c->work_counter);
     if (c->h_red) cudaFreeHost(c->h_red);
+    fr(c->cg_dev); fr(c->cg_flags);
+    if (c->cg_host) cudaFreeHost(c->cg_host);
+    for (auto& e : c->cg_ev) if (e) cudaEventDestroy(e);
     for (auto& sn : c->snap) {
         if (sn.dev) cudaFree(sn.dev);
         if (sn.host) cudaFreeHost(sn.host);
@@ -174,6 +177,8 @@ extern "C" int gvb_timer_elapsed_ms(gvb_ctx* c, int slot, float* ms) {
 }
 extern "C" long gvb_launch_count(gvb_ctx* c) { return c ? c->launches : 0; }
 extern "C" long gvb_sweep_count(gvb_ctx* c) { return c ? c->sweeps : 0; }
+extern "C" long gvb_host_sync_count(gvb_ctx* c) { return c ? c->host_syncs : 0; }
+extern "C" long gvb_layout_generation(gvb_ctx* c) { return c ? c->layout_gen : 0; }
 
 // ------------------------------------------------------------------------------------------------
 // device vectors
@@ -455,280 +460,4 @@ extern "C" int gvb_allreduce_host(gvb_ctx* c, double* buf, int n) {
     GVB_CUDA(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < n; i++) buf[i] = c->h_red[i];
     return GVB_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// LMMSE operator and preconditioned CG (vamp.cpp:1074-1229)
-// ------------------------------------------------------------------------------------------------
-__global__ void lmmse_combine_kernel(double* __restrict__ out, double tau, double gam2, const double* __restrict__ v, long n) {
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        double r = out[i] * tau;     // vamp.cpp:1113-1114: res *= tau; res += gam2*v
-        out[i] = r + gam2 * v[i];
-    }
-}
-
-static int lmmse_mult_dev(gvb_ctx* c, const gvb_vec_s* v, double tau, double gam2, gvb_vec_s* out, bool known_nonzero) {
-    if (!known_nonzero) {
-        // vamp.cpp:1079-1080: an all-zero input returns zeros without touching the matrix
-        gvb_vec xs[1] = {const_cast<gvb_vec_s*>(v)};
-        double nn = 0.0;
-        GVB_CHECK(gvb_vec_dots(c, 1, xs, nullptr, 1, &nn));
-        if (nn == 0.0) return gvb_vec_fill(c, out, 0.0);
-    }
-    GVB_CHECK(gvb_ax_dev(c, v->d, c->tmpN2, true));
-    GVB_CHECK(gvb_atx_dev(c, c->tmpN2, out->d));
-    lmmse_combine_kernel<<<(unsigned)std::min((v->n + 255) / 256, 1184l), 256, 0, c->stream>>>(out->d, tau, gam2, v->d, v->n);
-    GVB_LAUNCHED(c);
-    return GVB_OK;
-}
-
-extern "C" int gvb_lmmse_mult(gvb_ctx* c, gvb_vec v, double tau, double gam2, gvb_vec out) {
-    GVB_ARG(c && v && out && v != out && v->cap >= c->Mg_pad * 4 && out->cap >= c->Mg_pad * 4, "M-vectors from gvb_vec_alloc_M");
-    return lmmse_mult_dev(c, v, tau, gam2, out, false);
-}
-
-// fused CG updates ---------------------------------------------------------------------------------
-// p = r/diag + beta*p
-__global__ void cg_update_p_kernel(double* __restrict__ p, const double* __restrict__ r, double beta, double diag, long n) {
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = r[i] / diag + beta * p[i];
-}
-// r = rhs - q ; p = r/diag ; partial: <r, r/diag>, ||rhs||^2
-__global__ void __launch_bounds__(256) cg_init_kernel(double* __restrict__ r, double* __restrict__ p, const double* __restrict__ rhs,
-                                                      const double* __restrict__ q, double diag, long n, double* __restrict__ partial) {
-    double a0 = 0.0, a1 = 0.0;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        double b = rhs[i];
-        double x = b - q[i];
-        r[i] = x;
-        double z = x / diag;
-        p[i] = z;
-        a0 += x * z;
-        a1 += b * b;
-    }
-    __shared__ double sm[8][2];
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    }
-    if (lane == 0) { sm[warp][0] = a0; sm[warp][1] = a1; }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-        double s = 0.0;
-        for (int w = 0; w < 8; w++) s += sm[w][threadIdx.x];
-        partial[blockIdx.x * 2 + threadIdx.x] = s;
-    }
-}
-
-// ax += alpha * ap over the padded N-vector: the running A.mu of the CG by-product (see cg_solve_impl)
-__global__ void cg_axpy_n_kernel(double* __restrict__ ax, const double* __restrict__ ap, double alpha, long n) {
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) ax[i] += alpha * ap[i];
-}
-// ata = (d - gam2*mu)/tau: A^T A mu out of d = (tau A^T A + gam2) mu;  d = tau*ata + gam2*mu: the way back
-// (the running update ata += alpha (d - gam2 p)/tau lives in cg_update_mu_r_kernel)
-__global__ void cg_ata_from_d_kernel(double* __restrict__ ata, const double* __restrict__ d, const double* __restrict__ mu, double gam2, double tau, long n) {
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) ata[i] = (d[i] - gam2 * mu[i]) / tau;
-}
-__global__ void cg_d_from_ata_kernel(double* __restrict__ d, const double* __restrict__ ata, const double* __restrict__ mu, double gam2, double tau, long n) {
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) d[i] = tau * ata[i] + gam2 * mu[i];
-}
-// d = tau*d + gam2*p (the tail of lmmse_mult, vamp.cpp:1113-1114) fused with <d,p>
-__global__ void __launch_bounds__(256) cg_combine_dot_kernel(double* __restrict__ d, double tau, double gam2, const double* __restrict__ p, long n,
-                                                             double* __restrict__ partial) {
-    double a0 = 0.0;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        double x = d[i] * tau;
-        x = x + gam2 * p[i];
-        d[i] = x;
-        a0 += x * p[i];
-    }
-    __shared__ double sm[8];
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-    if (lane == 0) sm[warp] = a0;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int w = 0; w < 8; w++) s += sm[w];
-        partial[blockIdx.x] = s;
-    }
-}
-// mu += alpha p ; r -= alpha d ; [ata += alpha (d - gam2 p)/tau] ; partial: <rhs,mu>, ||mu||^2, <r, r/diag>, ||r||^2.
-// One kernel and ONE host-visible reduction for the two updates of a CG iteration (vamp.cpp:1160-1207); the Onsager exit test,
-// which the reference places between them, only reads <rhs,mu>, so testing it after both leaves mu and the decision unchanged.
-__global__ void __launch_bounds__(256) cg_update_mu_r_kernel(double* __restrict__ mu, double* __restrict__ r, const double* __restrict__ p,
-                                                             const double* __restrict__ d, const double* __restrict__ rhs, double* __restrict__ ata,
-                                                             double alpha, double diag, double gam2, double tau, long n, double* __restrict__ partial) {
-    double a[4] = {0.0, 0.0, 0.0, 0.0};
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        const double pi = p[i], di = d[i];
-        const double m = mu[i] + alpha * pi;
-        const double x = r[i] - di * alpha;
-        mu[i] = m;
-        r[i] = x;
-        if (ata) ata[i] += alpha * ((di - gam2 * pi) / tau);
-        a[0] += rhs[i] * m;
-        a[1] += m * m;
-        a[2] += x * (x / diag);
-        a[3] += x * x;
-    }
-    __shared__ double sm[8][4];
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
-        if (lane == 0) sm[warp][k] = a[k];
-    }
-    __syncthreads();
-    if (threadIdx.x < 4) {
-        double s = 0.0;
-        for (int w = 0; w < 8; w++) s += sm[w][threadIdx.x];
-        partial[blockIdx.x * 4 + threadIdx.x] = s;
-    }
-}
-
-static inline int cg_blocks(long n) { return (int)std::max(1l, std::min((n + 1023) / 1024, (long)GVB_RED_BLOCKS)); }
-
-// vamp::precondCG_solver, vamp.cpp:1130-1229.  z = r/diag is never materialised (diag is a constant,
-// :1137-1138); every scalar and every exit test is FP64 with the reference's formulas.
-//
-// By-products (both optional, no extra bed sweep): every iteration already forms A p (the N-vector inside lmmse_mult), so
-// ax_mu = A mu_start + sum_k alpha_k A p_k is A times the returned solution; and dots3 = {<rhs,rhs>, <rhs,mu>, <rhs,r>} with the
-// residual r = rhs - Q mu of the returned mu gives <rhs, A^T A mu> = (dots3[0] - gam2 dots3[1] - dots3[2]) / tau.
-// ata_mu (optional, needs ax_mu) = A^T A mu, accumulated the same way from d_k = Q p_k.  With have_start != 0 the caller passes
-// ax_mu / ata_mu of the START vector (the by-products of the previous solve that produced it, with whatever tau / gam2): the
-// initial residual rhs - (tau ata_mu + gam2 mu) then needs no sweep at all (the warm-started LMMSE solve of vamp.cpp:591-600).
-static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
-                         gvb_vec ax_mu, double* dots3, gvb_vec ata_mu = nullptr, int have_start = 0) {
-    GVB_ARG(c && rhs && mu && rhs != mu, "vectors");
-    GVB_ARG(rhs->cap >= c->Mg_pad * 4 && mu->cap >= c->Mg_pad * 4, "M-vectors from gvb_vec_alloc_M");
-    GVB_ARG(!ax_mu || ax_mu->cap >= c->Npad, "ax_mu must be an N-vector from gvb_vec_alloc_N");
-    GVB_ARG(!ata_mu || (ax_mu && ata_mu->cap >= c->Mg_pad * 4 && ata_mu != mu && ata_mu != rhs), "ata_mu needs ax_mu and must be its own M-vector");
-    GVB_ARG(!have_start || ata_mu, "have_start needs ax_mu and ata_mu of the start vector");
-    long n = c->M;
-    for (int k = 0; k < 3; k++) {
-        if (c->cg_ws[k] && c->cg_ws[k]->cap != c->Mg_pad * 4) {   // matrix was reloaded with another shape
-            gvb_vec_free(c, c->cg_ws[k]);
-            c->cg_ws[k] = nullptr;
-        }
-        if (!c->cg_ws[k]) GVB_CHECK(gvb_vec_alloc_M(c, &c->cg_ws[k]));
-    }
-    gvb_vec r = c->cg_ws[0], p = c->cg_ws[1], d = c->cg_ws[2];
-    int rc = GVB_OK;
-    int it_done = 0;
-    auto cleanup = [&]() {};
-#define CGCHK(x) do { rc = (x); if (rc != GVB_OK) { cleanup(); return rc; } } while (0)
-    const double diag = tau * (double)(c->N - 1) / (double)c->N + gam2;
-    const int nb = cg_blocks(n);
-    double s2[2];
-    // r = rhs - lmmse_mult(mu_start) ; z = r/diag ; p = z
-    const long sweeps_before = c->sweeps;
-    const unsigned nbm = (unsigned)std::min((n + 255) / 256, 1184l);
-    if (have_start) {
-        cg_d_from_ata_kernel<<<nbm, 256, 0, c->stream>>>(d->d, ata_mu->d, mu->d, gam2, tau, n);
-        c->launches++;
-    } else {
-        CGCHK(lmmse_mult_dev(c, mu, tau, gam2, d, false));
-        if (ax_mu) {   // A mu_start is in the operator's scratch unless the zero-vector shortcut skipped the sweeps
-            if (c->sweeps != sweeps_before)
-                GVB_CUDA(cudaMemcpyAsync(ax_mu->d, c->tmpN2, c->Npad * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-            else
-                GVB_CUDA(cudaMemsetAsync(ax_mu->d, 0, c->Npad * sizeof(double), c->stream));
-        }
-        if (ata_mu) {
-            cg_ata_from_d_kernel<<<nbm, 256, 0, c->stream>>>(ata_mu->d, d->d, mu->d, gam2, tau, n);
-            c->launches++;
-        }
-    }
-    const int nbn = (int)std::min((c->Npad + 255) / 256, 1184l);
-    double rhs_mu = 0.0;
-    cg_init_kernel<<<nb, 256, 0, c->stream>>>(r->d, p->d, rhs->d, d->d, diag, n, c->red_partial);
-    c->launches++;
-    CGCHK(gvb_reduce_finish(c, nb, 2, true, s2));
-    double rz = s2[0];
-    const double norm_v = sqrt(s2[1]);
-    double rr = 0.0;
-    double prev_onsager = 0.0;
-    for (int i = 0; i < max_iter; i++) {
-        it_done = i + 1;
-        // d = Q p  (p == 0 only when r == 0: the reference then returns zeros and alpha = 0/0)
-        double dp = 0.0;
-        if (rz != 0.0) {
-            CGCHK(gvb_ax_dev(c, p->d, c->tmpN2, true));
-            CGCHK(gvb_atx_dev(c, c->tmpN2, d->d));
-            cg_combine_dot_kernel<<<nb, 256, 0, c->stream>>>(d->d, tau, gam2, p->d, n, c->red_partial);
-            c->launches++;
-            CGCHK(gvb_reduce_finish(c, nb, 1, true, &dp));
-        } else {
-            CGCHK(lmmse_mult_dev(c, p, tau, gam2, d, false));
-            gvb_vec xs[1] = {d};
-            gvb_vec ys[1] = {p};
-            CGCHK(gvb_vec_dots(c, 1, xs, ys, 1, &dp));
-        }
-        double alpha = rz / dp;
-        if (ax_mu && rz != 0.0) {   // c->tmpN2 still holds A p of this iteration
-            cg_axpy_n_kernel<<<nbn, 256, 0, c->stream>>>(ax_mu->d, c->tmpN2, alpha, c->Npad);
-            c->launches++;
-        }
-        double s4[4];
-        cg_update_mu_r_kernel<<<nb, 256, 0, c->stream>>>(mu->d, r->d, p->d, d->d, rhs->d, (ata_mu && rz != 0.0) ? ata_mu->d : nullptr, alpha, diag, gam2, tau, n,
-                                                         c->red_partial);
-        c->launches++;
-        CGCHK(gvb_reduce_finish(c, nb, 4, true, s4));
-        double norm_mu = sqrt(s4[1]);
-        rhs_mu = s4[0];
-        double ons_rel = -1.0;
-        if (denoiser == 0) {   // vamp.cpp:1174-1193
-            double onsager = gam2 * s4[0];
-            ons_rel = (onsager != 0.0) ? fabs((onsager - prev_onsager) / onsager) : 1.0;
-            if (ons_rel < 1e-8) {
-                if (log4) { log4[4 * i + 0] = -1.0; log4[4 * i + 1] = norm_mu; log4[4 * i + 2] = -1.0; log4[4 * i + 3] = ons_rel; }
-                break;
-            }
-            prev_onsager = onsager;
-        }
-        double beta = 1.0 / rz;   // vamp.cpp:1198
-        rz = s4[2];
-        rr = s4[3];
-        beta *= rz;               // vamp.cpp:1207
-        cg_update_p_kernel<<<(unsigned)std::min((n + 255) / 256, 1184l), 256, 0, c->stream>>>(p->d, r->d, beta, diag, n);
-        c->launches++;
-        double rel_err = sqrt(rr) / norm_v;            // vamp.cpp:1215
-        double norm_z = sqrt(rr) / diag;               // ||z|| with z = r/diag
-        if (log4) { log4[4 * i + 0] = rel_err; log4[4 * i + 1] = norm_mu; log4[4 * i + 2] = norm_z / norm_v; log4[4 * i + 3] = ons_rel; }
-        if (rel_err < 1e-5) break;                     // vamp.cpp:1217-1223
-    }
-    if (dots3) {   // r is the residual of the returned mu in every exit path (the two updates are one kernel)
-        gvb_vec xs[1] = {rhs};
-        gvb_vec ys[1] = {r};
-        double rr_dot = 0.0;
-        CGCHK(gvb_vec_dots(c, 1, xs, ys, 1, &rr_dot));
-        dots3[0] = norm_v * norm_v;
-        dots3[1] = rhs_mu;
-        dots3[2] = rr_dot;
-    }
-#undef CGCHK
-    cudaError_t e = cudaGetLastError();
-    cleanup();
-    if (e != cudaSuccess) {
-        gvb_set_error("CUDA error in CG: %s", cudaGetErrorString(e));
-        return GVB_ERR_CUDA;
-    }
-    if (iters) *iters = it_done;
-    return GVB_OK;
-}
-
-extern "C" int gvb_cg_solve(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4) {
-    return cg_solve_impl(c, rhs, mu, tau, gam2, max_iter, denoiser, iters, log4, nullptr, nullptr);
-}
-extern "C" int gvb_cg_solve_ex(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
-                               gvb_vec ax_mu, double* dots3) {
-    return cg_solve_impl(c, rhs, mu, tau, gam2, max_iter, denoiser, iters, log4, ax_mu, dots3);
-}
-extern "C" int gvb_cg_solve_warm(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
-                                 gvb_vec ax_mu, gvb_vec ata_mu, int have_start, double* dots3) {
-    return cg_solve_impl(c, rhs, mu, tau, gam2, max_iter, denoiser, iters, log4, ax_mu, dots3, ata_mu, have_start);
 }

@@ -99,6 +99,9 @@ struct gvb_ctx {
     unsigned long long* acc_i64 = nullptr;  // fixed-point accumulators
     size_t acc_i64_cap = 0;
     int* work_counter = nullptr;
+    // device-side predicate of the sweep kernels (matvec_tile.cu, misslist.cu): when non-null and *skip != 0 every kernel of a
+    // sweep returns at once.  Set by the CG driver (cg.cu) around iterations it enqueues before it knows the solver has stopped.
+    const int* skip = nullptr;
     double* scal = nullptr;         // small device scalars
     int kernel_gen = 2;             // 0: simple FP64 kernels, 1: gen-1 table kernels, 2: gen-2 tile kernels (env GVB_KERNELS)
 
@@ -116,13 +119,22 @@ struct gvb_ctx {
     // timers and counters
     cudaEvent_t ev_start[8], ev_stop[8];
     long launches = 0, sweeps = 0;
+    long host_syncs = 0;            // stream synchronisations that return a reduction to the host (bench.py reports them per iteration)
     bool profile = false;
     std::vector<cudaEvent_t> prof_ev[2];   // [0] X.v, [1] X^T.u : start/stop pairs
     size_t prof_used[2] = {0, 0};
     std::vector<gvb_vec_s*> vecs;
     gvb_vec_s* cg_ws[3] = {nullptr, nullptr, nullptr};   // r, p, d of the CG solver (allocated once: no cudaMalloc in the loop)
+    // device-resident scalars of the CG solver (cg.cu): the iteration never returns to the host for alpha / beta / the exit tests
+    double* cg_dev = nullptr;       // [GVB_CG_NSCAL scalars][4 log doubles per iteration]
+    double* cg_host = nullptr;      // pinned: 4 ring slots of GVB_CG_NSCAL scalars, then the final copy of cg_dev
+    int cg_log_cap = 0;             // iterations the log has room for
+    int* cg_flags = nullptr;        // device: [0] != 0 once the solver has stopped (the predicate of every later kernel)
+    cudaEvent_t cg_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    long layout_gen = 0;            // bumped whenever the matrix or the mask is (re)loaded: callers drop cached by-products
 };
 
+#define GVB_CG_NSCAL 16
 #define GVB_RED_BLOCKS 296
 #define GVB_RED_MAXK 80
 
@@ -193,3 +205,5 @@ int gvb_atx_dev(gvb_ctx* c, const double* u, double* out);
 // reductions: res (host) <- sum over blocks (and ranks if sync) of the K per-block partials written
 // by the caller's kernel into c->red_partial[b*K + k], b < nblocks
 int gvb_reduce_finish(gvb_ctx* c, int nblocks, int K, bool sync, double* res_host);
+int gvb_reduce_device(gvb_ctx* c, int nblocks, int K, bool sync);                          // the same, result left in c->red_result
+int gvb_vec_dots_device(gvb_ctx* c, int n, const gvb_vec* x, const gvb_vec* y, bool sync); // gvb_vec_dots without the host round trip

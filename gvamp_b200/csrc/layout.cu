@@ -295,5 +295,6 @@ extern "C" int gvb_set_mask(gvb_ctx* c, const uint8_t* mask4, int nonas) {
     c->mask_present = present;
     c->have_mask = true;
     c->have_stats = false;
+    c->layout_gen++;   // by-products of earlier solves (A mu, A^T A mu, A^T y) describe another operator now
     return GVB_OK;
 }

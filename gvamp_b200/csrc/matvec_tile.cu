@@ -213,7 +213,8 @@ __device__ __forceinline__ void ax_consume(const char* __restrict__ tabc, uint32
 template <int NW, int NS, int MADK, bool TW>
 __global__ void __launch_bounds__(NW * 32 + 32, 1)
 ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, long Mg_pad, long n_stripes, int n_sblocks, int n_gchunks,
-               int tiles_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out, int one) {
+               int tiles_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out, int one, const int* __restrict__ skip) {
+    if (skip && *skip) return;   // device-side predicate of a speculatively enqueued CG iteration (cg.cu): uniform over the grid
     extern __shared__ __align__(1024) char smem[];
     __shared__ int s_item;
     __shared__ __align__(8) unsigned long long s_bar[NW * NS];
@@ -327,7 +328,8 @@ __device__ __forceinline__ void atx_consume(const char* __restrict__ tabc, uint3
 template <int NW, int NS, bool USE_MAD, int MODE>
 __global__ void __launch_bounds__(NW * 32 + 32, 1)
 atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, long Mg_pad, long n_stripes, int n_gblocks, int n_schunks,
-                int stripes_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out, int one) {
+                int stripes_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out, int one, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     extern __shared__ __align__(1024) char smem[];
     __shared__ int s_item;
     __shared__ __align__(8) unsigned long long s_bar[NW * NS];
@@ -464,7 +466,7 @@ int launch_ax(gvb_ctx* c, unsigned long long* accN) {
     const int tpc = pick_chunk(tune().ax_tiles_per_chunk, n_sblocks, n_tiles, c->sm_count);
     int n_gchunks = (int)((n_tiles + tpc - 1) / tpc);
     int grid = std::min(n_sblocks * n_gchunks, c->sm_count);
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(TW ? c->bed_twin : c->bed, c->tab_v, c->Mg_pad, c->n_stripes, n_sblocks, n_gchunks, tpc, c->work_counter, accN, 1);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(TW ? c->bed_twin : c->bed, c->tab_v, c->Mg_pad, c->n_stripes, n_sblocks, n_gchunks, tpc, c->work_counter, accN, 1, c->skip);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }
@@ -483,7 +485,7 @@ int launch_atx(gvb_ctx* c, const int* tab, unsigned long long* acc) {
     const int spc = pick_chunk(tune().atx_stripes_per_chunk, n_gblocks, c->n_stripes, c->sm_count);
     int n_schunks = (int)((c->n_stripes + spc - 1) / spc);
     int grid = std::min(n_gblocks * n_schunks, c->sm_count);
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(c->bed, tab, c->Mg_pad, c->n_stripes, n_gblocks, n_schunks, spc, c->work_counter, acc, 1);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(c->bed, tab, c->Mg_pad, c->n_stripes, n_gblocks, n_schunks, spc, c->work_counter, acc, 1, c->skip);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }
@@ -542,7 +544,8 @@ __device__ __forceinline__ void ax_code_values(int mode, double vj, double mu, d
 }
 
 __global__ void __launch_bounds__(128) ax_prep_kernel(const double* __restrict__ v, const double* __restrict__ mave, const double* __restrict__ msig,
-                                                      double* __restrict__ scal, unsigned long long* __restrict__ accN, long Npad, int mode) {
+                                                      double* __restrict__ scal, unsigned long long* __restrict__ accN, long Npad, int mode, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     const long j = blockIdx.x * 128l + threadIdx.x;
     double v00, v10, v11;
     ax_code_values(mode, v ? v[j] : 1.0, mave[j], msig[j], v00, v10, v11);
@@ -560,7 +563,8 @@ __global__ void __launch_bounds__(128) ax_prep_kernel(const double* __restrict__
 // pass 2 (one block per marker tile): tabv[(T*256 + e)*32 + s] = sum_q Q_{4g+q}(c_q(e)), g = 32 T + s,
 // Q_j(c) = rint(val_j(c) * scale), val_j(00) = (2-mu) w, val_j(10) = (1-mu) w, val_j(11) = -mu w, val_j(missing) = 0
 __global__ void __launch_bounds__(256) ax_build_kernel(const double* __restrict__ v, const double* __restrict__ mave, const double* __restrict__ msig,
-                                                       double* __restrict__ scal, int* __restrict__ tabv, int mode) {
+                                                       double* __restrict__ scal, int* __restrict__ tabv, int mode, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     __shared__ int Qs[4][4][32];   // [q][code][slot]: a warp reads one (q, code) row -> conflict free
     __shared__ double s_scale;
     const long T = blockIdx.x;
@@ -595,7 +599,8 @@ __global__ void __launch_bounds__(256) ax_build_kernel(const double* __restrict_
 
 // out[i] = present_i ? acc_i / scale / sqrt(N) : 0   (the mask m_i of data.cpp:972; pads are never present)
 __global__ void ax_finish_kernel(const unsigned long long* __restrict__ acc, double* __restrict__ scal, const uint32_t* __restrict__ maskw, long Npad,
-                                 double inv_sqrt_n, double* __restrict__ out) {
+                                 double inv_sqrt_n, double* __restrict__ out, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i == 0) scal[SCAL_AX_BOUND] = 0.0;
     if (i >= Npad) return;
@@ -608,7 +613,8 @@ __global__ void ax_finish_kernel(const unsigned long long* __restrict__ acc, dou
 // pass 1: bound = max over byte positions p of 2 (|u_4p| + ... + |u_4p+3|), the largest |table entry| / scale; clears
 // the accumulators of the markers and the running sum of U
 __global__ void __launch_bounds__(256) atx_prep_kernel(const double* __restrict__ u, long npos, double* __restrict__ scal,
-                                                       unsigned long long* __restrict__ acc, long nacc, long long* __restrict__ usum) {
+                                                       unsigned long long* __restrict__ acc, long nacc, long long* __restrict__ usum, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     double m = 0.0;
     const long tid = blockIdx.x * (long)blockDim.x + threadIdx.x, nth = (long)gridDim.x * blockDim.x;
     for (long p = tid; p < npos; p += nth) {
@@ -628,7 +634,8 @@ __global__ void __launch_bounds__(256) atx_prep_kernel(const double* __restrict_
 // pass 2 (one block per stripe): tab[(t*256 + B)*32 + l] = sum_k a(code_k(B)) U_{4p+k}, p = 32 t + l, U = rint(u * scale);
 // tabm (shards with missing genotypes) holds the same sum over the MISSING codes with weight 1; accumulates sum_i U_i
 __global__ void __launch_bounds__(256) atx_build_kernel(const double* __restrict__ u, double window, double* __restrict__ scal, int* __restrict__ tab,
-                                                        int* __restrict__ tabm, long long* __restrict__ usum, int* __restrict__ uq) {
+                                                        int* __restrict__ tabm, long long* __restrict__ usum, int* __restrict__ uq, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     __shared__ int Us[4][32];   // [k][position]
     __shared__ double s_scale;
     const long t = blockIdx.x;
@@ -667,7 +674,8 @@ __global__ void __launch_bounds__(256) atx_build_kernel(const double* __restrict
 // out[j] = sigma_j * (A_j - mu_j * B_j) / scale / sqrt(N),  B_j = sum_i U_i - sum_{i missing in j} U_i
 __global__ void atx_finish_kernel(const unsigned long long* __restrict__ acc, const unsigned long long* __restrict__ accm, const long long* __restrict__ usum,
                                   double* __restrict__ scal, const double* __restrict__ mave, const double* __restrict__ msig, long Mpad, long M,
-                                  double inv_sqrt_n, double* __restrict__ out, double* __restrict__ outB) {
+                                  double inv_sqrt_n, double* __restrict__ out, double* __restrict__ outB, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     long j = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (j == 0) scal[SCAL_ATX_BOUND] = 0.0;
     if (j >= Mpad) return;
@@ -747,13 +755,13 @@ int gvb_ax_tile(gvb_ctx* c, const double* v, double* out, int mode) {
     GVB_CHECK(ensure_scratch(c, false, true, false));
     const long n_tiles = c->Mg_pad / 32;
     unsigned long long* accN = c->acc_i64 + 2 * (size_t)c->Mg_pad * 4;
-    ax_prep_kernel<<<(unsigned)n_tiles, 128, 0, c->stream>>>(v, c->mave, c->msig, c->scal, accN, c->Npad, mode);
+    ax_prep_kernel<<<(unsigned)n_tiles, 128, 0, c->stream>>>(v, c->mave, c->msig, c->scal, accN, c->Npad, mode, c->skip);
     GVB_LAUNCHED(c);
-    ax_build_kernel<<<(unsigned)n_tiles, 256, 0, c->stream>>>(v, c->mave, c->msig, c->scal, c->tab_v, mode);
+    ax_build_kernel<<<(unsigned)n_tiles, 256, 0, c->stream>>>(v, c->mave, c->msig, c->scal, c->tab_v, mode, c->skip);
     GVB_LAUNCHED(c);
     GVB_CHECK(ax_main(c, accN));
     ax_finish_kernel<<<(unsigned)((c->Npad + 255) / 256), 256, 0, c->stream>>>(accN, c->scal, c->maskw, c->Npad,
-                                                                               mode == 0 ? 1.0 / sqrt((double)c->N) : 1.0, out);
+                                                                               mode == 0 ? 1.0 / sqrt((double)c->N) : 1.0, out, c->skip);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }
@@ -772,10 +780,10 @@ int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB) {
     unsigned long long* accm = c->acc_i64 + Mpad;
     long long* usum = reinterpret_cast<long long*>(c->acc_i64 + 2 * Mpad + c->Npad);
     int nb = (int)std::max(1l, std::min((npos + 255) / 256, 2l * c->sm_count));
-    atx_prep_kernel<<<nb, 256, 0, c->stream>>>(u, npos, c->scal, acc, (long)((miss ? 2 : 1) * Mpad), usum);
+    atx_prep_kernel<<<nb, 256, 0, c->stream>>>(u, npos, c->scal, acc, (long)((miss ? 2 : 1) * Mpad), usum, c->skip);
     GVB_LAUNCHED(c);
     atx_build_kernel<<<(unsigned)c->n_stripes, 256, 0, c->stream>>>(u, 32.0, c->scal, c->tab_u, (miss && !list) ? c->tab_u + total : nullptr, usum,
-                                                                    list ? c->uq : nullptr);
+                                                                    list ? c->uq : nullptr, c->skip);
     GVB_LAUNCHED(c);
     GVB_CHECK(atx_main(c, c->tab_u, acc));
     if (list)
@@ -783,7 +791,7 @@ int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB) {
     else if (miss)
         GVB_CHECK(atx_main(c, c->tab_u + total, accm));
     atx_finish_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, c->stream>>>(acc, miss ? accm : nullptr, usum, c->scal, c->mave, c->msig, (long)Mpad, c->M,
-                                                                             1.0 / sqrt((double)c->N), out, outB);
+                                                                             1.0 / sqrt((double)c->N), out, outB, c->skip);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }

@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(256) miss_fill_kernel(const uint32_t* __restri
 // of (block, 32-marker batch) items in block-major order and reloads the 128 KB U block when the block changes.
 __global__ void __launch_bounds__(MISS_THREADS, 1)
 miss_sum_kernel(const uint16_t* __restrict__ idx, const unsigned long long* __restrict__ seg_off, const int* __restrict__ uq, long Npad, long Mpad,
-                long n_items, unsigned long long* __restrict__ accm) {
+                long n_items, unsigned long long* __restrict__ accm, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     extern __shared__ __align__(16) int U[];   // [MISS_BLOCK_IND] + zero word(s)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long n_batches = Mpad / 32;
@@ -225,7 +226,7 @@ int gvb_misslist_sum(gvb_ctx* c, unsigned long long* accm) {
     const long Mpad = c->Mg_pad * 4;
     const long n_items = c->miss_nblk * (Mpad / 32);
     const int grid = (int)std::max(1l, std::min(n_items, (long)c->sm_count));
-    miss_sum_kernel<<<grid, MISS_THREADS, MISS_SMEM, c->stream>>>(c->miss_idx, c->miss_off, c->uq, c->Npad, Mpad, n_items, accm);
+    miss_sum_kernel<<<grid, MISS_THREADS, MISS_SMEM, c->stream>>>(c->miss_idx, c->miss_off, c->uq, c->Npad, Mpad, n_items, accm, c->skip);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }

@@ -41,15 +41,23 @@ __global__ void __launch_bounds__(1024) reduce_final_kernel(const double* __rest
     }
 }
 
-int gvb_reduce_finish(gvb_ctx* c, int nblocks, int K, bool sync, double* res_host) {
+// device part of a reduction: c->red_result[0..K) <- sum over blocks (and over ranks if sync) of the per-block partials; nothing
+// returns to the host (the CG driver of cg.cu consumes the scalars in its own kernels)
+int gvb_reduce_device(gvb_ctx* c, int nblocks, int K, bool sync) {
     reduce_final_kernel<<<1, 32 * std::min(K, 32), 0, c->stream>>>(c->red_partial, nblocks, K, c->red_result);
     GVB_LAUNCHED(c);
     if (sync && c->nranks > 1) {
         // replaces the per-scalar MPI_Allreduce calls (utilities.cpp:203, vamp.cpp:313,990,1012-1013)
         GVB_NCCL(ncclAllReduce(c->red_result, c->red_result, K, ncclDouble, ncclSum, c->comm, c->stream));
     }
+    return GVB_OK;
+}
+
+int gvb_reduce_finish(gvb_ctx* c, int nblocks, int K, bool sync, double* res_host) {
+    GVB_CHECK(gvb_reduce_device(c, nblocks, K, sync));
     GVB_CUDA(cudaMemcpyAsync(c->h_red, c->red_result, K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     GVB_CUDA(cudaStreamSynchronize(c->stream));
+    c->host_syncs++;
     for (int k = 0; k < K; k++) res_host[k] = c->h_red[k];
     return GVB_OK;
 }
@@ -107,8 +115,9 @@ __global__ void __launch_bounds__(256) dots_kernel(DotArgs a, long n, double* __
     block_reduce_store<K>(acc, partial);
 }
 
-extern "C" int gvb_vec_dots(gvb_ctx* c, int n, const gvb_vec* x, const gvb_vec* y, int sync, double* res) {
-    GVB_ARG(c && n >= 1 && n <= 8 && x && res, "1..8 dot products");
+// launches the fused dot products; the partials land in c->red_partial, *blocks_out tells the reduction how many
+static int vec_dots_launch(gvb_ctx* c, int n, const gvb_vec* x, const gvb_vec* y, int* blocks_out) {
+    GVB_ARG(c && n >= 1 && n <= 8 && x, "1..8 dot products");
     DotArgs a;
     long len = x[0]->n;
     for (int k = 0; k < 8; k++) {
@@ -129,7 +138,22 @@ extern "C" int gvb_vec_dots(gvb_ctx* c, int n, const gvb_vec* x, const gvb_vec* 
         default: dots_kernel<8><<<blocks, 256, 0, c->stream>>>(a, len, c->red_partial); break;
     }
     GVB_LAUNCHED(c);
+    *blocks_out = blocks;
+    return GVB_OK;
+}
+
+extern "C" int gvb_vec_dots(gvb_ctx* c, int n, const gvb_vec* x, const gvb_vec* y, int sync, double* res) {
+    GVB_ARG(res, "result pointer");
+    int blocks = 0;
+    GVB_CHECK(vec_dots_launch(c, n, x, y, &blocks));
     return gvb_reduce_finish(c, blocks, n, sync != 0, res);
+}
+
+// the same dot products, results left in c->red_result on the device
+int gvb_vec_dots_device(gvb_ctx* c, int n, const gvb_vec* x, const gvb_vec* y, bool sync) {
+    int blocks = 0;
+    GVB_CHECK(vec_dots_launch(c, n, x, y, &blocks));
+    return gvb_reduce_device(c, blocks, n, sync);
 }
 
 __global__ void __launch_bounds__(256) dist2_kernel(const double* __restrict__ x, const double* __restrict__ y, long n, double* __restrict__ partial) {
@@ -147,6 +171,93 @@ extern "C" int gvb_vec_dist2(gvb_ctx* c, gvb_vec x, gvb_vec y, int sync, double*
     dist2_kernel<<<blocks, 256, 0, c->stream>>>(x->d, y->d, x->n, c->red_partial);
     GVB_LAUNCHED(c);
     return gvb_reduce_finish(c, blocks, 1, sync != 0, res);
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched reductions: up to GVB_RED_BATCH dot products / squared norms of linear combinations over vectors of ANY lengths
+// (M- and N-vectors mixed) in two launches and ONE host synchronisation.  The VAMP loop's print-only diagnostics and its
+// end-of-iteration tests (vamp.cpp:388-392, 741-749, 892-927, 1232-1317: a dozen separate allreduces in the reference)
+// travel as two such batches per iteration.
+// ------------------------------------------------------------------------------------------------
+struct BatchArgs {
+    const double* x[GVB_RED_BATCH];
+    const double* y[GVB_RED_BATCH];
+    double a[GVB_RED_BATCH], b[GVB_RED_BATCH];
+    long n[GVB_RED_BATCH];
+    int kind[GVB_RED_BATCH], nblk[GVB_RED_BATCH], off[GVB_RED_BATCH];
+};
+
+__global__ void __launch_bounds__(256) batch_partial_kernel(BatchArgs A, double* __restrict__ partial) {
+    const int op = blockIdx.y;
+    if ((int)blockIdx.x >= A.nblk[op]) return;
+    const double* __restrict__ x = A.x[op];
+    const double* __restrict__ y = A.y[op];
+    const double a = A.a[op], b = A.b[op];
+    const long n = A.n[op], stride = (long)A.nblk[op] * 256;
+    double acc[1] = {0.0};
+    if (A.kind[op] == GVB_RED_DOT) {
+        for (long i = blockIdx.x * 256l + threadIdx.x; i < n; i += stride) acc[0] += x[i] * y[i];
+    } else {
+        for (long i = blockIdx.x * 256l + threadIdx.x; i < n; i += stride) {
+            const double d = y ? a * x[i] + b * y[i] : a * x[i];
+            acc[0] += d * d;
+        }
+    }
+    __shared__ double sm[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+    if (lane == 0) sm[warp] = acc[0];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += sm[w];
+        partial[A.off[op] + blockIdx.x] = t;
+    }
+}
+
+__global__ void batch_final_kernel(BatchArgs A, int nops, const double* __restrict__ partial, double* __restrict__ result) {
+    const int lane = threadIdx.x & 31, op = threadIdx.x >> 5;
+    if (op >= nops) return;
+    double t = 0.0;
+    for (int b = lane; b < A.nblk[op]; b += 32) t += partial[A.off[op] + b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) result[op] = t;
+}
+
+extern "C" int gvb_vec_reduce_batch(gvb_ctx* c, int nops, const gvb_red_op* ops, double* res) {
+    GVB_ARG(c && ops && res && nops >= 1 && nops <= GVB_RED_BATCH, "1..GVB_RED_BATCH operations");
+    BatchArgs A;
+    int off = 0, maxblk = 1, nsync = 0;
+    for (int k = 0; k < nops; k++) {
+        const gvb_red_op& o = ops[k];
+        GVB_ARG(o.x && (o.kind == GVB_RED_DOT || o.kind == GVB_RED_SQ), "operation");
+        GVB_ARG(!o.y || o.y->n == o.x->n, "vector lengths");
+        GVB_ARG(!(o.sync && k > nsync), "rank-summed operations come first in a batch");
+        if (o.sync) nsync = k + 1;
+        A.x[k] = o.x->d;
+        A.y[k] = o.y ? o.y->d : (o.kind == GVB_RED_DOT ? o.x->d : nullptr);
+        A.a[k] = o.a;
+        A.b[k] = o.b;
+        A.n[k] = o.x->n;
+        A.kind[k] = o.kind;
+        A.nblk[k] = red_blocks(c, o.x->n);
+        A.off[k] = off;
+        off += A.nblk[k];
+        maxblk = std::max(maxblk, A.nblk[k]);
+    }
+    for (int k = nops; k < GVB_RED_BATCH; k++) { A.x[k] = A.y[k] = nullptr; A.a[k] = A.b[k] = 0; A.n[k] = 0; A.kind[k] = 0; A.nblk[k] = 0; A.off[k] = 0; }
+    batch_partial_kernel<<<dim3((unsigned)maxblk, (unsigned)nops), 256, 0, c->stream>>>(A, c->red_partial);
+    GVB_LAUNCHED(c);
+    batch_final_kernel<<<1, 32 * nops, 0, c->stream>>>(A, nops, c->red_partial, c->red_result);
+    GVB_LAUNCHED(c);
+    if (nsync > 0 && c->nranks > 1) GVB_NCCL(ncclAllReduce(c->red_result, c->red_result, nsync, ncclDouble, ncclSum, c->comm, c->stream));
+    GVB_CUDA(cudaMemcpyAsync(c->h_red, c->red_result, nops * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GVB_CUDA(cudaStreamSynchronize(c->stream));
+    c->host_syncs++;
+    for (int k = 0; k < nops; k++) res[k] = c->h_red[k];
+    return GVB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -63,7 +63,7 @@ vamp::vamp(int N, int M, int Mt, double gam1, double gamw, int max_iter, double 
     const char* rs = getenv("GVB_REFERENCE_SWEEPS");
     reference_sweeps = rs && rs[0] == '1';
     const char* ow = getenv("GVB_ONSAGER_WARM");
-    onsager_warm = !(ow && ow[0] == '0') && !reference_sweeps;
+    onsager_warm = (ow && ow[0] == '1') && !reference_sweeps;   // opt-in: the default is the reference's zero start
     const char* ao = getenv("GVB_ASYNC_OUT");
     async_outputs = !(ao && ao[0] == '0');
 }
@@ -94,7 +94,7 @@ vamp::vamp(int M, double gam1, double gamw, std::vector<double> true_signal, int
     const char* rs = getenv("GVB_REFERENCE_SWEEPS");
     reference_sweeps = rs && rs[0] == '1';
     const char* ow = getenv("GVB_ONSAGER_WARM");
-    onsager_warm = !(ow && ow[0] == '0') && !reference_sweeps;
+    onsager_warm = (ow && ow[0] == '1') && !reference_sweeps;   // opt-in: the default is the reference's zero start
     const char* ao = getenv("GVB_ASYNC_OUT");
     async_outputs = !(ao && ao[0] == '0');
 }
@@ -105,9 +105,10 @@ vamp::~vamp() { dev_close(); }
 // device state
 // ---------------------------------------------------------------------------------------------------
 void vamp::dev_open(data* dataset) {
-    if (dev.ctx == dataset->device() && dev.r1) return;
+    if (dev.ctx == dataset->device() && dev.r1 && dev.layout_gen == gvb_layout_generation(dataset->device())) return;
     dev_close();
     dev.ctx = dataset->device();
+    dev.layout_gen = gvb_layout_generation(dev.ctx);
     gvb_vec* mvecs[] = {&dev.r1, &dev.r2, &dev.r2_prev, &dev.x1, &dev.x1_prev, &dev.x2, &dev.mu_last, &dev.rhs, &dev.bern, &dev.invq, &dev.tmpM, &dev.truth, &dev.aty, &dev.ata_x2, &dev.ata_invq};
     for (gvb_vec* v : mvecs) DEV(gvb_vec_alloc_M(dev.ctx, v));
     gvb_vec* nvecs[] = {&dev.y, &dev.z1, &dev.tmpN, &dev.tmpN2, &dev.ax_invq};
@@ -207,17 +208,6 @@ int vamp::dev_cg(gvb_vec rhs, gvb_vec mu, double tau, int denoiser, gvb_vec ax_m
         }
     }
     return iters;
-}
-
-// R2 = 1 - ||y - Ax||^2 / ||y||^2 over the N individuals (err_measures, vamp.cpp:1303-1317)
-double vamp::r2_train(gvb_vec ax) {
-    double num = 0, den = 0;
-    DEV(gvb_vec_dist2(dev.ctx, dev.y, ax, 0, &num));
-    gvb_vec xs[1] = {dev.y};
-    DEV(gvb_vec_dots(dev.ctx, 1, xs, nullptr, 0, &den));
-    double l2_pred_err = sqrt(num / den);
-    if (rank == 0) std::cout << "l2 prediction error = " << l2_pred_err << std::endl;
-    return 1 - l2_pred_err * l2_pred_err;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -385,10 +375,17 @@ bool vamp::linear_iteration(data* dataset, int it) {
         double xi = std::min(2 * std::min(alpha1, alpha2), 1.0);
         rho = std::max(rho, xi);
         {
-            double se = 0;
-            DEV(gvb_vec_axpby(ctx, dev.tmpM, scale, dev.truth, 0.0, nullptr));
-            DEV(gvb_vec_dist2(ctx, dev.r2, dev.tmpM, 1, &se));
-            if (rank == 0) std::cout << "true gam2 = " << Mt / se << std::endl;
+            // one batch for "true gam2" and everything err_measures(1) prints (vamp.cpp:505-510, 1232-1317)
+            const double isn = sqrt(1.0 / (double)N);
+            gvb_red_op ops[7] = {{dev.r2, dev.truth, 1.0, -scale, GVB_RED_SQ, 1},   {dev.x1, dev.truth, 0, 0, GVB_RED_DOT, 1},
+                                 {dev.x1, nullptr, 0, 0, GVB_RED_DOT, 1},          {dev.truth, nullptr, 0, 0, GVB_RED_DOT, 1},
+                                 {dev.x1, dev.truth, isn, -1.0, GVB_RED_SQ, 1},    {dev.y, dev.z1, 1.0, -1.0, GVB_RED_SQ, 0},
+                                 {dev.y, nullptr, 0, 0, GVB_RED_DOT, 0}};
+            double res[7];
+            DEV(gvb_vec_reduce_batch(ctx, 7, ops, res));
+            if (rank == 0) std::cout << "true gam2 = " << Mt / res[0] << std::endl;
+            for (int k = 0; k < 6; k++) diag_sums[k] = res[1 + k];
+            diag_valid = true;
         }
         double start_prior_up = wtime();
         if (auto_var_max_iter == 0 || it <= 1) updatePrior(1);
@@ -429,11 +426,12 @@ bool vamp::linear_iteration(data* dataset, int it) {
         // A^T A x2_hat falls out the same way, and since the next solve starts from this x2_hat, its initial residual needs no
         // sweep either; every 8th solve re-seeds both from real sweeps so that rounding cannot accumulate over a long run.
         if (reference_sweeps) {
-            last_cg_iters[0] = dev_cg(dev.rhs, dev.x2, gamw, 1);
+            last_cg_iters[0] = dev_cg(dev.rhs, dev.x2, gamw, 1, nullptr, nullptr, nullptr, it == 1 ? 2 : 0);
         } else {
-            const int warm = (it > 1 && dev.warm_age >= 0 && dev.warm_age < 8) ? 1 : 0;
+            // 2: zero start (iteration 1), 1: by-products of the previous solve describe the start vector, 0: re-seed by real sweeps
+            const int warm = (it == 1) ? 2 : ((dev.warm_age >= 0 && dev.warm_age < 8) ? 1 : 0);
             last_cg_iters[0] = dev_cg(dev.rhs, dev.x2, gamw, 1, dev.tmpN2, nullptr, dev.ata_x2, warm);
-            dev.warm_age = warm ? dev.warm_age + 1 : 0;
+            dev.warm_age = warm == 1 ? dev.warm_age + 1 : 0;
         }
         DEV(gvb_vec_copy(ctx, dev.mu_last, dev.x2));
         dev.ax_x2_valid = !reference_sweeps;
@@ -468,11 +466,30 @@ bool vamp::linear_iteration(data* dataset, int it) {
         gam1 = clampd(eta2 - gam2, gamma_min, gamma_max);
         DEV(gvb_vec_axpby_div(ctx, dev.r1, eta2, dev.x2, -gam2, dev.r2, gam1));   // r1 = (eta2 x2 - gam2 r2)/gam1
         if (rank == 0) std::cout << "gam1 = " << gam1 << std::endl;
+        double stop_dd = 0, stop_nn = 0;
         {
-            double se = 0;
-            DEV(gvb_vec_axpby(ctx, dev.tmpM, scale, dev.truth, 0.0, nullptr));
-            DEV(gvb_vec_dist2(ctx, dev.r1, dev.tmpM, 1, &se));
-            if (rank == 0) std::cout << "true gam1 = " << Mt / se << std::endl;
+            // one batch for "true gam1", the residual of updateNoisePrec, everything err_measures(2) prints and the stopping rule
+            // (vamp.cpp:709-713, 892-927, 1232-1317, 741-749)
+            if (!dev.ax_x2_valid) {
+                DEV(gvb_dAx(ctx, dev.x2, dev.tmpN2));
+                dev.ax_x2_valid = true;
+            }
+            const double isn = sqrt(1.0 / (double)N);
+            gvb_red_op ops[9] = {{dev.r1, dev.truth, 1.0, -scale, GVB_RED_SQ, 1},  {dev.x2, dev.truth, 0, 0, GVB_RED_DOT, 1},
+                                 {dev.x2, nullptr, 0, 0, GVB_RED_DOT, 1},         {dev.truth, nullptr, 0, 0, GVB_RED_DOT, 1},
+                                 {dev.x2, dev.truth, isn, -1.0, GVB_RED_SQ, 1},   {dev.x1_prev, dev.x1, 1.0, -1.0, GVB_RED_SQ, 1},
+                                 {dev.x1_prev, nullptr, 0, 0, GVB_RED_DOT, 1},    {dev.tmpN2, dev.y, 1.0, -1.0, GVB_RED_SQ, 0},
+                                 {dev.y, nullptr, 0, 0, GVB_RED_DOT, 0}};
+            double res[9];
+            DEV(gvb_vec_reduce_batch(ctx, 9, ops, res));
+            if (rank == 0) std::cout << "true gam1 = " << Mt / res[0] << std::endl;
+            diag_sums[0] = res[1]; diag_sums[1] = res[2]; diag_sums[2] = res[3]; diag_sums[3] = res[4];
+            diag_sums[4] = res[7]; diag_sums[5] = res[8];
+            diag_valid = true;
+            noise_res_norm2 = res[7];
+            noise_res_valid = true;
+            stop_dd = res[5];
+            stop_nn = res[6];
         }
 
         updateNoisePrec(dataset);
@@ -482,13 +499,10 @@ bool vamp::linear_iteration(data* dataset, int it) {
         double end_lmmse_step = wtime();
         if (rank == 0) std::cout << "lmmse step took " << end_lmmse_step - start_lmmse_step << " seconds." << std::endl;
         total_sweeps += gvb_sweep_count(ctx) - sweeps0;
-        if (rank == 0) std::cout << "bed sweeps this iteration = " << gvb_sweep_count(ctx) - sweeps0 << std::endl;
+        if (rank == 0 && extra_diagnostics) std::cout << "bed sweeps this iteration = " << gvb_sweep_count(ctx) - sweeps0 << std::endl;
 
-        // stopping rule (vamp.cpp:741-749)
-        double dd = 0, nn = 0;
-        DEV(gvb_vec_dist2(ctx, dev.x1_prev, dev.x1, 1, &dd));
-        gvb_vec xs[1] = {dev.x1_prev};
-        DEV(gvb_vec_dots(ctx, 1, xs, nullptr, 1, &nn));
+        // stopping rule (vamp.cpp:741-749); the two sums came with the end-of-iteration batch
+        const double dd = stop_dd, nn = stop_nn;
         if (it > 1 && sqrt(dd / nn) < stop_criteria_thr) {
             if (rank == 0) std::cout << "VAMP stopping criteria fulfilled with threshold = " << stop_criteria_thr << "." << std::endl;
             return true;
@@ -570,22 +584,17 @@ double vamp::g2d_onsager(double gam2, double tau, data* dataset) {
     }
     this->gam2 = gam2;
     double d3[3] = {0, 0, 0};
-    if (onsager_warm) {
-        const int warm = (dev.onsager_age >= 0 && dev.onsager_age < 8) ? 1 : 0;
-        if (!warm) DEV(gvb_vec_fill(dev.ctx, dev.invq, 0.0));
+    if (onsager_warm) {   // GVB_ONSAGER_WARM=1: start from the previous iteration's Q^-1 u (same probe); the solve then stops on the residual only
+        const int warm = (dev.onsager_age >= 0 && dev.onsager_age < 8) ? 1 : 2;
         last_cg_iters[1] = dev_cg(dev.bern, dev.invq, tau, 0, dev.ax_invq, d3, dev.ata_invq, warm);
-        dev.onsager_age = warm ? dev.onsager_age + 1 : 0;
-    } else {
-        DEV(gvb_vec_fill(dev.ctx, dev.invq, 0.0));
-        last_cg_iters[1] = dev_cg(dev.bern, dev.invq, tau, 0, nullptr, d3);
+        dev.onsager_age = warm == 1 ? dev.onsager_age + 1 : 0;
+    } else {              // the reference: from zero (vamp.cpp:884, 1120-1127)
+        last_cg_iters[1] = dev_cg(dev.bern, dev.invq, tau, 0, nullptr, d3, nullptr, 2);
     }
     // <u, A^T A Q^-1 u> from the solver's own residual: Q mu = u - r  =>  tau A^T A mu = u - r - gam2 mu
     onsager_u_AtA_invq = (d3[0] - gam2 * d3[1] - d3[2]) / tau;
     onsager_valid = true;
-    gvb_vec xs[1] = {dev.bern}, ys[1] = {dev.invq};
-    double dot = 0;
-    DEV(gvb_vec_dots(dev.ctx, 1, xs, ys, 1, &dot));
-    return gam2 * dot;   // gam2 * Tr[(tau X^T X + gam2 I)^-1] / Mt
+    return gam2 * d3[1];   // gam2 * <u, Q^-1 u> = gam2 * Tr[(tau X^T X + gam2 I)^-1] / Mt; <u, mu> is the solver's own last sum
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -663,7 +672,11 @@ void vamp::updateNoisePrec(data* dataset) {
         dev.ax_x2_valid = true;
     }
     double temp_norm2 = 0;
-    DEV(gvb_vec_dist2(ctx, dev.tmpN2, dev.y, 0, &temp_norm2));
+    if (noise_res_valid)
+        temp_norm2 = noise_res_norm2;   // ||A x2_hat - y||^2 arrived with the iteration's batch of reductions
+    else
+        DEV(gvb_vec_dist2(ctx, dev.tmpN2, dev.y, 0, &temp_norm2));
+    noise_res_valid = false;
     double dot = 0;
     if (onsager_valid && !reference_sweeps) {
         dot = onsager_u_AtA_invq;   // by-product of the Onsager CG (g2d_onsager), no sweep
@@ -781,28 +794,26 @@ std::vector<double> vamp::precondCG_solver(std::vector<double> v, std::vector<do
 void vamp::err_measures(data* dataset, int ind) {
     gvb_ctx* ctx = dev.ctx;
     gvb_vec est = (ind == 1) ? dev.x1 : dev.x2;
-    {
-        gvb_vec xs[3] = {est, est, dev.truth}, ys[3] = {dev.truth, nullptr, nullptr};
-        double d[3];
-        DEV(gvb_vec_dots(ctx, 3, xs, ys, 1, d));
-        double corr = d[0] / sqrt(d[1] * d[2]);
-        if (rank == 0) std::cout << "correlation " << (ind == 1 ? "x1_hat" : "x2_hat") << " = " << corr << std::endl;
-        DEV(gvb_vec_axpby(ctx, dev.tmpM, sqrt(1.0 / (double)N), est, -1.0, dev.truth));
-        gvb_vec x2s[1] = {dev.tmpM};
-        double e = 0;
-        DEV(gvb_vec_dots(ctx, 1, x2s, nullptr, 1, &e));
-        if (rank == 0) std::cout << "l2 signal error = " << sqrt(e / d[2]) << std::endl;
-    }
-    double R2;
-    if (ind == 1) {
-        R2 = r2_train(dev.z1);   // z1 = A x1_hat is already on the device
-    } else {
-        if (!dev.ax_x2_valid) {
+    if (!diag_valid) {   // stand-alone call: the same sums as the iteration's batches deliver
+        if (ind == 2 && !dev.ax_x2_valid) {
             DEV(gvb_dAx(ctx, dev.x2, dev.tmpN2));
             dev.ax_x2_valid = true;
         }
-        R2 = r2_train(dev.tmpN2);
+        const double isn = sqrt(1.0 / (double)N);
+        gvb_vec ax = (ind == 1) ? dev.z1 : dev.tmpN2;
+        gvb_red_op ops[6] = {{est, dev.truth, 0, 0, GVB_RED_DOT, 1},     {est, nullptr, 0, 0, GVB_RED_DOT, 1}, {dev.truth, nullptr, 0, 0, GVB_RED_DOT, 1},
+                             {est, dev.truth, isn, -1.0, GVB_RED_SQ, 1}, {dev.y, ax, 1.0, -1.0, GVB_RED_SQ, 0}, {dev.y, nullptr, 0, 0, GVB_RED_DOT, 0}};
+        DEV(gvb_vec_reduce_batch(ctx, 6, ops, diag_sums));
     }
+    diag_valid = false;
+    const double* d = diag_sums;   // <est,truth>, ||est||^2, ||truth||^2, ||est/sqrt(N) - truth||^2, ||y - A est||^2, ||y||^2
+    double corr = d[0] / sqrt(d[1] * d[2]);
+    if (rank == 0) std::cout << "correlation " << (ind == 1 ? "x1_hat" : "x2_hat") << " = " << corr << std::endl;
+    if (rank == 0) std::cout << "l2 signal error = " << sqrt(d[3] / d[2]) << std::endl;
+    // R2 = 1 - ||y - A est||^2 / ||y||^2 over the N individuals (vamp.cpp:1303-1317)
+    double l2_pred_err = sqrt(d[4] / d[5]);
+    if (rank == 0) std::cout << "l2 prediction error = " << l2_pred_err << std::endl;
+    double R2 = 1 - l2_pred_err * l2_pred_err;
     R2trains.push_back(R2);
     if (rank == 0) {
         std::cout << "R2 = " << R2 << std::endl;

@@ -72,14 +72,19 @@ private:
     // GVB_REFERENCE_SWEEPS=1: A x2_hat and <u, A^T A Q^-1 u> by their own bed sweeps like the reference (vamp.cpp:897-915) instead
     // of as by-products of the two CG solves (3 sweeps per iteration less; same values to rounding, tests compare both)
     bool reference_sweeps = false;
-    // The Onsager solve starts from the previous iteration's Q^-1 u instead of zero: the probe u is the same every iteration
-    // (mt19937{seed+S}, vamp.cpp:875), so this is the warm start the reference gives its LMMSE solve (vamp.cpp:591-600), applied to
-    // its second solve.  Unlike the CG by-products this changes the solver's path: results move inside the solver's own tolerance
-    // (alpha2 by < 3e-6 relative on config 1, final estimate 3e-7 vs 1.5e-7 from the reference).  GVB_ONSAGER_WARM=0 or
-    // GVB_REFERENCE_SWEEPS=1 start from zero like the reference.
-    bool onsager_warm = true;
+    // GVB_ONSAGER_WARM=1 (opt-in; the default is the reference's zero start, vamp.cpp:884): the Onsager solve starts from the previous
+    // iteration's Q^-1 u instead of zero -- the probe u is the same every iteration (mt19937{seed+S}, vamp.cpp:875), so this is the warm
+    // start the reference gives its LMMSE solve (vamp.cpp:591-600), applied to its second solve.  It changes the solver's path: the
+    // successive-difference Onsager exit presumes a zero start, so such a solve stops on ||r||/||rhs|| < 1e-5 only (cg.cu).
+    bool onsager_warm = false;
     bool onsager_valid = false;
     double onsager_u_AtA_invq = 0;
+    // sums of the iteration's batched reductions (gvb_vec_reduce_batch), consumed by err_measures / updateNoisePrec:
+    // <est,truth>, ||est||^2, ||truth||^2, ||est/sqrt(N) - truth||^2, ||y - A est||^2, ||y||^2
+    double diag_sums[6] = {0, 0, 0, 0, 0, 0};
+    bool diag_valid = false;
+    double noise_res_norm2 = 0;   // ||A x2_hat - y||^2
+    bool noise_res_valid = false;
     bool extra_diagnostics = false;   // GVB_DIAG=1: the reference's "onsager approx"/polynomial prints (3 extra sweeps)
 
     // ---- device-resident state (HBM) ----
@@ -89,6 +94,7 @@ private:
         gvb_vec rhs = nullptr, bern = nullptr, invq = nullptr, tmpM = nullptr, truth = nullptr;
         gvb_vec y = nullptr, z1 = nullptr, tmpN = nullptr, tmpN2 = nullptr;
         gvb_vec p1 = nullptr, p2 = nullptr, z1h = nullptr, z2h = nullptr, mcov = nullptr, p1_prev = nullptr;
+        long layout_gen = -1;       // gvb_layout_generation() the vectors and cached by-products were made for
         bool ax_x2_valid = false;   // tmpN2 holds Ax(x2) of the current iteration
         gvb_vec ata_x2 = nullptr;   // A^T A x2_hat, by-product of the LMMSE solve; with tmpN2 it warm-starts the next solve sweep-free
         int warm_age = -1;          // solves since tmpN2 / ata_x2 were last seeded by real sweeps (-1: not seeded)
@@ -115,7 +121,6 @@ private:
                int have_start = 0);
     void sync_host(gvb_vec v, std::vector<double>& h, size_t n);
     void store_scaled(gvb_vec v, const std::string& path, double div, int S);
-    double r2_train(gvb_vec ax);
 
 public:
     vamp(int N, int M, int Mt, double gam1, double gamw, int max_iter, double rho, std::vector<double> vars, std::vector<double> probs,

@@ -70,6 +70,10 @@ int gvb_timer_elapsed_ms(gvb_ctx* ctx, int slot, float* ms); /* synchronises on 
 long gvb_launch_count(gvb_ctx* ctx);
 /* bed sweeps (Ax + ATx passes over the packed matrix) since creation */
 long gvb_sweep_count(gvb_ctx* ctx);
+/* stream synchronisations that returned a reduction (or a solver's exit flag) to the host since the context was created */
+long gvb_host_sync_count(gvb_ctx* ctx);
+/* bumped by every (re)load of the matrix and every gvb_set_mask: cached by-products of earlier solves are stale after a change */
+long gvb_layout_generation(gvb_ctx* ctx);
 /* per-sweep device timing: when enabled every X.v / X^T.u sweep is bracketed by CUDA events on the
  * context's stream.  gvb_profile_read synchronises, returns out[0..3] = {X.v total ms, X.v sweeps,
  * X^T.u total ms, X^T.u sweeps} since the last read and resets the counters. */
@@ -155,6 +159,18 @@ int gvb_vec_axpby_div(gvb_ctx* ctx, gvb_vec out, double a, gvb_vec x, double b, 
 /* res[k] = <x[k], y[k]> (y[k]==NULL: squared norm); inner_prod / l2_norm2, utilities.cpp:190-214.
  * sync!=0 sums over ranks (one fused NCCL allreduce of n scalars instead of n MPI_Allreduce). */
 int gvb_vec_dots(gvb_ctx* ctx, int n, const gvb_vec* x, const gvb_vec* y, int sync, double* res);
+/* A batch of reductions over vectors of any lengths in ONE host synchronisation (two launches, one fused allreduce):
+ *   GVB_RED_DOT: res[k] = <x, y>  (y == NULL: ||x||^2)      GVB_RED_SQ: res[k] = ||a*x + b*y||^2  (y == NULL: ||a*x||^2)
+ * sync != 0 sums over the ranks (M-vectors); such operations must come first in the batch.  Replaces the separate
+ * inner_prod / l2_norm2 allreduces of the iteration's diagnostics and exit tests (vamp.cpp:741-749, 892-927, 1232-1317). */
+#define GVB_RED_BATCH 16
+enum { GVB_RED_DOT = 0, GVB_RED_SQ = 1 };
+typedef struct {
+    gvb_vec x, y;
+    double a, b;
+    int kind, sync;
+} gvb_red_op;
+int gvb_vec_reduce_batch(gvb_ctx* ctx, int nops, const gvb_red_op* ops, double* res);
 /* res[0] = ||x - y||^2 (local or rank-summed) -- the gamma re-estimation residuals, vamp.cpp:326,692 */
 int gvb_vec_dist2(gvb_ctx* ctx, gvb_vec x, gvb_vec y, int sync, double* res);
 
@@ -198,10 +214,15 @@ int gvb_assoc_pvals(gvb_ctx* ctx, gvb_vec yres, gvb_vec coef, gvb_vec select, gv
 int gvb_cg_solve_ex(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters,
                     double* rel_res, gvb_vec ax_mu, double* dots3);
 
-/* Warm-started variant: ata_mu (M-vector) additionally carries A^T A * mu.  have_start != 0: on entry ax_mu / ata_mu hold A mu and
+/* Warm-started variant: ata_mu (M-vector) additionally carries A^T A * mu.  have_start == 1: on entry ax_mu / ata_mu hold A mu and
  * A^T A mu of the START vector in mu (the outputs of the previous call that produced it; tau / gam2 may have changed since), and
  * the initial residual of precondCG_solver (vamp.cpp:1141-1146, two sweeps in the reference) is formed from them without a sweep.
- * On exit both describe the returned mu. */
+ * have_start == 2: the caller states that the start vector is zero (mu is cleared): no sweep and no host-visible norm -- the
+ * zero-vector shortcut of lmmse_mult, vamp.cpp:1079-1080.  have_start == 0: any start vector (one host-visible norm decides
+ * whether the shortcut applies).  An Onsager-mode solve (denoiser == 0) with have_start == 1 stops on ||r||/||rhs|| < 1e-5 only:
+ * the reference's successive-difference exit (vamp.cpp:1174-1193) presumes the monotone <u,mu_k> of a zero start.
+ * On exit both by-products describe the returned mu.
+ * The solver's scalars (alpha, beta, the exit tests) live on the device: the stream does not drain inside a solve. */
 int gvb_cg_solve_warm(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters,
                       double* rel_res, gvb_vec ax_mu, gvb_vec ata_mu, int have_start, double* dots3);
 

@@ -396,6 +396,19 @@ def bernoulli_probe(seed: int, S: int, M: int, Mt: int) -> np.ndarray:
     return (2.0 * (canon < 0.5) - 1.0) / math.sqrt(Mt)
 
 
+def sharded_probe(seed: int, S: int, M: int, Mt: int, nranks: int = 1) -> np.ndarray:
+    """The probe of an R-rank run laid end to end: shard r (divide_work, utilities.cpp:266-281) holds
+    bernoulli_probe(seed, S_r, M_r, Mt).  nranks == 1 is bernoulli_probe(seed, S, M, Mt) itself."""
+    if nranks <= 1:
+        return bernoulli_probe(seed, S, M, Mt)
+    assert S == 0 and M == Mt, "the emulated multi-rank probe covers the whole marker range"
+    parts = []
+    for r in range(nranks):
+        Mr, Sr = divide_work(Mt, nranks, r)
+        parts.append(bernoulli_probe(seed, Sr, Mr, Mt))
+    return np.concatenate(parts)
+
+
 # --------------------------------------------------------------------------------------------
 # LMMSE operator and preconditioned CG, vamp.cpp:1074-1229
 # --------------------------------------------------------------------------------------------
@@ -461,6 +474,10 @@ class VampConfig:
     gamma_min: float = 1e-11
     gamma_max: float = 1e11
     auto_var_max_iter: int = 5
+    # emulation of an R-rank run of the reference on one process: the only rank-dependent input of the algorithm is the
+    # Onsager probe, which rank r draws from mt19937{seed + S_r} for its own M_r markers (vamp.cpp:875-882); everything
+    # else is a sum over shards (MPI_Allreduce) and differs from the single-rank run by summation order only
+    nranks: int = 1
 
 
 @dataclass
@@ -534,7 +551,7 @@ def infere_linear(ds: Dataset, cfg: VampConfig) -> VampTrace:
         mu_CG_last = x2_hat.copy()
         tr.x2_hat.append(x2_hat / sqrtN)
         # Onsager, vamp.cpp:871-889
-        bern = bernoulli_probe(cfg.seed, ds.S, M, Mt)
+        bern = sharded_probe(cfg.seed, ds.S, M, Mt, cfg.nranks)
         invQ, k2 = precond_cg(ds, bern, np.zeros(M), gamw, gam2, cfg.CG_max_iter, 0)
         alpha2 = gam2 * bern.dot(invQ)
         tr.alpha2.append(alpha2)

@@ -503,3 +503,62 @@ def test_people_statistics_and_xxt_solver(C, oracle):
     assert np.array_equal(numb_p, g["numb_people"])
     assert relerr(mave_p, g["mave_people"]) < TOL_MATVEC and relerr(msig_p, g["msig_people"]) < TOL_MATVEC
     assert relerr(u, g["cg_u"]) < 1e-4 and log[-1, 0] < 1e-4
+
+
+@pytest.mark.parametrize("denoiser", [1, 0])
+def test_cg_device_resident_scalars(C, oracle, denoiser, monkeypatch):
+    """The CG driver keeps alpha / beta / the exit tests on the device and enqueues iteration i+1 before it has seen the flag of
+    iteration i (cg.cu).  The speculative form (default) and the wait-every-iteration form (GVB_CG_LAG=0) must run the same number of
+    iterations as the oracle's host loop (vamp.cpp:1161-1224), give bit-identical solutions and the same per-iteration log; the
+    speculative iteration is not counted as sweeps; max_iter == 0 returns the start vector and <rhs, mu_start>."""
+    N, M = 2000, 3100
+    bed = oracle.synth_bed(17, 0, M, N, miss_rate=0.005)
+    ds = oracle.Dataset(bed, N)
+    rng = np.random.default_rng(3)
+    tau, gam2, K = 1.7, 0.4, 40
+    rhs_h = rng.normal(size=M) if denoiser else oracle.bernoulli_probe(3, 0, M, M)
+    log_ref = []
+    mu_ref, its_ref = oracle.precond_cg(ds, rhs_h, np.zeros(M), tau, gam2, K, denoiser, log=log_ref)
+    out = {}
+    for lag in ("1", "0"):
+        monkeypatch.setenv("GVB_CG_LAG", lag)
+        with make_ctx(C, "lut") as ctx:
+            ctx.load_host(bed, N).compute_stats(1.0)
+            rhs, mu = ctx.vecM(rhs_h), ctx.vecM()
+            s0, h0 = ctx.sweeps(), ctx.host_syncs()
+            its, log = ctx.cg_solve(rhs, mu, tau, gam2, K, denoiser)
+            out[lag] = (its, log.copy(), mu.download(), ctx.sweeps() - s0, ctx.host_syncs() - h0)
+            if lag == "1":
+                mu0 = rng.normal(size=M)
+                mu.upload(mu0)
+                ax = ctx.vecN()
+                its0, _, d3 = ctx.cg_solve_ex(rhs, mu, tau, gam2, 0, denoiser, ax)
+                assert its0 == 0 and np.array_equal(mu.download(), mu0)
+                assert np.isclose(d3[1], rhs_h @ mu0, rtol=1e-12) and np.isclose(d3[0], rhs_h @ rhs_h, rtol=1e-12)
+    its, log, mu_d, sweeps, syncs = out["1"]
+    assert its == its_ref == out["0"][0], (its, its_ref, out["0"][0])
+    assert np.array_equal(mu_d, out["0"][2]) and np.array_equal(log, out["0"][1])
+    assert sweeps == 2 * its == out["0"][3]                      # the iteration enqueued after the exit is not a sweep
+    assert relerr(mu_d, mu_ref) < 1e-5
+    n_res = len(log_ref)                                         # an Onsager exit leaves no residual line for its last iteration
+    assert np.allclose(log[:n_res, 0], log_ref, rtol=1e-3)       # ||r||/||rhs|| per iteration: fixed-point sweeps vs FP64 oracle
+    assert syncs <= its + 3
+
+
+def test_reduce_batch(C, oracle):
+    """gvb_vec_reduce_batch: M- and N-vectors mixed, dot / squared-norm-of-combination kinds, one host synchronisation."""
+    N, M = 777, 3001
+    bed = oracle.synth_bed(1, 0, M, N)
+    rng = np.random.default_rng(1)
+    a, b, u, w = rng.normal(size=M), rng.normal(size=M), rng.normal(size=N), rng.normal(size=N)
+    with C.Context(0) as ctx:
+        ctx.load_host(bed, N)
+        va, vb, vu, vw = ctx.vecM(a), ctx.vecM(b), ctx.vecN(np.pad(u, (0, 4 * ((N + 3) // 4) - N))), ctx.vecN(np.pad(w, (0, 4 * ((N + 3) // 4) - N)))
+        h0 = ctx.host_syncs()
+        res = ctx.reduce_batch([(C.RED_DOT, va, vb, 0, 0, 1), (C.RED_DOT, va, None, 0, 0, 1), (C.RED_SQ, va, vb, 0.5, -2.0, 1), (C.RED_SQ, vb, None, 3.0, 0, 1),
+                                (C.RED_SQ, vu, vw, 1.0, -1.0, 0), (C.RED_DOT, vu, vw, 0, 0, 0)])
+        assert ctx.host_syncs() - h0 == 1
+        ref = [a @ b, a @ a, ((0.5 * a - 2.0 * b) ** 2).sum(), 9.0 * (b @ b), ((u - w) ** 2).sum(), u @ w]
+        assert np.allclose(res, ref, rtol=1e-13)
+        with pytest.raises(C.GvbError):
+            ctx.reduce_batch([(C.RED_DOT, vu, vw, 0, 0, 0), (C.RED_DOT, va, vb, 0, 0, 1)])   # rank-summed operations come first

@@ -149,3 +149,25 @@ def test_probit_pieces_against_the_live_reference(oracle, R):
             assert relerr(oracle.g1d_bin_class(p, tau1, y, mcov), gd) < 1e-12
     finally:
         rv.close()
+
+
+def test_sharded_probe_against_the_live_reference(oracle, R, tmp_path):
+    """The emulated R-rank probe (oracle.sharded_probe) is, shard by shard, what the reference's g2d_onsager draws when it
+    is built on shard (S_r, M_r) of the matrix: mt19937{seed + S_r}, M_r draws, scaled by 1/sqrt(Mt) (vamp.cpp:875-882)."""
+    N, Mt, seed, nranks = 120, 301, 9, 3
+    bed = oracle.synth_bed(4, 0, Mt, N)
+    bedp = str(tmp_path / "s.bed")
+    oracle.write_bed(bedp, bed)
+    whole = oracle.sharded_probe(seed, 0, Mt, Mt, nranks)
+    assert whole.shape == (Mt,) and np.array_equal(oracle.sharded_probe(seed, 0, Mt, Mt, 1), oracle.bernoulli_probe(seed, 0, Mt, Mt))
+    for r in range(nranks):
+        Mr, Sr = oracle.divide_work(Mt, nranks, r)
+        rd = R.RefData(bedp, N, Mr, Mt=Mt, S=Sr, y=np.zeros(N))
+        rv = R.RefVamp(N, Mr, Mt, [0.9, 0.1], [0.0, 0.1], CG_max_iter=2, seed=seed)
+        try:
+            rv.set_state(1.0, 0.5, 2.0)
+            _, bern, _ = rv.onsager(rd, 0.5, 2.0)
+            assert np.array_equal(bern, whole[Sr:Sr + Mr]), r
+        finally:
+            rv.close()
+            rd.close()

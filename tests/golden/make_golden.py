@@ -319,6 +319,126 @@ def case_pvals(tmp):
     print("pvals: LOO min %.3e, LOCO min %.3e" % (loo.min(), loco.min()))
 
 
+def default_prior_23(Mt):
+    """The reference's built-in 23-component prior (utilities.cpp:96-129) written out, so that it can be passed to a run with Mt <= 50000."""
+    p = min(50000.0 / Mt, 1.0) / (2 - 1.0 / 2 ** 21)
+    probs = [1 - min(50000.0 / Mt, 1.0)]
+    for _ in range(22):
+        probs.append(p)
+        p /= 2
+    step = 10 ** (math.log10(1e2 / 1e-5) / 21)
+    vars_, v = [0.0], 1e-5
+    for _ in range(22):
+        vars_.append(v)
+        v *= step
+    return probs, vars_
+
+
+def _grab_log(log):
+    f = lambda key: np.array([float(l.split("=")[1]) for l in log.splitlines() if l.startswith(key)])
+    pv = [np.array(l.split("=")[1].split(), dtype=float) for l in log.splitlines() if l.startswith("prior variances")]
+    pp = [np.array(l.split("=")[1].split(), dtype=float) for l in log.splitlines() if l.startswith("prior probabilities")]
+    return dict(gamw_log=f("gamw = "), alpha2_log=f("alpha2 = "), prior_vars_last=pv[-1], prior_probs_last=pp[-1])
+
+
+def case_vamp_stress(tmp):
+    """An ill-conditioned linear run: M/N = 5, heavy damping (rho = 0.05, the dnanexus setting), 30 iterations, a sparse
+    23-component prior of the reference's built-in shape (sized as for Mt = 500k markers: 10 % of the markers carry an effect), few causal markers."""
+    N, M, seed, h2, CV, iters = 600, 3000, 21, 0.6, 60, 30
+    bed = O.synth_bed(seed, 0, M, N)
+    bedp = os.path.join(tmp, "s.bed")
+    O.write_bed(bedp, bed)
+    ds0 = O.Dataset(bed, N)
+    beta = O.synth_beta(seed, M, CV, h2)
+    y = ds0.Ax(beta * math.sqrt(N))[:N] + O.synth_noise(seed, N, h2)
+    phenp = os.path.join(tmp, "s.phen")
+    O.write_phen(phenp, y)
+    probs, vars_ = default_prior_23(500000)
+    outd = os.path.join(tmp, "outs") + "/"
+    args = ["--run-mode", "infere", "--model", "linear", "--bed-file", bedp, "--phen-files", phenp, "--N", str(N), "--Mt", str(M),
+            "--out-dir", outd, "--out-name", "g", "--iterations", str(iters), "--CG-max-iter", "40", "--rho", "0.05",
+            "--probs", ",".join(repr(p) for p in probs), "--vars", ",".join(repr(v) for v in vars_), "--h2", str(h2), "--seed", "7",
+            "--stop-criteria-thr", "1e-9"]
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    log = subprocess.run([R.exe("main_real_scalar.exe")] + args, check=True, capture_output=True, text=True, env=env).stdout
+    done = len([l for l in log.splitlines() if l.startswith("iteration = ")])
+    out = dict(N=N, M=M, seed=seed, h2=h2, CV=CV, iterations=iters, iterations_done=done, args=np.array(args[8:]), y=y, beta=beta)
+    for it in (1, 2, 3, 5, 10, 20, done):
+        if it <= done:
+            out[f"x1_{it}"] = np.fromfile(f"{outd}g_it_{it}.bin")
+            out[f"x2_{it}"] = np.fromfile(f"{outd}g_it_{it}_x2_hat.bin")
+            out[f"r1_{it}"] = np.fromfile(f"{outd}g_r1_it_{it}.bin")
+    for nm in ("gam1s", "gam2s", "R2trains"):
+        out[nm] = np.loadtxt(f"{outd}g_{nm}.csv")
+    out.update(_grab_log(log))
+    out["cg_lines"] = len([l for l in log.splitlines() if l.startswith("[CG] it = ")])
+    np.savez_compressed(os.path.join(OUT, "vamp_stress.npz"), **out)
+    print("stress: %d iterations, %d CG lines, corr(x1, beta) = %.3f, R2 last %.4f" %
+          (done, out["cg_lines"], np.corrcoef(out[f"x1_{done}"], beta)[0, 1], out["R2trains"][-1]))
+
+
+def case_modes(tmp):
+    """The run modes around the hot path (main_real.cpp:129-330, 453-594): test (one estimate file and an iteration range), both,
+    restart (with its divide-by-sqrt(N) of the stored r1, vamp.cpp:226-233), predict_single -- outputs of the reference's executable."""
+    g = np.load(os.path.join(OUT, "vamp_linear.npz"))
+    N, M, seed, h2 = int(g["N"]), int(g["M"]), int(g["seed"]), float(g["h2"])
+    bed = O.synth_bed(seed, 0, M, N)
+    bedp, phenp = os.path.join(tmp, "m.bed"), os.path.join(tmp, "m.phen")
+    O.write_bed(bedp, bed)
+    O.write_phen(phenp, g["y"])
+    Nt, seed_t = 800, 99
+    bed_t = O.synth_bed(seed_t, 0, M, Nt)
+    y_t = O.Dataset(bed_t, Nt).Ax(g["beta"] * math.sqrt(Nt))[:Nt] + O.synth_noise(seed_t, Nt, h2)
+    bedt, phent = os.path.join(tmp, "t.bed"), os.path.join(tmp, "t.phen")
+    O.write_bed(bedt, bed_t)
+    O.write_phen(phent, y_t)   # no NAs: the reference's test modes read the raw phenotype and an NA turns every R2 into NaN
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    exe = R.exe("main_real_scalar.exe")
+    run = lambda a: subprocess.run([exe] + a, check=True, capture_output=True, text=True, env=env).stdout
+    val = lambda log, key: float([l for l in log.splitlines() if l.startswith(key)][-1].split("=")[1])
+    common = ["--model", "linear", "--CG-max-iter", "20", "--rho", "0.5", "--probs", ",".join(map(str, PROBS)), "--vars", ",".join(map(str, VARS)),
+              "--h2", str(h2), "--seed", "1"]
+    out = dict(N=N, M=M, seed=seed, N_test=Nt, seed_test=seed_t, y_test=y_t, common=np.array(common))
+    # estimate files of a 4-iteration run
+    outd = os.path.join(tmp, "outm") + "/"
+    run(["--run-mode", "infere", "--bed-file", bedp, "--phen-files", phenp, "--N", str(N), "--Mt", str(M), "--out-dir", outd, "--out-name", "g",
+         "--iterations", "4"] + common)
+    for it in range(1, 5):
+        out[f"est_{it}"] = np.fromfile(f"{outd}g_it_{it}.bin")
+    out["r1_3"] = np.fromfile(f"{outd}g_r1_it_3.bin")
+    test_args = ["--bed-file-test", bedt, "--phen-files-test", phent, "--N-test", str(Nt), "--Mt-test", str(M)]
+    # test, one file
+    log = run(["--run-mode", "test", "--estimate-file", f"{outd}g_it_4.bin"] + test_args)
+    out.update(test_R2=val(log, "test R2 = "), test_err2=val(log, "test l2 pred err^2 = "), test_sd2=val(log, "y stdev^2 = "))
+    # test, iteration range 1..4
+    log = run(["--run-mode", "test", "--estimate-file", f"{outd}g_it_4.bin", "--test-iter-range", "1,4"] + test_args)
+    line = [l for l in log.splitlines() if l.rstrip().endswith(",") and "," in l][-1]
+    out.update(range_R2=np.array([float(x) for x in line.split(",") if x.strip()]), range_max_R2=val(log, "max R2 = "), range_max_ind=val(log, "max ind = "))
+    # both
+    outb = os.path.join(tmp, "outb") + "/"
+    log = run(["--run-mode", "both", "--bed-file", bedp, "--phen-files", phenp, "--N", str(N), "--Mt", str(M), "--out-dir", outb, "--out-name", "g",
+               "--iterations", "4"] + common + test_args)
+    out.update(both_R2=val(log, "test R2 = "), both_err2=val(log, "test l2 pred err^2 = "), both_intercept=val(log, "intercept = "), both_scale=val(log, "scale = "),
+               both_x1_last=np.fromfile(f"{outb}g_it_4.bin"))
+    # restart from iteration 3's r1 with given precisions
+    outr = os.path.join(tmp, "outr") + "/"
+    gam1_init, gamw_init = float(g["gam1s"][2]), float(g["gamw_log"][5])
+    log = run(["--run-mode", "restart", "--bed-file", bedp, "--phen-files", phenp, "--N", str(N), "--Mt", str(M), "--out-dir", outr, "--out-name", "g",
+               "--iterations", "3", "--estimate-file", f"{outd}g_r1_it_3.bin", "--gam1-init", repr(gam1_init), "--gamw-init", repr(gamw_init)] + common)
+    out.update(restart_gam1_init=gam1_init, restart_gamw_init=gamw_init, restart_gam1s=np.loadtxt(f"{outr}g_gam1s.csv"),
+               restart_R2trains=np.loadtxt(f"{outr}g_R2trains.csv"), restart_gamw_log=_grab_log(log)["gamw_log"])
+    for it in range(1, 4):
+        out[f"restart_x1_{it}"] = np.fromfile(f"{outr}g_it_{it}.bin")
+    # predict_single
+    outp = os.path.join(tmp, "outp") + "/"
+    os.makedirs(outp, exist_ok=True)
+    run(["--run-mode", "predict_single", "--bed-file-test", bedt, "--N-test", str(Nt), "--Mt-test", str(M), "--estimate-file", f"{outd}g_it_4.bin",
+         "--out-dir", outp, "--out-name", "g"])
+    out["predict_single"] = np.loadtxt(f"{outp}g_predict.csv")
+    np.savez_compressed(os.path.join(OUT, "modes.npz"), **out)
+    print("modes: test R2 %.6f, range %s, both R2 %.6f, restart R2 %s" % (out["test_R2"], out["range_R2"], out["both_R2"], out["restart_R2trains"]))
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first: make -C oracle ref"
     with tempfile.TemporaryDirectory() as tmp:
@@ -331,4 +451,6 @@ if __name__ == "__main__":
         case_pvals(tmp)
         case_config1(tmp)
         case_xxt(tmp)
+        case_vamp_stress(tmp)
+        case_modes(tmp)
     print("golden vectors written to", OUT)

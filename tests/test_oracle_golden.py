@@ -193,3 +193,40 @@ def test_xxt_people_statistics_and_solver(oracle):
     assert np.array_equal(pe[2], g["numb_people"])                       # counts: exact
     u, its = oracle.cg_solver_aat(ds, g["cg_rhs"], np.zeros(4 * ds.mbytes), float(g["cg_tau"]), float(g["cg_gam2"]), pe, int(g["cg_max_iter"]))
     assert relerr(u, g["cg_u"]) < 1e-12
+
+
+def default_prior_23(Mt):
+    """The reference's built-in 23-component prior (utilities.cpp:96-129), as tests/golden/make_golden.py passed it."""
+    p = min(50000.0 / Mt, 1.0) / (2 - 1.0 / 2 ** 21)
+    probs = [1 - min(50000.0 / Mt, 1.0)]
+    for _ in range(22):
+        probs.append(p)
+        p /= 2
+    step = 10 ** (math.log10(1e2 / 1e-5) / 21)
+    vars_, v = [0.0], 1e-5
+    for _ in range(22):
+        vars_.append(v)
+        v *= step
+    return probs, vars_
+
+
+def test_vamp_stress_case(oracle):
+    """The restatement on the ill-conditioned golden case (M/N = 5, rho = 0.05, 30 iterations, the 23-component prior,
+    make_golden.py:case_vamp_stress) against main_real.exe's files and log."""
+    g = golden("vamp_stress.npz")
+    N, M, iters = int(g["N"]), int(g["M"]), int(g["iterations_done"])
+    bed = oracle.synth_bed(int(g["seed"]), 0, M, N)
+    y = g["y"]
+    avg = float(np.cumsum(y)[-1]) / N
+    sqn = math.sqrt((N - 1) / float(np.cumsum((y - avg) * (y - avg))[-1]))
+    ds = oracle.Dataset(bed, N, phen=y * sqn)
+    probs, vars_ = default_prior_23(500000)
+    cfg = oracle.VampConfig(iterations=iters, rho=0.05, probs=tuple(probs), vars=tuple(vars_), CG_max_iter=40, gamw=1.0 / (1.0 - float(g["h2"])),
+                            seed=7, stop_criteria_thr=1e-9)
+    tr = oracle.infere_linear(ds, cfg)
+    assert len(tr.x1_hat) == iters
+    for it in (2, 3, 5, 10, 20, iters):
+        assert relerr(tr.x1_hat[it - 1], g[f"x1_{it}"]) < 1e-8, it
+        assert relerr(tr.x2_hat[it - 1], g[f"x2_{it}"]) < 1e-8, it
+    assert np.allclose(tr.gamw, g["gamw_log"][1::2], rtol=1e-5) and np.allclose(tr.alpha2, g["alpha2_log"], rtol=1e-5)
+    assert np.allclose(tr.gam1s, g["gam1s"], rtol=1e-5) and np.allclose(tr.R2trains, g["R2trains"], rtol=1e-5, atol=1e-6)

@@ -194,6 +194,18 @@ class Context:
         self.h = h
         self.rank, self.nranks = rank, nranks
 
+    @classmethod
+    def shared(cls, parent: "Context") -> "Context":
+        """A second context on the parent's device that shares its NCCL communicator (gvb_ctx_create_shared): another matrix
+        (a test set, a small self-check problem) next to the resident one.  Close it before the parent."""
+        self = cls.__new__(cls)
+        self.L = load()
+        h = vp()
+        _chk(self.L.gvb_ctx_create_shared(ctypes.byref(h), parent.h))
+        self.h = h
+        self.rank, self.nranks = parent.rank, parent.nranks
+        return self
+
     def close(self):
         if self.h:
             self.L.gvb_ctx_destroy(self.h)

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <future>
 #include <iomanip>
 #include <iostream>
 #include <numeric>
@@ -99,7 +100,10 @@ vamp::vamp(int M, double gam1, double gamw, std::vector<double> true_signal, int
     async_outputs = !(ao && ao[0] == '0');
 }
 
-vamp::~vamp() { dev_close(); }
+vamp::~vamp() {
+    wait_writes();
+    dev_close();
+}
 
 // ---------------------------------------------------------------------------------------------------
 // device state
@@ -152,28 +156,53 @@ void vamp::emit_output(int which, gvb_vec v, size_t n, const std::string& path, 
     std::vector<double> h;
     sync_host(v, h, n);
     finish_output(which, h.data(), n, scale, S);
+    start_writes();
 }
 
 void vamp::finish_output(int which, const double* h, size_t n, double scale, int S) {
     const std::string& path = snap_path[which];
     if (which == SNAP_Z1) {
         z1.assign(h, h + n);
-        if (files_enabled() && rank == 0) {
-            std::ofstream f(path);
-            for (double v : z1) f << v << '\n';
-        }
+        if (files_enabled() && rank == 0) pending_writes.push_back({path, z1, S, (int)n, true});
         return;
     }
     if (which == SNAP_X1) {
         x1_hat.assign(h, h + n);
         for (size_t i = 0; i < n; i++) x1_hat_stored[i] = x1_hat[i] / scale;
-        if (files_enabled()) mpi_store_vec_to_file(path, x1_hat_stored, S, M);
+        if (files_enabled()) pending_writes.push_back({path, x1_hat_stored, S, M, false});
         return;
     }
     if (!files_enabled()) return;
     std::vector<double> scaled(n);
     for (size_t i = 0; i < n; i++) scaled[i] = h[i] / scale;
-    mpi_store_vec_to_file(path, scaled, S, M);
+    pending_writes.push_back({path, std::move(scaled), S, M, false});
+}
+
+// The iteration's files (the z1 csv is 400k formatted doubles at biobank scale: tens of milliseconds of host time) are written by a
+// background task while the next iteration's kernels run; at most one batch is in flight, and wait_writes() is called before
+// anything reads the files or the object goes away.  GVB_ASYNC_OUT=0: written in place.
+void vamp::wait_writes() {
+    if (writer.valid()) writer.get();
+}
+
+void vamp::start_writes() {
+    if (pending_writes.empty()) return;
+    wait_writes();
+    auto job = [batch = std::move(pending_writes)]() {
+        for (const OutFile& o : batch) {
+            if (o.text) {
+                std::ofstream f(o.path);
+                for (double v : o.data) f << v << '\n';
+            } else {
+                mpi_store_vec_to_file(o.path, o.data, o.S, o.M);
+            }
+        }
+    };
+    pending_writes.clear();
+    if (async_outputs)
+        writer = std::async(std::launch::async, std::move(job));
+    else
+        job();
 }
 
 void vamp::flush_outputs(double scale, int S) {
@@ -185,6 +214,7 @@ void vamp::flush_outputs(double scale, int S) {
         snap_open[which] = false;
         finish_output(which, h, (size_t)n, scale, S);
     }
+    start_writes();
 }
 
 void vamp::dev_denoise(double g1_prec, double* sum_d, double* dist2) {
@@ -239,6 +269,7 @@ std::vector<double> vamp::infere_linear(data* dataset) {
     linear_begin(dataset);
     for (int it = 1; it <= max_iter; it++)
         if (linear_iteration(dataset, it)) break;
+    wait_writes();
     if (store_pvals == 1) {   // association tests on the final estimate (vamp.cpp:761-777)
         std::vector<double> yf = dataset->filter_pheno();
         std::string filepath_out_pvals = out_dir + out_name + "_pvals.bin";
@@ -516,6 +547,7 @@ bool vamp::linear_iteration(data* dataset, int it) {
 }
 
 std::vector<double> vamp::linear_end() {
+    wait_writes();
     if (files_enabled() && rank == 0) {
         store_vec_to_file(out_dir + out_name + "_gam1s.csv", gam1s);
         store_vec_to_file(out_dir + out_name + "_gam2s.csv", gam2s);

@@ -7,6 +7,7 @@
 // the host keeps only scalars, the L-component prior and the file output.
 // Out of scope: --model robust, --use-XXT-denoiser, cross-validation, state evolution.
 #pragma once
+#include <future>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -114,6 +115,16 @@ private:
     void emit_output(int which, gvb_vec v, size_t n, const std::string& path, double scale, int S);
     void finish_output(int which, const double* h, size_t n, double scale, int S);
     void flush_outputs(double scale, int S);
+    struct OutFile {
+        std::string path;
+        std::vector<double> data;
+        int S, M;
+        bool text;   // one formatted value per line (the z1 csv) instead of raw doubles at byte offset S*8
+    };
+    std::vector<OutFile> pending_writes;
+    std::future<void> writer;   // the previous iteration's files, written while this iteration's kernels run
+    void start_writes();
+    void wait_writes();
     void dev_open(data* dataset);
     void dev_close();
     void dev_denoise(double g1_prec, double* sum_d, double* dist2);

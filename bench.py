@@ -345,7 +345,7 @@ def parity_check(D, ctx, N, Mt, S, M, miss):
       small:    a 3000 x 2501 matrix (1 % missing) sharded by divide_work over the same communicator: shard bytes bit-exact, X.v
                 (all-reduced) and X^T.u within 1e-6, CG solution within 1e-5 with the oracle's iteration count, denoiser sums;
       fullsize: on the resident workload matrix: three sampled markers per rank re-generated by the oracle (bytes bit-exact,
-                mu / 1/sigma 1e-12, their X^T.u entries and the all-reduced X.v of a vector supported on all ranks' samples 1e-6),
+                mu / 1/sigma 1e-10, their X^T.u entries and the all-reduced X.v of a vector supported on all ranks' samples 1e-6),
                 adjointness <X v, u> = sum_shards <v, X^T u> with dense vectors, bit-reproducibility of both sweeps."""
     from gvamp_b200 import capi
     from oracle import oracle as O
@@ -406,7 +406,7 @@ def parity_check(D, ctx, N, Mt, S, M, miss):
     rhs_sum = D.reduce([float(np.dot(vd, atx))], "sum")[0]
     fs["adjointness_rel"] = abs(lhs - rhs_sum) / float(np.linalg.norm(ax[:N]) * np.linalg.norm(u))
     fs["bit_reproducible"] = bool(np.array_equal(ctx.Ax(vd), ax) and np.array_equal(ctx.ATx(u), atx))
-    ok_full = (fs["bytes_equal"] and fs["stats_rel"] < 1e-12 and fs["atx_sampled_rel"] < 1e-6 and fs["ax_sampled_rel"] < 1e-6
+    ok_full = (fs["bytes_equal"] and fs["stats_rel"] < 1e-10 and fs["atx_sampled_rel"] < 1e-6 and fs["ax_sampled_rel"] < 1e-6
                and fs["adjointness_rel"] < 1e-6 and fs["bit_reproducible"])
     ok_all = D.reduce([1.0 if (ok_small and ok_full) else 0.0], "min")[0] == 1.0
     # the worst rank's figures travel to rank 0

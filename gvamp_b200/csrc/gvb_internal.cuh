@@ -56,7 +56,8 @@ struct gvb_ctx {
     // individual-major twin of the matrix (twin.cu): same indexing, every word 4x4-transposed, so that byte k of a word is
     // the ready-made table index of individual k for X.v; held only while spare HBM allows it
     uint32_t* bed_twin = nullptr;
-    int twin_state = 0;             // 0: not built yet, 1: built, -1: not available (X.v gathers its indices from `bed`)
+    int twin_state = 0;             // 0: not built yet, 1: built, 2: built for the first twin_stripes stripes only, -1: not available (X.v gathers from `bed`)
+    long twin_stripes = 0;          // stripes [0, twin_stripes) have a twin (== n_stripes when twin_state == 1)
 
     // phenotype mask / valid-individual mask, one 32-bit word per position: bits 0,2,4,6 of every
     // byte are set when individual k of that position is present (resp. < N)

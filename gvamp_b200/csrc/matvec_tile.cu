@@ -212,7 +212,7 @@ __device__ __forceinline__ void ax_consume(const char* __restrict__ tabc, uint32
 
 template <int NW, int NS, int MADK, bool TW>
 __global__ void __launch_bounds__(NW * 32 + 32, 1)
-ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, long Mg_pad, long n_stripes, int n_sblocks, int n_gchunks,
+ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, long Mg_pad, long stripe0, long n_stripes, int n_sblocks, int n_gchunks,
                int tiles_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out, int one, const int* __restrict__ skip) {
     if (skip && *skip) return;   // device-side predicate of a speculatively enqueued CG iteration (cg.cu): uniform over the grid
     extern __shared__ __align__(1024) char smem[];
@@ -255,9 +255,11 @@ ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, l
             tab_produce_item(tp, tab_sm, tsrc, nt, lane);
             continue;
         }
-        const long t = (long)sb * NW + warp;
-        const bool active = t < n_stripes;
-        const uint32_t* bsrc = bed + ((active ? t : 0) * Mg_pad + tile_lo * 32) * 32;
+        // stripes [stripe0, stripe0 + n_stripes) of the matrix behind `bed` (a partial twin covers a prefix of the stripes, the one
+        // matrix the rest: two launches with different TW)
+        const long t = stripe0 + (long)sb * NW + warp;
+        const bool active = (long)sb * NW + warp < n_stripes;
+        const uint32_t* bsrc = bed + ((active ? t : stripe0) * Mg_pad + tile_lo * 32) * 32;
         auto issue_bed = [&](int i) {
             if (active && i < nt) {
                 if (lane == 0) {
@@ -453,7 +455,7 @@ int pick_chunk(int requested, long rows, long steps, int sm_count) {
 }   // read per launch: the tests vary the chunking within one process
 
 template <int NW, int NS, int MADK, bool TW>
-int launch_ax(gvb_ctx* c, unsigned long long* accN) {
+int launch_ax(gvb_ctx* c, unsigned long long* accN, long stripe0, long n_stripes) {
     using Cfg = TileCfg<NW, NS>;
     auto kern = ax_tile_kernel<NW, NS, MADK, TW>;
     static unsigned long long attr_done = 0;   // one bit per device: the attribute is per device, a process may hold several contexts
@@ -461,12 +463,14 @@ int launch_ax(gvb_ctx* c, unsigned long long* accN) {
         GVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         attr_done |= 1ull << (c->device & 63);
     }
+    if (n_stripes <= 0) return GVB_OK;
     const long n_tiles = c->Mg_pad / 32;
-    int n_sblocks = (int)((c->n_stripes + NW - 1) / NW);
+    int n_sblocks = (int)((n_stripes + NW - 1) / NW);
     const int tpc = pick_chunk(tune().ax_tiles_per_chunk, n_sblocks, n_tiles, c->sm_count);
     int n_gchunks = (int)((n_tiles + tpc - 1) / tpc);
     int grid = std::min(n_sblocks * n_gchunks, c->sm_count);
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(TW ? c->bed_twin : c->bed, c->tab_v, c->Mg_pad, c->n_stripes, n_sblocks, n_gchunks, tpc, c->work_counter, accN, 1, c->skip);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(TW ? c->bed_twin : c->bed, c->tab_v, c->Mg_pad, stripe0, n_stripes, n_sblocks, n_gchunks, tpc, c->work_counter,
+                                                       accN, 1, c->skip);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }
@@ -721,24 +725,32 @@ int ensure_scratch(gvb_ctx* c, bool need_tab_u, bool need_tab_v, bool miss) {
     return GVB_OK;
 }
 
+int ax_gather(gvb_ctx* c, unsigned long long* accN, const TileTune& t, long stripe0, long n) {
+    if (t.variant == 1) return t.use_mad ? launch_ax<12, 3, 4, false>(c, accN, stripe0, n) : launch_ax<12, 3, 0, false>(c, accN, stripe0, n);
+    switch (t.use_mad) {
+        case 0: return launch_ax<15, 2, 0, false>(c, accN, stripe0, n);
+        case 1: return launch_ax<15, 2, 1, false>(c, accN, stripe0, n);
+        case 2: return launch_ax<15, 2, 2, false>(c, accN, stripe0, n);
+        case 3: return launch_ax<15, 2, 3, false>(c, accN, stripe0, n);
+        default: return launch_ax<15, 2, 4, false>(c, accN, stripe0, n);
+    }
+}
+
 int ax_main(gvb_ctx* c, unsigned long long* accN) {
     const TileTune t = tune();
-    // X.v on the individual-major twin (twin.cu) when spare HBM holds one: the walk of X^T.u, no index gather
+    // X.v on the individual-major twin (twin.cu) for as many stripes as spare HBM holds one: the walk of X^T.u, no index gather;
+    // the remaining stripes gather their indices from the one matrix
     const char* tw = getenv("GVB_TWIN");
     const bool want_twin = !(tw && !strcmp(tw, "0"));
     if (want_twin && c->twin_state == 0) GVB_CHECK(gvb_twin_build(c));
-    if (want_twin && c->twin_state == 1) {
-        if (t.variant == 1) return launch_ax<12, 3, 0, true>(c, accN);
-        return t.twin_mad > 0 ? launch_ax<15, 2, 1, true>(c, accN) : launch_ax<15, 2, 0, true>(c, accN);
+    long T = (want_twin && c->twin_state > 0) ? c->twin_stripes : 0;
+    if (T > 0) {
+        if (t.variant == 1)
+            GVB_CHECK((launch_ax<12, 3, 0, true>(c, accN, 0, T)));
+        else
+            GVB_CHECK((t.twin_mad > 0 ? launch_ax<15, 2, 1, true>(c, accN, 0, T) : launch_ax<15, 2, 0, true>(c, accN, 0, T)));
     }
-    if (t.variant == 1) return t.use_mad ? launch_ax<12, 3, 4, false>(c, accN) : launch_ax<12, 3, 0, false>(c, accN);
-    switch (t.use_mad) {
-        case 0: return launch_ax<15, 2, 0, false>(c, accN);
-        case 1: return launch_ax<15, 2, 1, false>(c, accN);
-        case 2: return launch_ax<15, 2, 2, false>(c, accN);
-        case 3: return launch_ax<15, 2, 3, false>(c, accN);
-        default: return launch_ax<15, 2, 4, false>(c, accN);
-    }
+    return ax_gather(c, accN, t, T, c->n_stripes - T);
 }
 
 int atx_main(gvb_ctx* c, const int* tab, unsigned long long* acc) {

@@ -150,6 +150,58 @@ miss_sum_kernel(const uint16_t* __restrict__ idx, const unsigned long long* __re
     }
 }
 
+// The same sum with ONE LANE PER MARKER: a warp still takes 32 consecutive markers of one block, but every lane walks its own
+// segment (8-byte groups, 8 in flight: two 32-byte sectors per lane, the L1 serves the three groups that follow a sector's first
+// touch) and owns its marker's sum: no lane sits idle on a short segment (1 % missing of a 32768-block is 82 groups for 128 lane
+// slots in the warp-per-segment form above), no shuffle tree and one RED per marker and block.  ncu of the warp-per-segment form at
+// 1 % missing (profiles/r01_ncu_full_miss_sum_c4shard_1pct.txt): 2.2 TB/s, long_scoreboard 5.5 / short_scoreboard 2.9 per issue,
+// i.e. latency bound; this form keeps 64 KB of index stream in flight per SM.
+__global__ void __launch_bounds__(MISS_THREADS, 1)
+miss_sum_lane_kernel(const uint16_t* __restrict__ idx, const unsigned long long* __restrict__ seg_off, const int* __restrict__ uq, long Npad, long Mpad,
+                     long n_items, unsigned long long* __restrict__ accm, const int* __restrict__ skip) {
+    if (skip && *skip) return;
+    extern __shared__ __align__(16) int U[];   // [MISS_BLOCK_IND] + zero word(s)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long n_batches = Mpad / 32;
+    const long per = (n_items + gridDim.x - 1) / gridDim.x;
+    const long lo = blockIdx.x * per, hi = min(n_items, lo + per);
+    const uint2* __restrict__ groups = reinterpret_cast<const uint2*>(idx);
+    long item = lo;
+    while (item < hi) {
+        const long b = item / n_batches;
+        const long item_end = min(hi, (b + 1) * n_batches);   // items of this CTA that share block b
+        __syncthreads();
+        const long i0 = b * MISS_BLOCK_IND;
+        for (int i = threadIdx.x * 4; i < MISS_BLOCK_IND; i += MISS_THREADS * 4) {
+            int4 x = make_int4(0, 0, 0, 0);
+            if (i0 + i < Npad) x = *reinterpret_cast<const int4*>(uq + i0 + i);   // Npad is a multiple of 128
+            *reinterpret_cast<int4*>(U + i) = x;
+        }
+        if (threadIdx.x < 32) U[MISS_BLOCK_IND + threadIdx.x] = 0;
+        __syncthreads();
+        for (long it = item + warp; it < item_end; it += MISS_THREADS / 32) {
+            const long m0 = (it - b * n_batches) * 32;
+            const long seg = b * Mpad + m0 + lane;
+            unsigned long long g = seg_off[seg];
+            const unsigned long long end = seg_off[seg + 1];
+            long long acc = 0;
+            // |U| < 2^24, so the 32 gathers of one pass fit an int32
+            while (__any_sync(0xffffffffu, g < end)) {
+                uint2 e[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) e[r] = (g + r < end) ? __ldg(groups + g + r) : make_uint2(0x80008000u, 0x80008000u);
+                int a32 = 0;
+#pragma unroll
+                for (int r = 0; r < 8; r++) a32 += U[e[r].x & 0xFFFFu] + U[e[r].x >> 16] + U[e[r].y & 0xFFFFu] + U[e[r].y >> 16];
+                acc += a32;
+                g += 8;
+            }
+            if (acc != 0) atomicAdd(accm + m0 + lane, (unsigned long long)acc);
+        }
+        item = item_end;
+    }
+}
+
 void free_list(gvb_ctx* c) {
     if (c->miss_idx) cudaFree(c->miss_idx);
     if (c->miss_off) cudaFree(c->miss_off);
@@ -214,6 +266,7 @@ int gvb_misslist_build(gvb_ctx* c) {
     miss_fill_kernel<<<grid, 256, 0, c->stream>>>(c->bed, c->validw, c->M, c->Mg, c->Mg_pad, c->n_stripes, c->miss_off, c->miss_idx);
     GVB_LAUNCHED(c);
     GVB_CUDA(cudaFuncSetAttribute(miss_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MISS_SMEM));
+    GVB_CUDA(cudaFuncSetAttribute(miss_sum_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MISS_SMEM));
     GVB_CUDA(cudaStreamSynchronize(c->stream));
     c->miss_nblk = nblk;
     c->miss_entries = (long)entries;
@@ -226,7 +279,11 @@ int gvb_misslist_sum(gvb_ctx* c, unsigned long long* accm) {
     const long Mpad = c->Mg_pad * 4;
     const long n_items = c->miss_nblk * (Mpad / 32);
     const int grid = (int)std::max(1l, std::min(n_items, (long)c->sm_count));
-    miss_sum_kernel<<<grid, MISS_THREADS, MISS_SMEM, c->stream>>>(c->miss_idx, c->miss_off, c->uq, c->Npad, Mpad, n_items, accm, c->skip);
+    const char* form = getenv("GVB_MISS_SUM");   // "warp": one warp per segment (the round-1 form, kept as a cross-check); default: one lane per marker
+    if (form && !strcmp(form, "warp"))
+        miss_sum_kernel<<<grid, MISS_THREADS, MISS_SMEM, c->stream>>>(c->miss_idx, c->miss_off, c->uq, c->Npad, Mpad, n_items, accm, c->skip);
+    else
+        miss_sum_lane_kernel<<<grid, MISS_THREADS, MISS_SMEM, c->stream>>>(c->miss_idx, c->miss_off, c->uq, c->Npad, Mpad, n_items, accm, c->skip);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }

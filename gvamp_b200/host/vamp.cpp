@@ -530,7 +530,7 @@ bool vamp::linear_iteration(data* dataset, int it) {
         double end_lmmse_step = wtime();
         if (rank == 0) std::cout << "lmmse step took " << end_lmmse_step - start_lmmse_step << " seconds." << std::endl;
         total_sweeps += gvb_sweep_count(ctx) - sweeps0;
-        if (rank == 0 && extra_diagnostics) std::cout << "bed sweeps this iteration = " << gvb_sweep_count(ctx) - sweeps0 << std::endl;
+        if (rank == 0 && (extra_diagnostics || getenv("GVB_LOG_SWEEPS"))) std::cout << "bed sweeps this iteration = " << gvb_sweep_count(ctx) - sweeps0 << std::endl;
 
         // stopping rule (vamp.cpp:741-749); the two sums came with the end-of-iteration batch
         const double dd = stop_dd, nn = stop_nn;

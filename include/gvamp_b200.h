@@ -115,9 +115,11 @@ int gvb_get_counts(gvb_ctx* ctx, int64_t* counts);
 long gvb_missing_list_entries(gvb_ctx* ctx);
 
 /* state of the individual-major twin of the matrix that X.v (data::Ax, data.cpp:848-1011) walks when spare HBM holds one:
- * 1 built, 0 not decided yet (the first X.v after gvb_compute_stats decides), -1 not held (shard too large for a second
- * orientation, or env GVB_TWIN=0): X.v then gathers its table indices from the one matrix.  Results are bit-identical. */
+ * 1 built, 2 built for a prefix of the stripes only (as many as spare HBM holds; the other stripes gather from the one matrix),
+ * 0 not decided yet (the first X.v after gvb_compute_stats decides), -1 not held (no spare HBM, or env GVB_TWIN=0): X.v then
+ * gathers its table indices from the one matrix.  Results are bit-identical in every state. */
 int gvb_twin_state(gvb_ctx* ctx);
+long gvb_twin_stripes(gvb_ctx* ctx); /* stripes (of 128 individuals) that have a twin */
 
 /* ---- X.v and X^T.u, host-pointer drop-in --------------------------------------------------------- */
 /* data::Ax(double* v, SB, LB), data.cpp:848-1011 incl. the MPI_Allreduce at :995.

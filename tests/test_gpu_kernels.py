@@ -187,12 +187,14 @@ def test_missing_list_equals_second_walk(C, oracle, N, M, miss, monkeypatch):
     ds = oracle.Dataset(bed, N)
     u = np.random.default_rng(3).normal(size=N)
     res = {}
-    for mode in ("list", "twopass"):
-        monkeypatch.setenv("GVB_MISS", mode)
+    for mode in ("list", "list_warp", "twopass"):
+        monkeypatch.setenv("GVB_MISS", mode.split("_")[0])
+        monkeypatch.setenv("GVB_MISS_SUM", "warp" if mode == "list_warp" else "lane")   # both forms of the gather kernel
         with make_ctx(C, "lut") as ctx:
             ctx.load_host(bed, N).compute_stats(1.0)
             res[mode] = (ctx.ATx(u), ctx.ATx(u), ctx.missing_list_entries())
     assert res["list"][2] > 0 and res["twopass"][2] == 0          # the list was really built / really bypassed
+    assert np.array_equal(res["list"][0], res["list_warp"][0])
     assert res["list"][2] % 4 == 0 and res["list"][2] >= ds.counts()[:, 5].sum()
     assert np.array_equal(res["list"][0], res["twopass"][0]) and np.array_equal(res["list"][0], res["list"][1])
     assert relerr(res["list"][0], ds.ATx(u)) < TOL_MATVEC
@@ -211,14 +213,22 @@ def test_twin_layout_is_bit_identical(C, oracle, N, M, miss, monkeypatch):
     ds = oracle.Dataset(bed, N, mask4=mask4, nonas=int(present.sum()))
     v = np.random.default_rng(4).normal(size=M)
     res = {}
-    for mode in ("0", "1"):
-        monkeypatch.setenv("GVB_TWIN", mode)
+    n_stripes = ((N + 3) // 4 + 31) // 32
+    for mode in ("0", "1", "partial"):
+        if mode == "partial":                                        # a twin for the first third of the stripes only: two launches per X.v
+            monkeypatch.delenv("GVB_TWIN")
+            monkeypatch.setenv("GVB_TWIN_STRIPES", str(n_stripes // 3))
+        else:
+            monkeypatch.setenv("GVB_TWIN", mode)
         with make_ctx(C, "lut") as ctx:
             ctx.load_host(bed, N).set_mask(mask4, int(present.sum())).compute_stats(1.0)
             assert ctx.twin_state() == 0                             # decided by the first X.v
-            res[mode] = (ctx.Ax(v), ctx.Ax(2.5 * v), ctx.twin_state())
+            res[mode] = (ctx.Ax(v), ctx.Ax(2.5 * v), ctx.twin_state(), ctx.twin_stripes())
+    monkeypatch.delenv("GVB_TWIN_STRIPES")
     assert res["0"][2] == 0 and res["1"][2] == 1                     # really bypassed / really built
+    assert res["partial"][2] == 2 and res["partial"][3] == n_stripes // 3 and res["1"][3] == n_stripes
     assert np.array_equal(res["0"][0], res["1"][0]) and np.array_equal(res["0"][1], res["1"][1])
+    assert np.array_equal(res["0"][0], res["partial"][0]) and np.array_equal(res["0"][1], res["partial"][1])
     assert relerr(res["1"][0], ds.Ax(v)) < TOL_MATVEC
 
 

@@ -145,6 +145,7 @@ def test_cg_by_products_leave_the_outputs_unchanged(oracle, tmp_path, monkeypatc
     outs = {}
     for mode in ("0", "1"):
         monkeypatch.setenv("GVB_REFERENCE_SWEEPS", mode)
+        monkeypatch.setenv("GVB_LOG_SWEEPS", "1")      # the per-iteration sweep count is not a line of the reference's log
         (tmp_path / mode).mkdir()
         outd, log, iters = _run_case(oracle, tmp_path / mode, g, "lut")
         x1 = np.fromfile(outd + f"g_it_{iters}.bin")

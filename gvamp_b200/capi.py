@@ -84,6 +84,7 @@ SIGNATURES = {
     "gvb_missing_list_entries": (cl, [vp]),
     "gvb_twin_state": (ci, [vp]),
     "gvb_twin_stripes": (cl, [vp]),
+    "gvb_twin_release": (ci, [vp]),
     "gvb_snapshot_begin": (ci, [vp, vp, cl, ci]),
     "gvb_snapshot_wait": (ci, [vp, ci, ctypes.POINTER(c_f64p), ctypes.POINTER(cl)]),
     "gvb_assoc_pvals": (ci, [vp, vp, vp, vp, vp]),
@@ -457,6 +458,9 @@ class Context:
     def twin_state(self) -> int:
         """1: X.v walks the individual-major twin of the matrix, -1: no twin (too large / GVB_TWIN=0), 0: not decided yet"""
         return self.L.gvb_twin_state(self.h)
+
+    def twin_release(self):
+        _chk(self.L.gvb_twin_release(self.h))
 
     def twin_stripes(self) -> int:
         return self.L.gvb_twin_stripes(self.h)

@@ -46,18 +46,33 @@ extern "C" void gvb_divide_work(long Mt, int nranks, int rank, long* M, long* S)
     if (S) *S = start;
 }
 
+static std::vector<gvb_ctx*> g_live_ctx;   // every context of this process (one host thread drives the library, see the header)
+
+int gvb_release_twins(int device) {
+    int n = 0;
+    for (gvb_ctx* x : g_live_ctx) {
+        if (x->device != device || !x->bed_twin) continue;
+        cudaStreamSynchronize(x->stream);   // a sweep on the twin may still be running
+        gvb_twin_reset(x);
+        x->twin_state = -1;                 // not rebuilt: the memory is needed elsewhere
+        n++;
+    }
+    return n;
+}
+
 static int ctx_common_init(gvb_ctx* c) {
+    g_live_ctx.push_back(c);
     GVB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 8; i++) {
         GVB_CUDA(cudaEventCreate(&c->ev_start[i]));
         GVB_CUDA(cudaEventCreate(&c->ev_stop[i]));
     }
-    GVB_CUDA(cudaMalloc(&c->red_partial, sizeof(double) * GVB_RED_BLOCKS * GVB_RED_MAXK));
-    GVB_CUDA(cudaMalloc(&c->red_result, sizeof(double) * GVB_RED_MAXK));
+    GVB_CUDA(gvb_malloc(c, &c->red_partial, sizeof(double) * GVB_RED_BLOCKS * GVB_RED_MAXK));
+    GVB_CUDA(gvb_malloc(c, &c->red_result, sizeof(double) * GVB_RED_MAXK));
     GVB_CUDA(cudaMallocHost(&c->h_red, sizeof(double) * GVB_RED_MAXK));
-    GVB_CUDA(cudaMalloc(&c->scal, sizeof(double) * 64));
+    GVB_CUDA(gvb_malloc(c, &c->scal, sizeof(double) * 64));
     GVB_CUDA(cudaMemset(c->scal, 0, sizeof(double) * 64));
-    GVB_CUDA(cudaMalloc(&c->work_counter, sizeof(int) * 16));
+    GVB_CUDA(gvb_malloc(c, &c->work_counter, sizeof(int) * 16));
     GVB_CUDA(cudaMemset(c->work_counter, 0, sizeof(int) * 16));
     const char* gen = getenv("GVB_KERNELS");
     c->kernel_gen = (gen && !strcmp(gen, "simple")) ? 0 : ((gen && !strcmp(gen, "lut1")) ? 1 : 2);
@@ -116,6 +131,7 @@ extern "C" int gvb_ctx_create(gvb_ctx** out, int device, int rank, int nranks, c
 
 extern "C" void gvb_ctx_destroy(gvb_ctx* c) {
     if (!c) return;
+    g_live_ctx.erase(std::remove(g_live_ctx.begin(), g_live_ctx.end(), c), g_live_ctx.end());
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (gvb_vec_s* v : c->vecs) {
@@ -126,7 +142,7 @@ extern "C" void gvb_ctx_destroy(gvb_ctx* c) {
     fr(c->tmpN); fr(c->tmpN2); fr(c->tmpM); fr(c->tmpM2); fr(c->wv); fr(c->cv); fr(c->ax_partial);
     gvb_misslist_reset(c);
     gvb_twin_reset(c);
-    fr(c->tab_u); fr(c->tab_v); fr(c->acc_i64); fr(c->red_partial); fr(c->red_result); fr(c->scal); fr(c->work_counter);
+    fr(c->tab_u); fr(c->tab_v); fr(c->shift_u); fr(c->shift_v); fr(c->acc_i64); fr(c->red_partial); fr(c->red_result); fr(c->scal); fr(c->work_counter);
     if (c->h_red) cudaFreeHost(c->h_red);
     fr(c->cg_dev); fr(c->cg_flags);
     if (c->cg_host) cudaFreeHost(c->cg_host);
@@ -189,7 +205,7 @@ static int vec_alloc_cap(gvb_ctx* c, long n, long cap, gvb_vec* out) {
     gvb_vec_s* v = new gvb_vec_s();
     v->n = n;
     v->cap = cap;
-    cudaError_t e = cudaMalloc(&v->d, cap * sizeof(double));
+    cudaError_t e = gvb_malloc(c, &v->d, cap * sizeof(double));
     if (e != cudaSuccess) {
         delete v;
         gvb_set_error("cudaMalloc of a %ld-double vector failed: %s", cap, cudaGetErrorString(e));
@@ -249,7 +265,7 @@ extern "C" int gvb_snapshot_begin(gvb_ctx* c, gvb_vec src, long n, int slot) {
         if (sn.host) cudaFreeHost(sn.host);
         sn.dev = sn.host = nullptr;
         sn.cap = 0;
-        GVB_CUDA(cudaMalloc(&sn.dev, std::max(n, 1l) * sizeof(double)));
+        GVB_CUDA(gvb_malloc(c, &sn.dev, std::max(n, 1l) * sizeof(double)));
         GVB_CUDA(cudaMallocHost(&sn.host, std::max(n, 1l) * sizeof(double)));
         sn.cap = n;
     }

@@ -191,7 +191,7 @@ inline int cg_blocks(long n) { return (int)std::max(1l, std::min((n + 1023) / 10
 
 int ensure_cg_state(gvb_ctx* c, int max_iter) {
     if (!c->cg_flags) {
-        GVB_CUDA(cudaMalloc(&c->cg_flags, 4 * sizeof(int)));
+        GVB_CUDA(gvb_malloc(c, &c->cg_flags, 4 * sizeof(int)));
         GVB_CUDA(cudaMemsetAsync(c->cg_flags, 0, 4 * sizeof(int), c->stream));
         for (int k = 0; k < 4; k++) GVB_CUDA(cudaEventCreateWithFlags(&c->cg_ev[k], cudaEventDisableTiming));
     }
@@ -201,7 +201,7 @@ int ensure_cg_state(gvb_ctx* c, int max_iter) {
         c->cg_dev = nullptr;
         c->cg_host = nullptr;
         c->cg_log_cap = 0;
-        GVB_CUDA(cudaMalloc(&c->cg_dev, (GVB_CG_NSCAL + 4 * (size_t)cap) * sizeof(double)));
+        GVB_CUDA(gvb_malloc(c, &c->cg_dev, (GVB_CG_NSCAL + 4 * (size_t)cap) * sizeof(double)));
         GVB_CUDA(cudaMallocHost(&c->cg_host, (5 * GVB_CG_NSCAL + 4 * (size_t)cap) * sizeof(double)));
         GVB_CUDA(cudaMemsetAsync(c->cg_dev, 0, (GVB_CG_NSCAL + 4 * (size_t)cap) * sizeof(double), c->stream));
         c->cg_log_cap = cap;

@@ -97,6 +97,9 @@ struct gvb_ctx {
     size_t tab_u_cap = 0;
     int32_t* tab_v = nullptr;       // per-marker-group tables for X.v
     size_t tab_v_cap = 0;
+    int* shift_u = nullptr;         // per stripe: left shift of its table's int32 windows (scale classes, matvec_tile.cu)
+    int* shift_v = nullptr;         // per marker tile, likewise
+    size_t shift_cap = 0;
     unsigned long long* acc_i64 = nullptr;  // fixed-point accumulators
     size_t acc_i64_cap = 0;
     int* work_counter = nullptr;
@@ -181,6 +184,22 @@ void gvb_set_error(const char* fmt, ...);
     } while (0)
 
 static inline long gvb_roundup(long x, long m) { return (x + m - 1) / m * m; }
+
+// Frees every individual-major twin held on `device` (the one optional, re-creatable consumer of HBM: X.v then gathers from the one
+// matrix, bit-identical results); returns the number of twins released.  capi.cu keeps the registry of live contexts.
+int gvb_release_twins(int device);
+
+// cudaMalloc that gives the twins back before it gives up: a later allocation (a second matrix in run mode `both`, the scratch of the
+// association tests, solver vectors) must not fail because spare HBM was spent on the optional second orientation.
+template <typename T>
+static inline cudaError_t gvb_malloc(gvb_ctx* c, T** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation && gvb_release_twins(c->device) > 0) {
+        cudaGetLastError();
+        e = cudaMalloc(p, bytes);
+    }
+    return e;
+}
 
 // ---- internal entry points (implemented across the .cu files) ----
 int gvb_layout_alloc(gvb_ctx* c, long N, long Mt, long S, long M);

@@ -105,6 +105,7 @@ static void free_layout(gvb_ctx* c) {
     fr(c->ax_partial); c->ax_partial_cap = 0;
     fr(c->tab_u); c->tab_u_cap = 0;
     fr(c->tab_v); c->tab_v_cap = 0;
+    fr(c->shift_u); fr(c->shift_v); c->shift_cap = 0;
     fr(c->acc_i64); c->acc_i64_cap = 0;
     gvb_misslist_reset(c);
     gvb_twin_reset(c);
@@ -125,7 +126,7 @@ int gvb_layout_alloc(gvb_ctx* c, long N, long Mt, long S, long M) {
     c->bed_words = (size_t)c->n_stripes * (size_t)c->Mg_pad * 32;
     // 64 KB of slack behind the last stripe: the X^T.u kernel's last marker block may read past Mg_pad
     const size_t slack_words = 16384;
-    cudaError_t e = cudaMalloc(&c->bed, (c->bed_words + slack_words) * sizeof(uint32_t));
+    cudaError_t e = gvb_malloc(c, &c->bed, (c->bed_words + slack_words) * sizeof(uint32_t));
     if (e != cudaSuccess) {
         gvb_set_error("cannot allocate %.3f GB of HBM for the packed genotype matrix: %s", c->bed_words * 4.0 / 1e9, cudaGetErrorString(e));
         return GVB_ERR_NOMEM;
@@ -133,17 +134,17 @@ int gvb_layout_alloc(gvb_ctx* c, long N, long Mt, long S, long M) {
     GVB_CUDA(cudaMemsetAsync(c->bed, 0x55, (c->bed_words + slack_words) * sizeof(uint32_t), c->stream));
     size_t npos = (size_t)c->n_stripes * 32;
     size_t mp = (size_t)c->Mg_pad * 4;
-    GVB_CUDA(cudaMalloc(&c->maskw, npos * 4));
-    GVB_CUDA(cudaMalloc(&c->validw, npos * 4));
-    GVB_CUDA(cudaMalloc(&c->mave, mp * 8));
-    GVB_CUDA(cudaMalloc(&c->msig, mp * 8));
-    GVB_CUDA(cudaMalloc(&c->counts, mp * 8 * sizeof(int64_t)));
-    GVB_CUDA(cudaMalloc(&c->tmpN, c->Npad * 8));
-    GVB_CUDA(cudaMalloc(&c->tmpN2, c->Npad * 8));
-    GVB_CUDA(cudaMalloc(&c->tmpM, mp * 8));
-    GVB_CUDA(cudaMalloc(&c->tmpM2, mp * 8));
-    GVB_CUDA(cudaMalloc(&c->wv, mp * 8));
-    GVB_CUDA(cudaMalloc(&c->cv, mp * 8));
+    GVB_CUDA(gvb_malloc(c, &c->maskw, npos * 4));
+    GVB_CUDA(gvb_malloc(c, &c->validw, npos * 4));
+    GVB_CUDA(gvb_malloc(c, &c->mave, mp * 8));
+    GVB_CUDA(gvb_malloc(c, &c->msig, mp * 8));
+    GVB_CUDA(gvb_malloc(c, &c->counts, mp * 8 * sizeof(int64_t)));
+    GVB_CUDA(gvb_malloc(c, &c->tmpN, c->Npad * 8));
+    GVB_CUDA(gvb_malloc(c, &c->tmpN2, c->Npad * 8));
+    GVB_CUDA(gvb_malloc(c, &c->tmpM, mp * 8));
+    GVB_CUDA(gvb_malloc(c, &c->tmpM2, mp * 8));
+    GVB_CUDA(gvb_malloc(c, &c->wv, mp * 8));
+    GVB_CUDA(gvb_malloc(c, &c->cv, mp * 8));
     GVB_CUDA(cudaMemsetAsync(c->mave, 0, mp * 8, c->stream));
     GVB_CUDA(cudaMemsetAsync(c->msig, 0, mp * 8, c->stream));
     GVB_CUDA(cudaMemsetAsync(c->tmpN, 0, c->Npad * 8, c->stream));
@@ -176,7 +177,7 @@ extern "C" int gvb_bed_load_host(gvb_ctx* c, const uint8_t* bed, long N, long Mt
     GVB_CHECK(gvb_layout_alloc(c, N, Mt, S, M));
     long cm = chunk_markers(c);
     uint8_t* d_stage = nullptr;
-    GVB_CUDA(cudaMalloc(&d_stage, (size_t)cm * c->mbytes));
+    GVB_CUDA(gvb_malloc(c, &d_stage, (size_t)cm * c->mbytes));
     for (long j0 = 0; j0 < M; j0 += cm) {
         long n = std::min(cm, M - j0);
         GVB_CUDA(cudaMemcpyAsync(d_stage, bed + (size_t)j0 * c->mbytes, (size_t)n * c->mbytes, cudaMemcpyHostToDevice, c->stream));
@@ -203,7 +204,7 @@ extern "C" int gvb_bed_load_file(gvb_ctx* c, const char* path, long N, long Mt, 
     uint8_t* d_stage[2] = {nullptr, nullptr};
     cudaEvent_t done[2];
     for (int b = 0; b < 2; b++) {
-        if (cudaMallocHost(&h_stage[b], chunk_bytes) != cudaSuccess || cudaMalloc(&d_stage[b], chunk_bytes) != cudaSuccess) {
+        if (cudaMallocHost(&h_stage[b], chunk_bytes) != cudaSuccess || gvb_malloc(c, &d_stage[b], chunk_bytes) != cudaSuccess) {
             gvb_set_error("cannot allocate staging buffers for the bed upload");
             close(fd);
             return GVB_ERR_NOMEM;
@@ -257,7 +258,7 @@ extern "C" int gvb_bed_decode(gvb_ctx* c, long j0, long n, uint8_t* out) {
     GVB_ARG(j0 >= 0 && n > 0 && j0 + n <= c->M, "marker range");
     uint8_t* d_out = nullptr;
     size_t bytes = (size_t)n * c->mbytes;
-    GVB_CUDA(cudaMalloc(&d_out, bytes));
+    GVB_CUDA(gvb_malloc(c, &d_out, bytes));
     int threads = 256;
     long blocks = ((long)bytes + threads - 1) / threads;
     decode_kernel<<<(unsigned)blocks, threads, 0, c->stream>>>(c->bed, c->Mg_pad, c->mbytes, j0, n, d_out);

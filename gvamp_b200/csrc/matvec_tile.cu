@@ -213,7 +213,8 @@ __device__ __forceinline__ void ax_consume(const char* __restrict__ tabc, uint32
 template <int NW, int NS, int MADK, bool TW>
 __global__ void __launch_bounds__(NW * 32 + 32, 1)
 ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, long Mg_pad, long stripe0, long n_stripes, int n_sblocks, int n_gchunks,
-               int tiles_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out, int one, const int* __restrict__ skip) {
+               int tiles_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out, int one, const int* __restrict__ skip,
+               const int* __restrict__ shifts) {
     if (skip && *skip) return;   // device-side predicate of a speculatively enqueued CG iteration (cg.cu): uniform over the grid
     extern __shared__ __align__(1024) char smem[];
     __shared__ int s_item;
@@ -279,6 +280,7 @@ ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, l
     if (i0 + B < nt) {                                                                       \
         const int i = i0 + B;                                                                \
         issue_bed(i + NS - 1); /* its stage was consumed in step i-1 by this same warp */    \
+        const int sh = __ldg(shifts + tile_lo + i); /* scale class of this table tile */     \
         mbar_wait(tp.full + 8 * B, tp.fills<B>() & 1); /* table i has landed */              \
         tp.fills<B>()++;                                                                     \
         if (active) {                                                                        \
@@ -287,7 +289,7 @@ ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, l
             n_use++;                                                                         \
             int a32[4] = {0, 0, 0, 0};                                                       \
             ax_consume<B, MADK, TW>(smem, bed_sm + s * TILE_BYTES + lane_off, spack, one, a32); \
-            _Pragma("unroll") for (int k = 0; k < 4; k++) acc64[k] += (long long)a32[k];     \
+            _Pragma("unroll") for (int k = 0; k < 4; k++) acc64[k] += (long long)a32[k] << sh; \
         }                                                                                    \
         __syncwarp();                                                                        \
         if (lane == 0) mbar_arrive(tp.empty + 8 * B); /* this warp has left table buffer B */ \
@@ -330,7 +332,8 @@ __device__ __forceinline__ void atx_consume(const char* __restrict__ tabc, uint3
 template <int NW, int NS, bool USE_MAD, int MODE>
 __global__ void __launch_bounds__(NW * 32 + 32, 1)
 atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, long Mg_pad, long n_stripes, int n_gblocks, int n_schunks,
-                int stripes_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out, int one, const int* __restrict__ skip) {
+                int stripes_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out, int one, const int* __restrict__ skip,
+                const int* __restrict__ shifts) {
     if (skip && *skip) return;
     extern __shared__ __align__(1024) char smem[];
     __shared__ int s_item;
@@ -394,6 +397,7 @@ atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
     if (i0 + B < ns) {                                                                         \
         const int i = i0 + B;                                                                  \
         issue_bed(i + NS - 1);                                                                 \
+        const int sh = (MODE == 0 && shifts) ? __ldg(shifts + t_lo + i) : 0; /* scale class of this stripe's table */ \
         mbar_wait(tp.full + 8 * B, tp.fills<B>() & 1);                                         \
         tp.fills<B>()++;                                                                       \
         if (active) {                                                                          \
@@ -404,7 +408,7 @@ atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
             atx_consume<B, USE_MAD>(smem, bed_sm + s * TILE_BYTES + lane_off, spack, one, a32); \
             _Pragma("unroll") for (int q = 0; q < 4; q++) {                                    \
                 if (MODE == 0) {                                                               \
-                    acc64[q] += (long long)a32[q];                                             \
+                    acc64[q] += (long long)a32[q] << sh;                                       \
                 } else {                                                                       \
                     const unsigned a = (unsigned)a32[q];                                       \
                     acc64[q] += (long long)((unsigned long long)(a & 0x3FFu) | ((unsigned long long)((a >> 10) & 0x3FFu) << 21) | \
@@ -470,13 +474,13 @@ int launch_ax(gvb_ctx* c, unsigned long long* accN, long stripe0, long n_stripes
     int n_gchunks = (int)((n_tiles + tpc - 1) / tpc);
     int grid = std::min(n_sblocks * n_gchunks, c->sm_count);
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(TW ? c->bed_twin : c->bed, c->tab_v, c->Mg_pad, stripe0, n_stripes, n_sblocks, n_gchunks, tpc, c->work_counter,
-                                                       accN, 1, c->skip);
+                                                       accN, 1, c->skip, c->shift_v);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }
 
 template <int NW, int NS, bool USE_MAD, int MODE>
-int launch_atx(gvb_ctx* c, const int* tab, unsigned long long* acc) {
+int launch_atx(gvb_ctx* c, const int* tab, unsigned long long* acc, const int* shifts) {
     using Cfg = TileCfg<NW, NS>;
     auto kern = atx_tile_kernel<NW, NS, USE_MAD, MODE>;
     static unsigned long long attr_done = 0;   // one bit per device: the attribute is per device, a process may hold several contexts
@@ -489,7 +493,7 @@ int launch_atx(gvb_ctx* c, const int* tab, unsigned long long* acc) {
     const int spc = pick_chunk(tune().atx_stripes_per_chunk, n_gblocks, c->n_stripes, c->sm_count);
     int n_schunks = (int)((c->n_stripes + spc - 1) / spc);
     int grid = std::min(n_gblocks * n_schunks, c->sm_count);
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(c->bed, tab, c->Mg_pad, c->n_stripes, n_gblocks, n_schunks, spc, c->work_counter, acc, 1, c->skip);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(c->bed, tab, c->Mg_pad, c->n_stripes, n_gblocks, n_schunks, spc, c->work_counter, acc, 1, c->skip, shifts);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }
@@ -504,6 +508,16 @@ int launch_atx(gvb_ctx* c, const int* tab, unsigned long long* acc) {
 // [10] / [11]: 1.0 when the input vector of the running X^T.u / X.v sweep holds a NaN or an infinity.  The reference's FP64 sums then
 // turn every output into NaN (0 * NaN in the LUT products of data.cpp:766 / :975); fixed point cannot carry a NaN, so the
 // sweep carries this flag from its build kernel to its finish kernel instead.
+// Scale classes.  One global power-of-two scale makes the resolution of EVERY table entry that of the largest one: a single outlier
+// in u (or one tile of 128 clustered large effects in v) would cost all other entries its magnitude in precision.  The build
+// kernels therefore give every stripe (X^T.u) / marker tile (X.v) its own class k in {0, 1, 2} from its OWN magnitude bound b:
+// k = 2 if b <= B 2^-12, 1 if b <= B 2^-6, else 0 (B = the global bound), and quantise it with scale_0 * 2^(6k) -- the int32 window
+// stays safe because b * 2^(6k) <= B.  A step of the walk covers exactly one stripe / tile, so the main kernels flush their int32
+// window into the int64 accumulator shifted left by (12 - 6k): everything is summed at the finest scale scale_0 * 2^12, still exact
+// integer arithmetic, at the cost of one shift per 32 lookups.  Vectors without outliers fall into class 0 throughout and give the
+// bits of the single-scale form.  Head room: |window| < 2^31, shift <= 12, <= 2^16 steps per output -> |sum| < 2^59.
+#define GVB_CLASS_BITS 6
+#define GVB_CLASS_MAX 2
 #define SCAL_ATX_BOUND 8
 #define SCAL_AX_BOUND 9
 #define SCAL_ATX_BAD 10
@@ -520,6 +534,14 @@ __device__ __forceinline__ double scale_for(double bound, double window, double 
         s = ldexp(1.0, e);
     }
     return s;
+}
+
+// class of a stripe / tile with magnitude bound b under the global bound B (see "Scale classes")
+__device__ __forceinline__ int scale_class(double b, double B) {
+    if (!(B > 0.0) || !isfinite(B)) return 0;
+    if (b <= ldexp(B, -2 * GVB_CLASS_BITS)) return 2;
+    if (b <= ldexp(B, -GVB_CLASS_BITS)) return 1;
+    return 0;
 }
 
 __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
@@ -567,27 +589,41 @@ __global__ void __launch_bounds__(128) ax_prep_kernel(const double* __restrict__
 // pass 2 (one block per marker tile): tabv[(T*256 + e)*32 + s] = sum_q Q_{4g+q}(c_q(e)), g = 32 T + s,
 // Q_j(c) = rint(val_j(c) * scale), val_j(00) = (2-mu) w, val_j(10) = (1-mu) w, val_j(11) = -mu w, val_j(missing) = 0
 __global__ void __launch_bounds__(256) ax_build_kernel(const double* __restrict__ v, const double* __restrict__ mave, const double* __restrict__ msig,
-                                                       double* __restrict__ scal, int* __restrict__ tabv, int mode, const int* __restrict__ skip) {
+                                                       double* __restrict__ scal, int* __restrict__ tabv, int mode, const int* __restrict__ skip,
+                                                       int* __restrict__ shifts) {
     if (skip && *skip) return;
     __shared__ int Qs[4][4][32];   // [q][code][slot]: a warp reads one (q, code) row -> conflict free
     __shared__ double s_scale;
+    __shared__ double s_e[4];
     const long T = blockIdx.x;
+    double v00 = 0.0, v10 = 0.0, v11 = 0.0;
+    if (threadIdx.x < 128) {       // this tile's own bound: sum_j max_c |val_j(c)|, the same sum ax_prep_kernel maximised over the tiles
+        const long j = T * 128 + threadIdx.x;
+        ax_code_values(mode, v ? v[j] : 1.0, mave[j], msig[j], v00, v10, v11);
+        double e = fmax(fmax(fabs(v00), fabs(v11)), fabs(v10));
+        if (!isfinite(v00 + v10 + v11)) e = INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        if ((threadIdx.x & 31) == 0) s_e[threadIdx.x >> 5] = e;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        const double sc = scale_for(scal[SCAL_AX_BOUND], 1.0, 64.0 + 1.0);
-        s_scale = sc;
+        const double B = scal[SCAL_AX_BOUND];
+        const double sc0 = scale_for(B, 1.0, 64.0 + 1.0);
+        const int k = scale_class(s_e[0] + s_e[1] + s_e[2] + s_e[3], B);
+        s_scale = ldexp(sc0, GVB_CLASS_BITS * k);
+        shifts[T] = GVB_CLASS_BITS * (GVB_CLASS_MAX - k);
         if (T == 0) {
-            scal[2] = sc;
-            scal[3] = 1.0 / sc;
-            scal[SCAL_AX_BAD] = isfinite(scal[SCAL_AX_BOUND]) ? 0.0 : 1.0;
+            const double fine = ldexp(sc0, GVB_CLASS_BITS * GVB_CLASS_MAX);   // the scale everything is summed at
+            scal[2] = fine;
+            scal[3] = 1.0 / fine;
+            scal[SCAL_AX_BAD] = isfinite(B) ? 0.0 : 1.0;
         }
     }
     __syncthreads();
     if (threadIdx.x < 128) {
-        const long j = T * 128 + threadIdx.x;
         const int s = threadIdx.x >> 2, q = threadIdx.x & 3;
         const double sc = s_scale;
-        double v00, v10, v11;
-        ax_code_values(mode, v ? v[j] : 1.0, mave[j], msig[j], v00, v10, v11);
         Qs[q][0][s] = (int)rint(v00 * sc);
         Qs[q][1][s] = 0;
         Qs[q][2][s] = (int)rint(v10 * sc);
@@ -638,29 +674,48 @@ __global__ void __launch_bounds__(256) atx_prep_kernel(const double* __restrict_
 // pass 2 (one block per stripe): tab[(t*256 + B)*32 + l] = sum_k a(code_k(B)) U_{4p+k}, p = 32 t + l, U = rint(u * scale);
 // tabm (shards with missing genotypes) holds the same sum over the MISSING codes with weight 1; accumulates sum_i U_i
 __global__ void __launch_bounds__(256) atx_build_kernel(const double* __restrict__ u, double window, double* __restrict__ scal, int* __restrict__ tab,
-                                                        int* __restrict__ tabm, long long* __restrict__ usum, int* __restrict__ uq, const int* __restrict__ skip) {
+                                                        int* __restrict__ tabm, long long* __restrict__ usum, int* __restrict__ uq, const int* __restrict__ skip,
+                                                        int* __restrict__ shifts) {
     if (skip && *skip) return;
     __shared__ int Us[4][32];   // [k][position]
-    __shared__ double s_scale;
+    __shared__ double s_scale, s_scale0;
+    __shared__ int s_shift;
     const long t = blockIdx.x;
-    if (threadIdx.x == 0) {
-        const double sc = scale_for(scal[SCAL_ATX_BOUND], window, 4.0);
-        s_scale = sc;
-        if (t == 0) {
-            scal[0] = sc;
-            scal[1] = 1.0 / sc;
-            scal[SCAL_ATX_BAD] = isfinite(scal[SCAL_ATX_BOUND]) ? 0.0 : 1.0;
+    double ui = 0.0;
+    if (threadIdx.x < 128) ui = u[t * 128 + threadIdx.x];
+    if (threadIdx.x < 32) {       // this stripe's own bound: max over its 32 positions of 2 (|u_4p| + ... + |u_4p+3|), as atx_prep_kernel
+        const double2* up = reinterpret_cast<const double2*>(u + t * 128 + 4 * threadIdx.x);
+        const double2 a = up[0], b = up[1];
+        double m = 2.0 * (fabs(a.x) + fabs(a.y) + fabs(b.x) + fabs(b.y));
+        if (!isfinite(m)) m = INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) {
+            const double B = scal[SCAL_ATX_BOUND];
+            const double sc0 = scale_for(B, window, 4.0);
+            const int k = scale_class(m, B);
+            s_scale0 = sc0;
+            s_scale = ldexp(sc0, GVB_CLASS_BITS * k);
+            s_shift = GVB_CLASS_BITS * (GVB_CLASS_MAX - k);
+            shifts[t] = s_shift;
+            if (t == 0) {
+                const double fine = ldexp(sc0, GVB_CLASS_BITS * GVB_CLASS_MAX);   // the scale everything is summed at
+                scal[0] = fine;
+                scal[1] = 1.0 / fine;
+                scal[SCAL_ATX_BAD] = isfinite(B) ? 0.0 : 1.0;
+            }
         }
     }
     __syncthreads();
     if (threadIdx.x < 128) {
-        const int Ui = (int)rint(u[t * 128 + threadIdx.x] * s_scale);
+        const int Ui = (int)rint(ui * s_scale);
         Us[threadIdx.x & 3][threadIdx.x >> 2] = Ui;
-        if (uq) uq[t * 128 + threadIdx.x] = Ui;   // the gather of misslist.cu reads the same integers
+        // the gather of misslist.cu sums U's of MANY stripes in one int32 window: it keeps the common class-0 scale
+        if (uq) uq[t * 128 + threadIdx.x] = (int)rint(ui * s_scale0);
         long long ls = Ui;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
-        if ((threadIdx.x & 31) == 0 && ls != 0) atomicAdd(reinterpret_cast<unsigned long long*>(usum), (unsigned long long)ls);
+        if ((threadIdx.x & 31) == 0 && ls != 0) atomicAdd(reinterpret_cast<unsigned long long*>(usum), (unsigned long long)(ls << s_shift));
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -678,7 +733,7 @@ __global__ void __launch_bounds__(256) atx_build_kernel(const double* __restrict
 // out[j] = sigma_j * (A_j - mu_j * B_j) / scale / sqrt(N),  B_j = sum_i U_i - sum_{i missing in j} U_i
 __global__ void atx_finish_kernel(const unsigned long long* __restrict__ acc, const unsigned long long* __restrict__ accm, const long long* __restrict__ usum,
                                   double* __restrict__ scal, const double* __restrict__ mave, const double* __restrict__ msig, long Mpad, long M,
-                                  double inv_sqrt_n, double* __restrict__ out, double* __restrict__ outB, const int* __restrict__ skip) {
+                                  double inv_sqrt_n, double* __restrict__ out, double* __restrict__ outB, const int* __restrict__ skip, int accm_shift) {
     if (skip && *skip) return;
     long j = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (j == 0) scal[SCAL_ATX_BOUND] = 0.0;
@@ -690,7 +745,7 @@ __global__ void atx_finish_kernel(const unsigned long long* __restrict__ acc, co
         return;
     }
     long long A = (long long)acc[j];
-    long long Bs = *usum - (accm ? (long long)accm[j] : 0ll);
+    long long Bs = *usum - (accm ? ((long long)accm[j] << accm_shift) : 0ll);   // the list's gather sums at the class-0 scale
     double inv_s = scal[1];
     out[j] = msig[j] * ((double)A * inv_s - mave[j] * ((double)Bs * inv_s)) * inv_sqrt_n;
     if (outB) outB[j] = (double)Bs * inv_s;   // sum_i b_ij u_i on its own (association tests, assoc.cu)
@@ -702,7 +757,7 @@ int ensure_scratch(gvb_ctx* c, bool need_tab_u, bool need_tab_v, bool miss) {
         if (c->tab_u_cap < tab_ints) {
             if (c->tab_u) cudaFree(c->tab_u);
             c->tab_u = nullptr;
-            GVB_CUDA(cudaMalloc(&c->tab_u, tab_ints * sizeof(int)));
+            GVB_CUDA(gvb_malloc(c, &c->tab_u, tab_ints * sizeof(int)));
             c->tab_u_cap = tab_ints;
         }
     }
@@ -711,15 +766,24 @@ int ensure_scratch(gvb_ctx* c, bool need_tab_u, bool need_tab_v, bool miss) {
         if (c->tab_v_cap < tab_ints) {
             if (c->tab_v) cudaFree(c->tab_v);
             c->tab_v = nullptr;
-            GVB_CUDA(cudaMalloc(&c->tab_v, tab_ints * sizeof(int)));
+            GVB_CUDA(gvb_malloc(c, &c->tab_v, tab_ints * sizeof(int)));
             c->tab_v_cap = tab_ints;
         }
+    }
+    const size_t shift_need = (size_t)std::max(c->n_stripes, c->Mg_pad / 32);
+    if (c->shift_cap < shift_need) {
+        if (c->shift_u) cudaFree(c->shift_u);
+        if (c->shift_v) cudaFree(c->shift_v);
+        c->shift_u = c->shift_v = nullptr;
+        GVB_CUDA(gvb_malloc(c, &c->shift_u, shift_need * sizeof(int)));
+        GVB_CUDA(gvb_malloc(c, &c->shift_v, shift_need * sizeof(int)));
+        c->shift_cap = shift_need;
     }
     const size_t acc_need = 2 * (size_t)c->Mg_pad * 4 + (size_t)c->Npad + 8;
     if (c->acc_i64_cap < acc_need) {
         if (c->acc_i64) cudaFree(c->acc_i64);
         c->acc_i64 = nullptr;
-        GVB_CUDA(cudaMalloc(&c->acc_i64, acc_need * sizeof(unsigned long long)));
+        GVB_CUDA(gvb_malloc(c, &c->acc_i64, acc_need * sizeof(unsigned long long)));
         c->acc_i64_cap = acc_need;
     }
     return GVB_OK;
@@ -755,8 +819,8 @@ int ax_main(gvb_ctx* c, unsigned long long* accN) {
 
 int atx_main(gvb_ctx* c, const int* tab, unsigned long long* acc) {
     const TileTune t = tune();
-    if (t.variant == 1) return t.use_mad >= 4 ? launch_atx<12, 3, true, 0>(c, tab, acc) : launch_atx<12, 3, false, 0>(c, tab, acc);
-    return t.use_mad >= 4 ? launch_atx<15, 2, true, 0>(c, tab, acc) : launch_atx<15, 2, false, 0>(c, tab, acc);
+    if (t.variant == 1) return t.use_mad >= 4 ? launch_atx<12, 3, true, 0>(c, tab, acc, c->shift_u) : launch_atx<12, 3, false, 0>(c, tab, acc, c->shift_u);
+    return t.use_mad >= 4 ? launch_atx<15, 2, true, 0>(c, tab, acc, c->shift_u) : launch_atx<15, 2, false, 0>(c, tab, acc, c->shift_u);
 }
 
 }   // namespace
@@ -769,7 +833,7 @@ int gvb_ax_tile(gvb_ctx* c, const double* v, double* out, int mode) {
     unsigned long long* accN = c->acc_i64 + 2 * (size_t)c->Mg_pad * 4;
     ax_prep_kernel<<<(unsigned)n_tiles, 128, 0, c->stream>>>(v, c->mave, c->msig, c->scal, accN, c->Npad, mode, c->skip);
     GVB_LAUNCHED(c);
-    ax_build_kernel<<<(unsigned)n_tiles, 256, 0, c->stream>>>(v, c->mave, c->msig, c->scal, c->tab_v, mode, c->skip);
+    ax_build_kernel<<<(unsigned)n_tiles, 256, 0, c->stream>>>(v, c->mave, c->msig, c->scal, c->tab_v, mode, c->skip, c->shift_v);
     GVB_LAUNCHED(c);
     GVB_CHECK(ax_main(c, accN));
     ax_finish_kernel<<<(unsigned)((c->Npad + 255) / 256), 256, 0, c->stream>>>(accN, c->scal, c->maskw, c->Npad,
@@ -795,7 +859,7 @@ int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB) {
     atx_prep_kernel<<<nb, 256, 0, c->stream>>>(u, npos, c->scal, acc, (long)((miss ? 2 : 1) * Mpad), usum, c->skip);
     GVB_LAUNCHED(c);
     atx_build_kernel<<<(unsigned)c->n_stripes, 256, 0, c->stream>>>(u, 32.0, c->scal, c->tab_u, (miss && !list) ? c->tab_u + total : nullptr, usum,
-                                                                    list ? c->uq : nullptr, c->skip);
+                                                                    list ? c->uq : nullptr, c->skip, c->shift_u);
     GVB_LAUNCHED(c);
     GVB_CHECK(atx_main(c, c->tab_u, acc));
     if (list)
@@ -803,7 +867,7 @@ int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB) {
     else if (miss)
         GVB_CHECK(atx_main(c, c->tab_u + total, accm));
     atx_finish_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, c->stream>>>(acc, miss ? accm : nullptr, usum, c->scal, c->mave, c->msig, (long)Mpad, c->M,
-                                                                             1.0 / sqrt((double)c->N), out, outB, c->skip);
+                                                                             1.0 / sqrt((double)c->N), out, outB, c->skip, list ? GVB_CLASS_BITS * GVB_CLASS_MAX : 0);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }
@@ -811,6 +875,6 @@ int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB) {
 // the table walk of X^T.u with packed counters (MODE 1): acc[j] = n00 | n10 << 21 | n11 << 42 over the individuals the table weights
 int gvb_count_tile_main(gvb_ctx* c, const int* tab, unsigned long long* acc) {
     const TileTune t = tune();
-    if (t.variant == 1) return launch_atx<12, 3, false, 1>(c, tab, acc);
-    return launch_atx<15, 2, false, 1>(c, tab, acc);
+    if (t.variant == 1) return launch_atx<12, 3, false, 1>(c, tab, acc, nullptr);
+    return launch_atx<15, 2, false, 1>(c, tab, acc, nullptr);
 }

@@ -94,7 +94,7 @@ static int counts_tile_run(gvb_ctx* c) {
     if (c->tab_u_cap < tab_ints) {
         if (c->tab_u) cudaFree(c->tab_u);
         c->tab_u = nullptr;
-        GVB_CUDA(cudaMalloc(&c->tab_u, tab_ints * sizeof(int)));
+        GVB_CUDA(gvb_malloc(c, &c->tab_u, tab_ints * sizeof(int)));
         c->tab_u_cap = tab_ints;
     }
     const size_t Mpad = (size_t)c->Mg_pad * 4;
@@ -102,7 +102,7 @@ static int counts_tile_run(gvb_ctx* c) {
     if (c->acc_i64_cap < acc_need) {
         if (c->acc_i64) cudaFree(c->acc_i64);
         c->acc_i64 = nullptr;
-        GVB_CUDA(cudaMalloc(&c->acc_i64, acc_need * sizeof(unsigned long long)));
+        GVB_CUDA(gvb_malloc(c, &c->acc_i64, acc_need * sizeof(unsigned long long)));
         c->acc_i64_cap = acc_need;
     }
     // no phenotype NAs: the masked and the unmasked counts coincide and one walk serves both

@@ -92,4 +92,12 @@ int gvb_twin_build(gvb_ctx* c) {
 }
 
 extern "C" int gvb_twin_state(gvb_ctx* c) { return c ? c->twin_state : 0; }
+extern "C" int gvb_twin_release(gvb_ctx* c) {
+    GVB_ARG(c, "ctx");
+    GVB_CUDA(cudaStreamSynchronize(c->stream));
+    const bool had = c->bed_twin != nullptr;
+    gvb_twin_reset(c);
+    if (had) c->twin_state = -1;
+    return GVB_OK;
+}
 extern "C" long gvb_twin_stripes(gvb_ctx* c) { return c ? c->twin_stripes : 0; }

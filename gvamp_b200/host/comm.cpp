@@ -39,6 +39,16 @@ static std::string rendezvous_path() {
     return buf;
 }
 
+static std::string g_rdzv_file;
+
+// rank 0: the id has been consumed by every rank once the NCCL communicator exists (ncclCommInitRank returns on all ranks together)
+void rendezvous_done() {
+    if (!g_rdzv_file.empty()) {
+        unlink(g_rdzv_file.c_str());
+        g_rdzv_file.clear();
+    }
+}
+
 Comm& world() {
     static Comm c;
     static bool init = false;
@@ -49,30 +59,41 @@ Comm& world() {
     c.local_rank = env_int("GVB_LOCAL_RANK", "LOCAL_RANK", c.rank);
     if (c.nranks <= 1) { c.rank = 0; c.nranks = 1; return c; }
     if (id_from_hex(getenv("GVB_NCCL_ID"), c.nccl_id)) { c.have_id = true; return c; }
-    // rendezvous through a file next to the launcher: rank 0 publishes, the others wait for a file
-    // that is not older than this process
+    // Rendezvous through a file (SINGLE NODE: the name is built from the launcher's pid and the master port; a multi-node launch passes
+    // GVB_NCCL_ID instead).  The payload is the 128-byte id followed by rank 0's wall-clock start time, so that a file left behind by
+    // an earlier run under the same launcher can never be taken for this run's; rank 0 replaces any such file (unlink, then O_EXCL |
+    // O_NOFOLLOW: no symlink in a shared /tmp is followed) and removes its own once the communicator exists (rendezvous_done()).
     std::string path = rendezvous_path();
-    time_t started = time(nullptr);
+    struct timespec now;
+    clock_gettime(CLOCK_REALTIME, &now);
+    const long long started = (long long)now.tv_sec;
     if (c.rank == 0) {
         if (gvb_nccl_unique_id(c.nccl_id) != GVB_OK) {
             std::cout << "FATAL: cannot create a NCCL unique id: " << gvb_last_error() << std::endl;
             exit(EXIT_FAILURE);
         }
         std::string tmp = path + ".tmp";
-        int fd = open(tmp.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0600);
-        if (fd < 0 || write(fd, c.nccl_id, 128) != 128) {
+        unlink(tmp.c_str());
+        unlink(path.c_str());
+        int fd = open(tmp.c_str(), O_CREAT | O_EXCL | O_NOFOLLOW | O_WRONLY, 0600);
+        if (fd < 0 || write(fd, c.nccl_id, 128) != 128 || write(fd, &started, sizeof(started)) != (ssize_t)sizeof(started)) {
             std::cout << "FATAL: cannot write the rendezvous file " << tmp << std::endl;
             exit(EXIT_FAILURE);
         }
         close(fd);
         rename(tmp.c_str(), path.c_str());
+        g_rdzv_file = path;
+        atexit(rendezvous_done);
     } else {
         for (int tries = 0;; tries++) {
-            struct stat st;
-            if (stat(path.c_str(), &st) == 0 && st.st_size == 128 && st.st_mtime + 2 >= started) {
-                int fd = open(path.c_str(), O_RDONLY);
-                if (fd >= 0 && read(fd, c.nccl_id, 128) == 128) { close(fd); break; }
-                if (fd >= 0) close(fd);
+            int fd = open(path.c_str(), O_RDONLY | O_NOFOLLOW);
+            if (fd >= 0) {
+                long long stamp = 0;
+                const bool ok = read(fd, c.nccl_id, 128) == 128 && read(fd, &stamp, sizeof(stamp)) == (ssize_t)sizeof(stamp);
+                close(fd);
+                // the ranks of one launch start within seconds of each other; an id published long before this process started
+                // belongs to an earlier run whose rank 0 did not get to remove it
+                if (ok && stamp + 30 >= started) break;
             }
             if (tries > 6000) {
                 std::cout << "FATAL: rank " << c.rank << " timed out waiting for " << path << std::endl;

@@ -17,8 +17,9 @@ struct Comm {
 
 // Reads GVB_RANK / GVB_NRANKS / GVB_LOCAL_RANK, falling back to torchrun's RANK / WORLD_SIZE /
 // LOCAL_RANK; obtains the NCCL unique id from GVB_NCCL_ID (hex, set by gvamp-launch) or through a
-// rendezvous file written by rank 0.  Idempotent.
+// rendezvous file written by rank 0 (single node only: its name derives from the launcher's pid).  Idempotent.
 Comm& world();
+void rendezvous_done();   // rank 0 removes the rendezvous file (called once the communicator exists, and at exit)
 bool is_root();
 double wtime();
 

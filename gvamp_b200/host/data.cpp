@@ -29,6 +29,7 @@ void data::open_device() {
     const gvb_host::Comm& w = gvb_host::world();
     if (!g_root_ctx) {
         if (gvb_ctx_create(&ctx, w.local_rank, w.rank, w.nranks, w.have_id ? w.nccl_id : nullptr) != GVB_OK) device_fatal("cannot open the CUDA device");
+        gvb_host::rendezvous_done();
         g_root_ctx = ctx;
         gvb_host::set_collective_ctx(ctx);
     } else {

@@ -151,27 +151,27 @@ int run_pvals_calc(const Options& opt, int rank) {
     if (rank == 0) std::cout << "iter range = [" << range[0] << ", " << range[1] << "]" << std::endl;
     std::vector<std::vector<double>> z1_hats, x1_hats;
     std::vector<std::string> out_loo, out_loco;
-    auto add = [&](const std::string& file, const std::string& stem) {
+    auto add = [&](const std::string& file, const std::string& loo_name, const std::string& loco_name) {
         std::vector<double> x = ext == "bin" ? mpi_read_vec_from_file(file, sh.M, sh.S) : read_vec_from_file(file, sh.M, sh.S);
         x.resize(sh.M, 0.0);
         for (double& v : x) v *= sqrt((double)N);
         z1_hats.push_back(dataset.Ax(x.data()));
         x1_hats.push_back(x);
-        if (rank == 0) std::cout << "filepath_out_pvals = " << stem << std::endl << "filepath_out_pvals_LOCO = " << stem << std::endl;
+        if (rank == 0) std::cout << "filepath_out_pvals = " << loo_name << std::endl << "filepath_out_pvals_LOCO = " << loco_name << std::endl;
     };
     if (range[0] != -1) {
         size_t pos_it = est.rfind("it");
         for (int it = range[0]; it <= range[1]; it++) {
             std::string stem = opt.get_out_dir() + opt.get_out_name() + "_it_" + std::to_string(it);
-            add(est.substr(0, pos_it) + "it_" + std::to_string(it) + "." + ext, stem);
+            add(est.substr(0, pos_it) + "it_" + std::to_string(it) + "." + ext, stem, stem);   // the range form prints the stems (main_real.cpp:395-400)
             out_loo.push_back(stem + "_pvals.bin");
             out_loco.push_back(stem + "_pvals_LOCO.bin");
         }
     } else {
         if (rank == 0) std::cout << "end_est_file_name = " << ext << std::endl;
-        add(est, opt.get_out_dir() + opt.get_out_name());
         out_loo.push_back(opt.get_out_dir() + opt.get_out_name() + "_pvals.bin");
         out_loco.push_back(opt.get_out_dir() + opt.get_out_name() + "_pvals_LOCO.bin");
+        add(est, out_loo.back(), out_loco.back());   // the single-estimate form prints the full paths (main_real.cpp:429-434)
     }
     std::vector<double> y = dataset.filter_pheno();
     const unsigned store_pvals = opt.get_store_pvals();

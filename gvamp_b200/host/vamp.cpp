@@ -661,6 +661,15 @@ std::vector<double> vamp::CG_solverAAT(std::vector<double> v, std::vector<double
         std::cout << "FATAL: compute_people_statistics() must run before the XXT solver" << std::endl;
         exit(EXIT_FAILURE);
     }
+    if (rank == 0) {   // the first entries of the preconditioner, as the reference prints them (denoiserXXT.cpp:68-78)
+        double a[3] = {0, 0, 0}, sg[3] = {1, 1, 1}, nb[3] = {0, 0, 0};
+        const long k = std::min<long>(3, N);
+        DEV(gvb_vec_download(ctx, pe[0], a, k));
+        DEV(gvb_vec_download(ctx, pe[1], sg, k));
+        DEV(gvb_vec_download(ctx, pe[2], nb, k));
+        for (long i = 0; i < k; i++)
+            std::cout << "diag[" << i << "] = " << tau * ((nb[i] - 1) / sg[i] / sg[i] + a[i] * a[i] * nb[i]) / N + gam2 << std::endl;
+    }
     std::vector<double> log(3 * (size_t)CG_max_iter, 0.0);
     int iters = 0;
     DEV(gvb_cg_solve_aat(ctx, dv, dmu, tau, gam2, pe[0], pe[1], pe[2], CG_max_iter, &iters, log.data()));

@@ -120,6 +120,9 @@ long gvb_missing_list_entries(gvb_ctx* ctx);
  * gathers its table indices from the one matrix.  Results are bit-identical in every state. */
 int gvb_twin_state(gvb_ctx* ctx);
 long gvb_twin_stripes(gvb_ctx* ctx); /* stripes (of 128 individuals) that have a twin */
+/* gives the twin's HBM back (state becomes -1: it is not rebuilt).  The library does this by itself for every context of the device
+ * when one of its own allocations fails (a second matrix in run mode `both`, main_real.cpp:255-330, scratch of later stages). */
+int gvb_twin_release(gvb_ctx* ctx);
 
 /* ---- X.v and X^T.u, host-pointer drop-in --------------------------------------------------------- */
 /* data::Ax(double* v, SB, LB), data.cpp:848-1011 incl. the MPI_Allreduce at :995.

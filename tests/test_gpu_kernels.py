@@ -224,6 +224,9 @@ def test_twin_layout_is_bit_identical(C, oracle, N, M, miss, monkeypatch):
             ctx.load_host(bed, N).set_mask(mask4, int(present.sum())).compute_stats(1.0)
             assert ctx.twin_state() == 0                             # decided by the first X.v
             res[mode] = (ctx.Ax(v), ctx.Ax(2.5 * v), ctx.twin_state(), ctx.twin_stripes())
+            if mode == "1":                                          # giving the twin back (what a failed allocation triggers) changes nothing
+                ctx.twin_release()
+                assert ctx.twin_state() == -1 and ctx.twin_stripes() == 0 and np.array_equal(ctx.Ax(v), res[mode][0])
     monkeypatch.delenv("GVB_TWIN_STRIPES")
     assert res["0"][2] == 0 and res["1"][2] == 1                     # really bypassed / really built
     assert res["partial"][2] == 2 and res["partial"][3] == n_stripes // 3 and res["1"][3] == n_stripes
@@ -572,3 +575,63 @@ def test_reduce_batch(C, oracle):
         assert np.allclose(res, ref, rtol=1e-13)
         with pytest.raises(C.GvbError):
             ctx.reduce_batch([(C.RED_DOT, vu, vw, 0, 0, 0), (C.RED_DOT, va, vb, 0, 0, 1)])   # rank-summed operations come first
+
+
+ADVERSARIAL = ["u_outlier_1e6", "u_outlier_1e3", "u_two_scales", "v_outlier_1e6", "v_clustered_tile", "v_sparse", "both_tiny_and_huge"]
+
+
+@pytest.mark.parametrize("case", ADVERSARIAL)
+def test_fixed_point_dynamic_range(C, oracle, case):
+    """The fixed-point sweeps under adversarial dynamic range: a single outlier 10^3 / 10^6 times the rest in u,
+    stripes of u on two scales 10^4 apart, a single outlier in v, 128 clustered large effects in ONE marker tile over a tiny dense
+    background, a 99.9 % sparse v.  With one global scale the outlier's magnitude would set the resolution of every table entry
+    (norm-wise error ~ 3.5e-8 * max|u| / rms(u), i.e. 2e-5 for the 10^6 outlier at this N); the per-stripe / per-tile scale classes
+    (matvec_tile.cu "Scale classes") keep BOTH the norm-wise error ||d||_2 / ||ref||_2 and the worst element against the largest
+    output, ||d||_inf / ||ref||_inf, below the north_star's 1e-6.  N = 131072 (1024 stripes): the error grows with sqrt(N)."""
+    N, M = 131072, 2048
+    bed = oracle.synth_bed(23, 0, M, N, miss_rate=0.0)
+    ds = oracle.Dataset(bed, N)
+    rng = np.random.default_rng(len(case))
+    u, v = rng.normal(size=N), rng.normal(size=M)
+    if case == "u_outlier_1e6":
+        u[54321] = 1e6
+    elif case == "u_outlier_1e3":
+        u[777] = -1e3
+    elif case == "u_two_scales":
+        u[: N // 2] *= 1e-4
+    elif case == "v_outlier_1e6":
+        v[77] = 1e6
+    elif case == "v_clustered_tile":
+        v *= 1e-3
+        v[256:384] = rng.normal(size=128) * 1e3
+    elif case == "v_sparse":
+        v[rng.random(M) > 0.001] = 0.0
+        v[5] = 3.0
+    elif case == "both_tiny_and_huge":
+        u *= 1e-150
+        v *= 1e150
+    with make_ctx(C, "lut") as ctx:
+        ctx.load_host(bed, N).compute_stats(1.0)
+        ax, atx = ctx.Ax(v)[:N], ctx.ATx(u)
+    ax_ref, atx_ref = ds.Ax(v)[:N], ds.ATx(u)
+    linf = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+    assert relerr(ax, ax_ref) < TOL_MATVEC and linf(ax, ax_ref) < TOL_MATVEC, (relerr(ax, ax_ref), linf(ax, ax_ref))
+    assert relerr(atx, atx_ref) < TOL_MATVEC and linf(atx, atx_ref) < TOL_MATVEC, (relerr(atx, atx_ref), linf(atx, atx_ref))
+
+
+def test_fixed_point_dynamic_range_with_missing_genotypes(C, oracle):
+    """The same outlier on a shard WITH missing genotypes: the missing-genotype correction sum_{i missing} u_i is gathered at the common
+    class-0 scale (misslist.cu sums indices of many stripes in one window), so its share of the result keeps the single-scale
+    resolution; with 2 % missing genotypes and a 10^3 outlier both norms stay below 1e-6, and the list and the second walk (which
+    carries the classes) agree to that accuracy instead of bit for bit."""
+    N, M = 131072, 1024
+    bed = oracle.synth_bed(29, 0, M, N, miss_rate=0.02)
+    ds = oracle.Dataset(bed, N)
+    u = np.random.default_rng(2).normal(size=N)
+    u[4242] = 1e3
+    with make_ctx(C, "lut") as ctx:
+        ctx.load_host(bed, N).compute_stats(1.0)
+        atx = ctx.ATx(u)
+        assert ctx.missing_list_entries() > 0
+    ref = ds.ATx(u)
+    assert relerr(atx, ref) < TOL_MATVEC and float(np.max(np.abs(atx - ref)) / np.max(np.abs(ref))) < TOL_MATVEC

@@ -22,7 +22,11 @@ LIB = os.path.join(LIBDIR, "libgvamp_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CU_SOURCES = ["capi.cu", "cg.cu", "layout.cu", "stats.cu", "matvec_simple.cu", "matvec_lut.cu", "matvec_tile.cu", "misslist.cu", "twin.cu", "assoc.cu", "people.cu", "vecops.cu"]
+CU_SOURCES = ["capi.cu", "cg.cu", "layout.cu", "stats.cu", "matvec_tile.cu", "misslist.cu", "twin.cu", "assoc.cu", "people.cu", "vecops.cu"]
+# test-only build (gvamp_b200/lib/xcheck/libgvamp_b200.so): the same library plus the two earlier kernel generations that the parity tests
+# use as on-device cross-checks (env GVB_KERNELS=simple|lut1); capi.cu is compiled a second time with -DGVB_LEGACY_KERNELS for it
+XCHECK_EXTRA = ["matvec_simple.cu", "matvec_lut.cu"]
+XCHECK_LIB = os.path.join(LIBDIR, "xcheck", "libgvamp_b200.so")
 NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", HOSTCXX, "--expt-relaxed-constexpr",
               "-Xcompiler", "-Wno-unused-result"] + ARCH
 
@@ -44,22 +48,33 @@ def build_cuda(force=False, verbose=True, ptxas_v=False):
     os.makedirs(LIBDIR, exist_ok=True)
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
+    os.makedirs(os.path.dirname(XCHECK_LIB), exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [os.path.join(ROOT, "include", "gvamp_b200.h")]
-    objs, procs = [], []
-    for src in CU_SOURCES:
+    procs = []
+
+    def compile_obj(src, obj, extra):
         s = os.path.join(CSRC, src)
-        o = os.path.join(objdir, src.replace(".cu", ".o"))
-        objs.append(o)
+        o = os.path.join(objdir, obj)
         if force or _newer(o, [s] + headers):
-            cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", s, "-o", o]
+            cmd = [NVCC] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd), flush=True)
             procs.append((src, subprocess.Popen(cmd)))
+        return o
+
+    objs = [compile_obj(src, src.replace(".cu", ".o"), []) for src in CU_SOURCES]
+    xobjs = [o for o in objs if not o.endswith(os.sep + "capi.o")]
+    xobjs.append(compile_obj("capi.cu", "capi_xcheck.o", ["-DGVB_LEGACY_KERNELS"]))
+    xobjs += [compile_obj(src, src.replace(".cu", ".o"), ["-DGVB_LEGACY_KERNELS"]) for src in XCHECK_EXTRA]
     for src, p in procs:
         if p.wait() != 0:
             raise RuntimeError(f"nvcc failed on {src}")
+    # -Bsymbolic: a process may hold both builds (the tests do); each binds its own gvb_* symbols
+    link = ARCH + ["-ccbin", HOSTCXX, "-lnccl", "-L/usr/lib/x86_64-linux-gnu", "-Xlinker", "-Bsymbolic"]
     if force or procs or _newer(LIB, objs):
-        _run([NVCC, "-shared", "-o", LIB] + objs + ARCH + ["-ccbin", HOSTCXX, "-lnccl", "-L/usr/lib/x86_64-linux-gnu"], verbose)
+        _run([NVCC, "-shared", "-o", LIB] + objs + link, verbose)
+    if force or procs or _newer(XCHECK_LIB, xobjs):
+        _run([NVCC, "-shared", "-o", XCHECK_LIB] + xobjs + link, verbose)
     return LIB
 
 
@@ -70,8 +85,9 @@ def build_host(force=False, verbose=True):
     common = [os.path.join(HOST, f) for f in ("options.cpp", "data.cpp", "vamp.cpp", "utilities.cpp", "comm.cpp") if os.path.exists(os.path.join(HOST, f))]
     headers = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")] + [os.path.join(ROOT, "include", "gvamp_b200.h")]
     outs = []
-    flags = ["-O2", "-std=c++17", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + HOST, "-Wno-unused-result"]
-    link = ["-L" + LIBDIR, "-lgvamp_b200", "-Wl,-rpath," + LIBDIR, "-Wl,-rpath,$ORIGIN/../lib", "-lpthread"]
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(NVCC)), "include")    # nvtx3 (header-only) for the phase ranges
+    flags = ["-O2", "-std=c++17", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + HOST, "-isystem", cuda_inc, "-Wno-unused-result"]
+    link = ["-L" + LIBDIR, "-lgvamp_b200", "-Wl,-rpath," + LIBDIR, "-Wl,-rpath,$ORIGIN/../lib", "-lpthread", "-ldl"]
     hostlib = os.path.join(LIBDIR, "libgvamp_host.so")
     capi = os.path.join(HOST, "host_capi.cpp")
     if common and os.path.exists(capi) and (force or _newer(hostlib, common + [capi] + headers + [LIB])):

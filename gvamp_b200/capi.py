@@ -101,7 +101,9 @@ class RedOp(ctypes.Structure):
 
 RED_DOT, RED_SQ = 0, 1
 
+XCHECK_LIB_PATH = os.path.join(HERE, "lib", "xcheck", "libgvamp_b200.so")
 _LIB = None
+_XLIB = None
 
 
 class GvbError(RuntimeError):
@@ -123,9 +125,25 @@ def load():
     return _LIB
 
 
-def _chk(rc):
+def load_xcheck():
+    """The TEST build of the library (gvamp_b200/lib/xcheck/): the product library plus the two earlier kernel generations that the
+    parity tests use as on-device cross-checks (env GVB_KERNELS=simple|lut1).  Never loaded by the product path or by bench.py."""
+    global _XLIB
+    if _XLIB is None:
+        if not os.path.exists(XCHECK_LIB_PATH):
+            raise GvbError(f"{XCHECK_LIB_PATH} is missing: run `python -m gvamp_b200.build`")
+        L = ctypes.CDLL(XCHECK_LIB_PATH, mode=ctypes.RTLD_LOCAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _XLIB = L
+    return _XLIB
+
+
+def _chk(rc, L=None):
     if rc != 0:
-        raise GvbError(f"gvamp_b200 error {rc}: {load().gvb_last_error().decode()}")
+        raise GvbError(f"gvamp_b200 error {rc}: {(L or load()).gvb_last_error().decode()}")
 
 
 def _f64(a):
@@ -158,41 +176,41 @@ class Vec:
         self.ctx, self.h = ctx, handle
 
     def __len__(self):
-        return load().gvb_vec_len(self.h)
+        return self.ctx.L.gvb_vec_len(self.h)
 
     def upload(self, a):
         a, p = _f64(a)
-        _chk(load().gvb_vec_upload(self.ctx.h, self.h, p, len(a)))
+        _chk(self.ctx.L.gvb_vec_upload(self.ctx.h, self.h, p, len(a)), self.ctx.L)
         return self
 
     def download(self, n=None):
         n = len(self) if n is None else n
         out = np.empty(n)
-        _chk(load().gvb_vec_download(self.ctx.h, self.h, out.ctypes.data_as(c_f64p), n))
+        _chk(self.ctx.L.gvb_vec_download(self.ctx.h, self.h, out.ctypes.data_as(c_f64p), n), self.ctx.L)
         return out
 
     def fill(self, v):
-        _chk(load().gvb_vec_fill(self.ctx.h, self.h, float(v)))
+        _chk(self.ctx.L.gvb_vec_fill(self.ctx.h, self.h, float(v)), self.ctx.L)
         return self
 
     def copy_from(self, other):
-        _chk(load().gvb_vec_copy(self.ctx.h, self.h, other.h))
+        _chk(self.ctx.L.gvb_vec_copy(self.ctx.h, self.h, other.h), self.ctx.L)
         return self
 
     def free(self):
         if self.h:
-            load().gvb_vec_free(self.ctx.h, self.h)
+            self.ctx.L.gvb_vec_free(self.ctx.h, self.h)
             self.h = None
 
 
 class Context:
     """One B200 / one marker shard (include/gvamp_b200.h: gvb_ctx)."""
 
-    def __init__(self, device=0, rank=0, nranks=1, nccl_id: bytes | None = None):
-        self.L = load()
+    def __init__(self, device=0, rank=0, nranks=1, nccl_id: bytes | None = None, xcheck: bool = False):
+        self.L = load_xcheck() if xcheck else load()
         h = vp()
         idbuf = ctypes.create_string_buffer(nccl_id, NCCL_ID_BYTES) if nccl_id else None
-        _chk(self.L.gvb_ctx_create(ctypes.byref(h), device, rank, nranks, idbuf))
+        _chk(self.L.gvb_ctx_create(ctypes.byref(h), device, rank, nranks, idbuf), self.L)
         self.h = h
         self.rank, self.nranks = rank, nranks
 
@@ -201,9 +219,9 @@ class Context:
         """A second context on the parent's device that shares its NCCL communicator (gvb_ctx_create_shared): another matrix
         (a test set, a small self-check problem) next to the resident one.  Close it before the parent."""
         self = cls.__new__(cls)
-        self.L = load()
+        self.L = parent.L
         h = vp()
-        _chk(self.L.gvb_ctx_create_shared(ctypes.byref(h), parent.h))
+        _chk(self.L.gvb_ctx_create_shared(ctypes.byref(h), parent.h), self.L)
         self.h = h
         self.rank, self.nranks = parent.rank, parent.nranks
         return self
@@ -223,50 +241,50 @@ class Context:
     def load_host(self, bed, N, Mt=None, S=0):
         bed = np.ascontiguousarray(bed, dtype=np.uint8)
         M = bed.shape[0]
-        _chk(self.L.gvb_bed_load_host(self.h, bed.ctypes.data_as(c_u8p), N, Mt or M, S, M))
+        _chk(self.L.gvb_bed_load_host(self.h, bed.ctypes.data_as(c_u8p), N, Mt or M, S, M), self.L)
         return self
 
     def load_file(self, path, N, Mt, S, M):
-        _chk(self.L.gvb_bed_load_file(self.h, path.encode(), N, Mt, S, M))
+        _chk(self.L.gvb_bed_load_file(self.h, path.encode(), N, Mt, S, M), self.L)
         return self
 
     def synth(self, seed, N, Mt, S, M, miss_rate=0.0):
-        _chk(self.L.gvb_bed_synth(self.h, seed, N, Mt, S, M, miss_rate))
+        _chk(self.L.gvb_bed_synth(self.h, seed, N, Mt, S, M, miss_rate), self.L)
         return self
 
     def info(self):
         v = [cl(0) for _ in range(5)]
-        _chk(self.L.gvb_ctx_info(self.h, *[ctypes.byref(x) for x in v]))
+        _chk(self.L.gvb_ctx_info(self.h, *[ctypes.byref(x) for x in v]), self.L)
         return dict(zip(("N", "Mt", "S", "M", "mbytes"), (x.value for x in v)))
 
     def decode(self, j0, n):
         mb = self.info()["mbytes"]
         out = np.empty((n, mb), dtype=np.uint8)
-        _chk(self.L.gvb_bed_decode(self.h, j0, n, out.ctypes.data_as(c_u8p)))
+        _chk(self.L.gvb_bed_decode(self.h, j0, n, out.ctypes.data_as(c_u8p)), self.L)
         return out
 
     def set_mask(self, mask4, nonas):
         if mask4 is None:
-            _chk(self.L.gvb_set_mask(self.h, None, nonas))
+            _chk(self.L.gvb_set_mask(self.h, None, nonas), self.L)
         else:
             m = np.ascontiguousarray(mask4, dtype=np.uint8)
-            _chk(self.L.gvb_set_mask(self.h, m.ctypes.data_as(c_u8p), nonas))
+            _chk(self.L.gvb_set_mask(self.h, m.ctypes.data_as(c_u8p), nonas), self.L)
         return self
 
     def compute_stats(self, alpha_scale=1.0):
-        _chk(self.L.gvb_compute_stats(self.h, alpha_scale))
+        _chk(self.L.gvb_compute_stats(self.h, alpha_scale), self.L)
         return self
 
     def stats(self):
         M = self.info()["M"]
         a, s = np.empty(M), np.empty(M)
-        _chk(self.L.gvb_get_stats(self.h, a.ctypes.data_as(c_f64p), s.ctypes.data_as(c_f64p)))
+        _chk(self.L.gvb_get_stats(self.h, a.ctypes.data_as(c_f64p), s.ctypes.data_as(c_f64p)), self.L)
         return a, s
 
     def counts(self):
         M = self.info()["M"]
         out = np.empty((M, 8), dtype=np.int64)
-        _chk(self.L.gvb_get_counts(self.h, out.ctypes.data_as(c_i64p)))
+        _chk(self.L.gvb_get_counts(self.h, out.ctypes.data_as(c_i64p)), self.L)
         return out
 
     # ---- host-pointer drop-ins
@@ -276,7 +294,7 @@ class Context:
         v, pv = _f64(v)
         assert len(v) == inf["M"]
         out = np.empty(4 * LB)
-        _chk(self.L.gvb_Ax(self.h, pv, out.ctypes.data_as(c_f64p), SB, LB))
+        _chk(self.L.gvb_Ax(self.h, pv, out.ctypes.data_as(c_f64p), SB, LB), self.L)
         return out
 
     def ATx(self, u, SB=0, LB=None):
@@ -286,36 +304,36 @@ class Context:
         u = np.asarray(u, dtype=np.float64)
         uu[: min(len(u), 4 * LB)] = u[: 4 * LB]
         out = np.empty(inf["M"])
-        _chk(self.L.gvb_ATx(self.h, uu.ctypes.data_as(c_f64p), out.ctypes.data_as(c_f64p), SB, LB))
+        _chk(self.L.gvb_ATx(self.h, uu.ctypes.data_as(c_f64p), out.ctypes.data_as(c_f64p), SB, LB), self.L)
         return out
 
     # ---- device vectors
     def vec(self, n):
         h = vp()
-        _chk(self.L.gvb_vec_alloc(self.h, n, ctypes.byref(h)))
+        _chk(self.L.gvb_vec_alloc(self.h, n, ctypes.byref(h)), self.L)
         return Vec(self, h)
 
     def vecM(self, init=None):
         h = vp()
-        _chk(self.L.gvb_vec_alloc_M(self.h, ctypes.byref(h)))
+        _chk(self.L.gvb_vec_alloc_M(self.h, ctypes.byref(h)), self.L)
         v = Vec(self, h)
         return v.upload(init) if init is not None else v
 
     def vecN(self, init=None):
         h = vp()
-        _chk(self.L.gvb_vec_alloc_N(self.h, ctypes.byref(h)))
+        _chk(self.L.gvb_vec_alloc_N(self.h, ctypes.byref(h)), self.L)
         v = Vec(self, h)
         return v.upload(init) if init is not None else v
 
     def axpby(self, out, a, x, b=0.0, y=None):
-        _chk(self.L.gvb_vec_axpby(self.h, out.h, a, x.h, b, y.h if y is not None else None))
+        _chk(self.L.gvb_vec_axpby(self.h, out.h, a, x.h, b, y.h if y is not None else None), self.L)
 
     def dots(self, xs, ys=None, sync=True):
         n = len(xs)
         X = (vp * n)(*[x.h for x in xs])
         Y = (vp * n)(*[(y.h if y is not None else None) for y in (ys or [None] * n)])
         res = np.empty(n)
-        _chk(self.L.gvb_vec_dots(self.h, n, X, Y, int(sync), res.ctypes.data_as(c_f64p)))
+        _chk(self.L.gvb_vec_dots(self.h, n, X, Y, int(sync), res.ctypes.data_as(c_f64p)), self.L)
         return res
 
     def reduce_batch(self, ops):
@@ -323,25 +341,25 @@ class Context:
         n = len(ops)
         arr = (RedOp * n)(*[RedOp(x.h, y.h if y is not None else None, a, b, kind, int(sync)) for kind, x, y, a, b, sync in ops])
         res = np.empty(n)
-        _chk(self.L.gvb_vec_reduce_batch(self.h, n, ctypes.cast(arr, vp), res.ctypes.data_as(c_f64p)))
+        _chk(self.L.gvb_vec_reduce_batch(self.h, n, ctypes.cast(arr, vp), res.ctypes.data_as(c_f64p)), self.L)
         return res
 
     def dist2(self, x, y, sync=True):
         res = np.empty(1)
-        _chk(self.L.gvb_vec_dist2(self.h, x.h, y.h, int(sync), res.ctypes.data_as(c_f64p)))
+        _chk(self.L.gvb_vec_dist2(self.h, x.h, y.h, int(sync), res.ctypes.data_as(c_f64p)), self.L)
         return float(res[0])
 
     def dAx(self, v, out):
-        _chk(self.L.gvb_dAx(self.h, v.h, out.h))
+        _chk(self.L.gvb_dAx(self.h, v.h, out.h), self.L)
 
     def dATx(self, u, out):
-        _chk(self.L.gvb_dATx(self.h, u.h, out.h))
+        _chk(self.L.gvb_dATx(self.h, u.h, out.h), self.L)
 
     def denoise(self, r1, gam1, probs, vars_, x1_hat):
         p, pp = _f64(probs)
         v, pv = _f64(vars_)
         sums = np.empty(2)
-        _chk(self.L.gvb_denoise(self.h, r1.h, gam1, pp, pv, len(p), x1_hat.h, sums.ctypes.data_as(c_f64p)))
+        _chk(self.L.gvb_denoise(self.h, r1.h, gam1, pp, pv, len(p), x1_hat.h, sums.ctypes.data_as(c_f64p)), self.L)
         return sums
 
     def em_stats(self, r1, gam1, lam, omegas, vars_):
@@ -349,16 +367,16 @@ class Context:
         v, pv = _f64(vars_)
         L = len(o)
         sums = np.empty(2 * L - 1)
-        _chk(self.L.gvb_em_stats(self.h, r1.h, gam1, lam, po, pv, L, sums.ctypes.data_as(c_f64p)))
+        _chk(self.L.gvb_em_stats(self.h, r1.h, gam1, lam, po, pv, L, sums.ctypes.data_as(c_f64p)), self.L)
         return sums
 
     def lmmse_mult(self, v, tau, gam2, out):
-        _chk(self.L.gvb_lmmse_mult(self.h, v.h, tau, gam2, out.h))
+        _chk(self.L.gvb_lmmse_mult(self.h, v.h, tau, gam2, out.h), self.L)
 
     def cg_solve(self, rhs, mu, tau, gam2, max_iter, denoiser):
         it = ci(0)
         log = np.zeros(4 * max_iter)
-        _chk(self.L.gvb_cg_solve(self.h, rhs.h, mu.h, tau, gam2, max_iter, denoiser, ctypes.byref(it), log.ctypes.data_as(c_f64p)))
+        _chk(self.L.gvb_cg_solve(self.h, rhs.h, mu.h, tau, gam2, max_iter, denoiser, ctypes.byref(it), log.ctypes.data_as(c_f64p)), self.L)
         return it.value, log.reshape(max_iter, 4)[: it.value]
 
     def cg_solve_ex(self, rhs, mu, tau, gam2, max_iter, denoiser, ax_mu=None):
@@ -379,7 +397,7 @@ class Context:
 
     def people_stats(self):
         a, s, n = self.vecN(), self.vecN(), self.vecN()
-        _chk(self.L.gvb_people_stats(self.h, a.h, s.h, n.h))
+        _chk(self.L.gvb_people_stats(self.h, a.h, s.h, n.h), self.L)
         return a, s, n
 
     def cg_solve_aat(self, rhs, mu, tau, gam2, people, max_iter):
@@ -397,25 +415,25 @@ class Context:
 
     # ---- timing / counters
     def sync(self):
-        _chk(self.L.gvb_ctx_sync(self.h))
+        _chk(self.L.gvb_ctx_sync(self.h), self.L)
 
     def timer_start(self, slot=0):
-        _chk(self.L.gvb_timer_start(self.h, slot))
+        _chk(self.L.gvb_timer_start(self.h, slot), self.L)
 
     def timer_stop(self, slot=0):
-        _chk(self.L.gvb_timer_stop(self.h, slot))
+        _chk(self.L.gvb_timer_stop(self.h, slot), self.L)
 
     def timer_ms(self, slot=0) -> float:
         ms = ctypes.c_float(0)
-        _chk(self.L.gvb_timer_elapsed_ms(self.h, slot, ctypes.byref(ms)))
+        _chk(self.L.gvb_timer_elapsed_ms(self.h, slot, ctypes.byref(ms)), self.L)
         return ms.value
 
     def profile(self, on=True):
-        _chk(self.L.gvb_profile_enable(self.h, int(on)))
+        _chk(self.L.gvb_profile_enable(self.h, int(on)), self.L)
 
     def profile_read(self):
         out = np.zeros(4)
-        _chk(self.L.gvb_profile_read(self.h, out.ctypes.data_as(c_f64p)))
+        _chk(self.L.gvb_profile_read(self.h, out.ctypes.data_as(c_f64p)), self.L)
         return dict(ax_ms=out[0], ax_n=int(out[1]), atx_ms=out[2], atx_n=int(out[3]))
 
     def launches(self) -> int:
@@ -433,26 +451,26 @@ class Context:
     def probit_cov_pass(self, y, gg, Z, C, eta, probit_var=1.0, what=7):
         e, pe = _f64(eta)
         out = np.empty(1 + 2 * C + C * C)
-        _chk(self.L.gvb_probit_cov_pass(self.h, y.h, gg.h if gg is not None else None, Z.h, C, pe, probit_var, what, out.ctypes.data_as(c_f64p)))
+        _chk(self.L.gvb_probit_cov_pass(self.h, y.h, gg.h if gg is not None else None, Z.h, C, pe, probit_var, what, out.ctypes.data_as(c_f64p)), self.L)
         return out[0], out[1:1 + C].copy(), out[1 + C:1 + 2 * C].copy(), out[1 + 2 * C:].reshape(C, C).copy()
 
     def probit_cov_apply(self, Z, C, eta, mcov):
         e, pe = _f64(eta)
-        _chk(self.L.gvb_probit_cov_apply(self.h, Z.h, C, pe, mcov.h))
+        _chk(self.L.gvb_probit_cov_apply(self.h, Z.h, C, pe, mcov.h), self.L)
 
     def assoc_pvals(self, yres, coef, select, pvals):
-        _chk(self.L.gvb_assoc_pvals(self.h, yres.h, coef.h if coef is not None else None, select.h if select is not None else None, pvals.h))
+        _chk(self.L.gvb_assoc_pvals(self.h, yres.h, coef.h if coef is not None else None, select.h if select is not None else None, pvals.h), self.L)
 
     def missing_list_entries(self) -> int:
         return self.L.gvb_missing_list_entries(self.h)
 
     def snapshot_begin(self, vec, n, slot):
-        _chk(self.L.gvb_snapshot_begin(self.h, vec.h, n, slot))
+        _chk(self.L.gvb_snapshot_begin(self.h, vec.h, n, slot), self.L)
 
     def snapshot_wait(self, slot):
         """copy of the pinned host buffer of a snapshot (blocks until the device -> host copy has landed)"""
         ptr, n = c_f64p(), cl()
-        _chk(self.L.gvb_snapshot_wait(self.h, slot, ctypes.byref(ptr), ctypes.byref(n)))
+        _chk(self.L.gvb_snapshot_wait(self.h, slot, ctypes.byref(ptr), ctypes.byref(n)), self.L)
         return np.ctypeslib.as_array(ptr, shape=(n.value,)).copy()
 
     def twin_state(self) -> int:
@@ -460,7 +478,7 @@ class Context:
         return self.L.gvb_twin_state(self.h)
 
     def twin_release(self):
-        _chk(self.L.gvb_twin_release(self.h))
+        _chk(self.L.gvb_twin_release(self.h), self.L)
 
     def twin_stripes(self) -> int:
         return self.L.gvb_twin_stripes(self.h)

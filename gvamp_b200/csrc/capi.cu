@@ -46,6 +46,23 @@ extern "C" void gvb_divide_work(long Mt, int nranks, int rank, long* M, long* S)
     if (S) *S = start;
 }
 
+// The product library ships ONE implementation of the sweeps (the tile kernels of matvec_tile.cu).  The earlier generations -- FP64
+// decode-multiply kernels ("simple") and the first table kernels ("lut1") -- are cross-checks for the tests and exist only in the
+// test build of the library (gvamp_b200/lib/xcheck/, compiled with -DGVB_LEGACY_KERNELS), selected there by env GVB_KERNELS.
+static int pick_kernel_gen(int* out) {
+    const char* gen = getenv("GVB_KERNELS");
+    *out = 2;
+    if (gen && (!strcmp(gen, "simple") || !strcmp(gen, "lut1"))) {
+#ifdef GVB_LEGACY_KERNELS
+        *out = !strcmp(gen, "simple") ? 0 : 1;
+#else
+        gvb_set_error("GVB_KERNELS=%s: the cross-check kernels are not part of the product library (the tests load gvamp_b200/lib/xcheck/libgvamp_b200.so)", gen);
+        return GVB_ERR_ARG;
+#endif
+    }
+    return GVB_OK;
+}
+
 static std::vector<gvb_ctx*> g_live_ctx;   // every context of this process (one host thread drives the library, see the header)
 
 int gvb_release_twins(int device) {
@@ -74,14 +91,15 @@ static int ctx_common_init(gvb_ctx* c) {
     GVB_CUDA(cudaMemset(c->scal, 0, sizeof(double) * 64));
     GVB_CUDA(gvb_malloc(c, &c->work_counter, sizeof(int) * 16));
     GVB_CUDA(cudaMemset(c->work_counter, 0, sizeof(int) * 16));
-    const char* gen = getenv("GVB_KERNELS");
-    c->kernel_gen = (gen && !strcmp(gen, "simple")) ? 0 : ((gen && !strcmp(gen, "lut1")) ? 1 : 2);
+    GVB_CHECK(pick_kernel_gen(&c->kernel_gen));
     return GVB_OK;
 }
 
 extern "C" int gvb_ctx_create_shared(gvb_ctx** out, gvb_ctx* parent) {
     GVB_ARG(out && parent, "out / parent");
     GVB_CUDA(cudaSetDevice(parent->device));
+    int gen_probe = 2;
+    GVB_CHECK(pick_kernel_gen(&gen_probe));
     gvb_ctx* c = new gvb_ctx();
     c->device = parent->device;
     c->rank = parent->rank;
@@ -114,6 +132,8 @@ extern "C" int gvb_ctx_create(gvb_ctx** out, int device, int rank, int nranks, c
         gvb_set_error("device %d (%s, sm_%d%d) is not a Blackwell part: this library ships sm_100a code only", device, prop.name, prop.major, prop.minor);
         return GVB_ERR_CUDA;
     }
+    int gen_probe = 2;
+    GVB_CHECK(pick_kernel_gen(&gen_probe));
     gvb_ctx* c = new gvb_ctx();
     c->device = device;
     c->rank = rank;
@@ -348,7 +368,11 @@ extern "C" int gvb_profile_read(gvb_ctx* c, double* out4) {
 int gvb_ax_dev(gvb_ctx* c, const double* v, double* out, bool allreduce) {
     GVB_ARG(c->have_stats, "compute_stats must run before Ax");
     prof_mark(c, 0);
+#ifdef GVB_LEGACY_KERNELS
     int rc_mv = c->kernel_gen == 0 ? gvb_ax_simple(c, v, out) : (c->kernel_gen == 1 ? gvb_ax_lut(c, v, out) : gvb_ax_tile(c, v, out));
+#else
+    int rc_mv = gvb_ax_tile(c, v, out);
+#endif
     prof_mark(c, 0);
     GVB_CHECK(rc_mv);
     c->sweeps++;
@@ -361,7 +385,11 @@ int gvb_ax_dev(gvb_ctx* c, const double* v, double* out, bool allreduce) {
 int gvb_atx_dev(gvb_ctx* c, const double* u, double* out) {
     GVB_ARG(c->have_stats, "compute_stats must run before ATx");
     prof_mark(c, 1);
+#ifdef GVB_LEGACY_KERNELS
     int rc_mv = c->kernel_gen == 0 ? gvb_atx_simple(c, u, out) : (c->kernel_gen == 1 ? gvb_atx_lut(c, u, out) : gvb_atx_tile(c, u, out));
+#else
+    int rc_mv = gvb_atx_tile(c, u, out);
+#endif
     prof_mark(c, 1);
     GVB_CHECK(rc_mv);
     c->sweeps++;

@@ -15,6 +15,8 @@
 #include <random>
 #include <stdexcept>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "comm.hpp"
 #include "utilities.hpp"
 
@@ -31,6 +33,13 @@ namespace {
     } while (0)
 
 inline double clampd(double x, double lo, double hi) { return std::min(std::max(x, lo), hi); }
+
+// NVTX range over one phase of an iteration (denoise / z1 / LMMSE CG / Onsager / noise precision / outputs): what a timeline
+// tool shows as the iteration's structure; a no-op without an attached tool (nvtx3 is header-only and loads its injection lazily)
+struct Phase {
+    explicit Phase(const char* name) { nvtxRangePushA(name); }
+    ~Phase() { nvtxRangePop(); }
+};
 
 bool files_enabled() {
     const char* e = getenv("GVB_NO_FILES");
@@ -342,6 +351,8 @@ bool vamp::linear_iteration(data* dataset, int it) {
         if (rank == 0)
             std::cout << std::endl << "********************" << std::endl << "iteration = " << it << std::endl << "********************" << std::endl
                       << "->DENOISING" << std::endl;
+        nvtxRangePushA("vamp.iteration");
+        nvtxRangePushA("vamp.denoise+EM");
         DEV(gvb_vec_copy(ctx, dev.x1_prev, dev.x1));
         probs_before = probs;
         vars_before = vars;
@@ -372,8 +383,12 @@ bool vamp::linear_iteration(data* dataset, int it) {
             alpha1 = rho * alpha1 + (1 - rho) * alpha1_prev;
         }
 
+        nvtxRangePop();
         double start_z1 = wtime();
-        DEV(gvb_dAx(ctx, dev.x1, dev.z1));
+        {
+            Phase ph("vamp.z1 = X.x1");
+            DEV(gvb_dAx(ctx, dev.x1, dev.z1));
+        }
         std::string filepath_out_z1 = out_dir + out_name + "_z1_it_" + std::to_string(it) + ".csv";
         emit_output(SNAP_Z1, dev.z1, 4 * dataset->get_mbytes(), filepath_out_z1, scale, S);
         double end_z1 = wtime();
@@ -433,6 +448,7 @@ bool vamp::linear_iteration(data* dataset, int it) {
         if (rank == 0) std::cout << "______________________" << std::endl << "->LMMSE" << std::endl;
 
         double start_CG = wtime();
+        nvtxRangePushA("vamp.LMMSE CG");
         if (reverse == 1) {   // XXT form: solve in N-space (vamp.cpp:599-606)
             if (it == 1) mu_CG_last = std::vector<double>(4 * dataset->get_mbytes(), 0.0);
             std::vector<double> r2_h;
@@ -467,13 +483,17 @@ bool vamp::linear_iteration(data* dataset, int it) {
         DEV(gvb_vec_copy(ctx, dev.mu_last, dev.x2));
         dev.ax_x2_valid = !reference_sweeps;
         }
+        nvtxRangePop();
         std::string filepath_out_x2 = out_dir + out_name + "_it_" + std::to_string(it) + "_x2_hat.bin";
         emit_output(SNAP_X2, dev.x2, M, filepath_out_x2, scale, S);
         if (rank == 0) std::cout << "x2_hat filepath_out is " << filepath_out_x2 << std::endl;
         if (rank == 0) std::cout << "CG took " << wtime() - start_CG << " seconds." << std::endl;
 
         double start_onsager = wtime();
-        alpha2 = g2d_onsager(gam2, gamw, dataset);
+        {
+            Phase ph("vamp.Onsager CG");
+            alpha2 = g2d_onsager(gam2, gamw, dataset);
+        }
         if (rank == 0) std::cout << "onsager took " << wtime() - start_onsager << " seconds." << std::endl;
         if (rank == 0) std::cout << "alpha2 = " << alpha2 << std::endl;
 
@@ -523,9 +543,13 @@ bool vamp::linear_iteration(data* dataset, int it) {
             stop_nn = res[6];
         }
 
-        updateNoisePrec(dataset);
-        err_measures(dataset, 2);
-        flush_outputs(scale, S);   // the snapshots of this iteration's outputs have landed long ago: scale and write them
+        {
+            Phase ph("vamp.noise precision + outputs");
+            updateNoisePrec(dataset);
+            err_measures(dataset, 2);
+            flush_outputs(scale, S);
+        }
+        nvtxRangePop();   // vamp.iteration   // the snapshots of this iteration's outputs have landed long ago: scale and write them
 
         double end_lmmse_step = wtime();
         if (rank == 0) std::cout << "lmmse step took " << end_lmmse_step - start_lmmse_step << " seconds." << std::endl;

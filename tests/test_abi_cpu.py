@@ -54,3 +54,19 @@ def test_no_cpu_fallback(capi):
     with pytest.raises(capi.GvbError) as e:
         capi.Context(0)
     assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_library_ships_one_kernel_generation(capi):
+    """The product library holds only the tile kernels; the earlier generations (FP64 decode kernels, first table kernels) that the
+    parity tests use as on-device cross-checks exist only in the test build gvamp_b200/lib/xcheck/libgvamp_b200.so, which exports
+    the same C ABI."""
+    import subprocess
+    syms = lambda path: subprocess.run(["nm", "-C", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    product, xcheck = syms(capi.LIB_PATH), syms(capi.XCHECK_LIB_PATH)
+    for legacy in ("gvb_ax_lut", "gvb_atx_lut", "gvb_ax_simple", "gvb_atx_simple"):
+        assert legacy not in product and legacy in xcheck, legacy
+    assert "gvb_ax_tile" in product and "gvb_atx_tile" in product
+    hdr = open(os.path.join(ROOT, "include", "gvamp_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    lib = ctypes.CDLL(capi.XCHECK_LIB_PATH, mode=ctypes.RTLD_LOCAL)
+    assert all(hasattr(lib, n) for n in set(re.findall(r"\b(gvb_[a-zA-Z0-9_]+)\s*\(", hdr)))

@@ -25,8 +25,10 @@ def C():
 
 
 def make_ctx(C, gen):
+    """"lut": the product library.  "simple" / "lut1": the on-device cross-check kernels, which exist only in the test build of the
+    library (gvamp_b200/lib/xcheck/libgvamp_b200.so)."""
     os.environ["GVB_KERNELS"] = gen
-    return C.Context(0)
+    return C.Context(0, xcheck=gen in ("simple", "lut1"))
 
 
 @pytest.fixture(scope="module")
@@ -635,3 +637,14 @@ def test_fixed_point_dynamic_range_with_missing_genotypes(C, oracle):
         assert ctx.missing_list_entries() > 0
     ref = ds.ATx(u)
     assert relerr(atx, ref) < TOL_MATVEC and float(np.max(np.abs(atx - ref)) / np.max(np.abs(ref))) < TOL_MATVEC
+
+
+def test_product_library_refuses_cross_check_kernels(C, monkeypatch):
+    """GVB_KERNELS=simple|lut1 selects a kernel generation of the TEST build only; the product library fails loudly instead of
+    silently running something else."""
+    monkeypatch.setenv("GVB_KERNELS", "simple")
+    with pytest.raises(C.GvbError) as e:
+        C.Context(0)
+    assert "not part of the product library" in str(e.value)
+    monkeypatch.setenv("GVB_KERNELS", "lut")
+    C.Context(0).close()

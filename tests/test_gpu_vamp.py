@@ -15,6 +15,15 @@ EXE = os.path.join(ROOT, "gvamp_b200", "bin", "main_real")
 TOL_FINAL = 1e-4
 
 
+def _kernel_env(gen, extra=None):
+    """Environment of a driver run with kernel generation `gen`: the cross-check generations live in the test build of the library,
+    which the executables pick up through LD_LIBRARY_PATH (their RUNPATH to gvamp_b200/lib is searched after it)."""
+    env = dict(os.environ, GVB_KERNELS=gen, **(extra or {}))
+    if gen in ("simple", "lut1"):
+        env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "gvamp_b200", "lib", "xcheck") + ":" + env.get("LD_LIBRARY_PATH", "")
+    return env
+
+
 def _run_case(oracle, tmp_path, g, gen, env_extra=None):
     N, M, iters = int(g["N"]), int(g["M"]), int(g["iterations"])
     bed = oracle.synth_bed(int(g["seed"]), 0, M, N)
@@ -30,7 +39,7 @@ def _run_case(oracle, tmp_path, g, gen, env_extra=None):
     for k in range(0, len(extra), 2):
         if extra[k] not in skip:
             args += [extra[k], extra[k + 1]]
-    env = dict(os.environ, GVB_KERNELS=gen, **(env_extra or {}))
+    env = _kernel_env(gen, env_extra)
     r = subprocess.run([EXE] + args, capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return outd, r.stdout, iters
@@ -230,7 +239,7 @@ def test_probit_vamp_matches_reference_files(oracle, tmp_path, gen):
     for k in range(0, len(extra), 2):
         if extra[k] not in skip:
             args += [extra[k], extra[k + 1]]
-    r = subprocess.run([EXE_PROBIT] + args, capture_output=True, text=True, env=dict(os.environ, GVB_KERNELS=gen), timeout=600)
+    r = subprocess.run([EXE_PROBIT] + args, capture_output=True, text=True, env=_kernel_env(gen), timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert int(g["iterations_done"]) == iters
     for it in range(1, iters + 1):

@@ -17,7 +17,7 @@ void allreduce_sum(double* buf, int n);   // MPI_Allreduce(SUM) replacement, NCC
 }  // namespace gvb_host
 
 void initialize_prior(std::vector<double>& probs, std::vector<double>& vars, int N, int Mt, int rank);
-double generate_mixture_gaussians(int K_grp, std::vector<double> eta, std::vector<double> pi, long unsigned int seed = 1);
+double generate_mixture_gaussians(int K_grp, const std::vector<double>& eta, const std::vector<double>& pi, long unsigned int seed = 1);
 std::vector<double> simulate(int M, std::vector<double> eta, std::vector<double> pi, long unsigned int seed = 1);
 double noise_prec_calc(double SNR, std::vector<double> vars, std::vector<double> probs, int Mt, int N);
 

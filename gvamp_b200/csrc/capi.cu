@@ -92,6 +92,8 @@ static int ctx_common_init(gvb_ctx* c) {
     GVB_CUDA(gvb_malloc(c, &c->work_counter, sizeof(int) * 16));
     GVB_CUDA(cudaMemset(c->work_counter, 0, sizeof(int) * 16));
     GVB_CHECK(pick_kernel_gen(&c->kernel_gen));
+    const char* tabmode = getenv("GVB_TAB");   // "cpasync": tables staged by the producer warp's cp.async; default "tma": pair-interleaved tables, one bulk copy per pair
+    c->tab_pairs = (c->kernel_gen == 2 && !(tabmode && !strcmp(tabmode, "cpasync"))) ? 1 : 0;
     return GVB_OK;
 }
 

@@ -107,6 +107,9 @@ struct gvb_ctx {
     // sweep returns at once.  Set by the CG driver (cg.cu) around iterations it enqueues before it knows the solver has stopped.
     const int* skip = nullptr;
     double* scal = nullptr;         // small device scalars
+    // layout of the lookup tables in global memory (matvec_tile.cu): 0 = one 32 KB tile per step, [step][256 entries][32 slots]; 1 = the
+    // tiles of two consecutive steps interleaved, [pair][256][2][32], so that one TMA bulk copy fills a 64 KB table region ("pair" mode)
+    int tab_pairs = 0;
     int kernel_gen = 2;             // 0: simple FP64 kernels, 1: gen-1 table kernels, 2: gen-2 tile kernels (env GVB_KERNELS)
 
     // asynchronous device -> host snapshots of vectors (capi.cu): the iteration outputs leave over a copy stream while
@@ -184,6 +187,11 @@ void gvb_set_error(const char* fmt, ...);
     } while (0)
 
 static inline long gvb_roundup(long x, long m) { return (x + m - 1) / m * m; }
+
+// index of table entry (step, entry e, slot s) in the global table array, see gvb_ctx::tab_pairs
+__host__ __device__ static inline size_t gvb_tab_index(long step, int e, int s, int pairs) {
+    return pairs ? (((size_t)(step >> 1) * 256 + e) * 2 + (step & 1)) * 32 + s : ((size_t)step * 256 + e) * 32 + s;
+}
 
 // Frees every individual-major twin held on `device` (the one optional, re-creatable consumer of HBM: X.v then gathers from the one
 // matrix, bit-identical results); returns the number of twins released.  capi.cu keeps the registry of live contexts.

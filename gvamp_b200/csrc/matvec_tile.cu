@@ -192,9 +192,9 @@ __device__ __forceinline__ void release_work_counter(int* work_counter) {
 // MADK of the four accumulators take their additions as IMAD (fma pipe), the others as IADD3 (alu pipe, two lookups per
 // instruction): the alu pipe also carries the LOP3 / PRMT of every lookup and is the busiest unit of this kernel
 // TW: the words come from the individual-major twin (twin.cu): byte k IS the index of individual k, no gather
-template <int BUF, int MADK, bool TW>
-__device__ __forceinline__ void ax_consume(const char* __restrict__ tabc, uint32_t bb, const unsigned (&spack)[8], int one, int (&a32)[4]) {
-    const char* tb = tabc + BUF * 128;
+template <int MADK, bool TW>
+__device__ __forceinline__ void ax_consume(const char* __restrict__ tb, uint32_t bb, const unsigned (&spack)[8], int one, int (&a32)[4]) {
+    // tb: the step's table inside the table region -- a compile-time offset in the two-buffer form, a warp-uniform register in pair mode
 #pragma unroll
     for (int tau = 0; tau < 32; tau++) {
         const uint32_t w = lds32(bb ^ (uint32_t)(tau << 7));   // row tau ^ lane, column lane
@@ -288,7 +288,7 @@ ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, l
             mbar_wait(bar0 + 8 * s, (n_use / NS) & 1);                                       \
             n_use++;                                                                         \
             int a32[4] = {0, 0, 0, 0};                                                       \
-            ax_consume<B, MADK, TW>(smem, bed_sm + s * TILE_BYTES + lane_off, spack, one, a32); \
+            ax_consume<MADK, TW>(smem + B * 128, bed_sm + s * TILE_BYTES + lane_off, spack, one, a32); \
             _Pragma("unroll") for (int k = 0; k < 4; k++) acc64[k] += (long long)a32[k] << sh; \
         }                                                                                    \
         __syncwarp();                                                                        \
@@ -310,9 +310,8 @@ ax_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, l
 // ===================================================================================================
 //  X^T . u : warp = marker tile (32 groups), lane = marker group (4 markers), walk over the stripes of a chunk
 // ===================================================================================================
-template <int BUF, bool USE_MAD>
-__device__ __forceinline__ void atx_consume(const char* __restrict__ tabc, uint32_t bb, const unsigned (&spack)[8], int one, int (&a32)[4]) {
-    const char* tb = tabc + BUF * 128;
+template <bool USE_MAD>
+__device__ __forceinline__ void atx_consume(const char* __restrict__ tb, uint32_t bb, const unsigned (&spack)[8], int one, int (&a32)[4]) {
 #pragma unroll
     for (int tau = 0; tau < 32; tau++) {
         const uint32_t w = lds32(bb ^ (uint32_t)(tau << 2));   // row lane, column tau ^ lane
@@ -405,7 +404,7 @@ atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
             mbar_wait(bar0 + 8 * s, (n_use / NS) & 1);                                         \
             n_use++;                                                                           \
             int a32[4] = {0, 0, 0, 0};                                                         \
-            atx_consume<B, USE_MAD>(smem, bed_sm + s * TILE_BYTES + lane_off, spack, one, a32); \
+            atx_consume<USE_MAD>(smem + B * 128, bed_sm + s * TILE_BYTES + lane_off, spack, one, a32); \
             _Pragma("unroll") for (int q = 0; q < 4; q++) {                                    \
                 if (MODE == 0) {                                                               \
                     acc64[q] += (long long)a32[q] << sh;                                       \
@@ -432,6 +431,298 @@ atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
     release_work_counter(work_counter);
 }
 
+
+// ===================================================================================================
+//  Table staging by TMA ("pair" mode).  The producer warp of the kernels above moves every 32 KB table tile with 2048 cp.async of 16
+//  bytes: 256 shared-memory store wavefronts per step on the load/store pipe that is the limiter of both walks (measured: skipping the
+//  staging is worth 3.7 %), and two table buffers keep the consumer warps within one step of each other (dropping the barrier: +8 %).
+//  Here the tables of two consecutive steps are INTERLEAVED IN GLOBAL MEMORY the way the consumers address them in shared memory
+//  ([pair][256 entries][2 steps][32 slots], gvb_tab_index): one table region (64 KB = two steps) is a contiguous run that ONE
+//  cp.async.bulk fills -- no load/store-pipe traffic, one elected thread instead of a warp -- and two regions double-buffer PAIRS of
+//  steps, so a warp may run up to three steps ahead of the slowest one.  Shared memory: 128 KB of tables + NW x NS x 4 KB of bed tiles.
+// ===================================================================================================
+constexpr int PAIR_REGION = 65536;   // [256 entries][2 steps][32 slots] int32
+
+template <int NW, int NS>
+struct PairCfg {
+    static constexpr int THREADS = NW * 32 + 32;
+    static constexpr int SMEM = 2 * PAIR_REGION + NW * NS * TILE_BYTES + TILE_BYTES;
+};
+
+__device__ __forceinline__ void bulk_g2s_plain(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+struct PairPipe {
+    uint32_t full, empty;      // shared-memory addresses of full[2] / empty[2]
+    uint32_t fills0, fills1;   // how often region 0 / 1 has been filled since kernel start (uniform over the CTA)
+    template <int R>
+    __device__ __forceinline__ uint32_t& fills() { return R ? fills1 : fills0; }
+};
+__device__ __forceinline__ void pair_pipe_init(PairPipe& pp, unsigned long long* s_tab, int consumers) {
+    pp.full = smem_u32(&s_tab[0]);
+    pp.empty = smem_u32(&s_tab[2]);
+    pp.fills0 = pp.fills1 = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(pp.full, 1);
+        mbar_init(pp.full + 8, 1);
+        mbar_init(pp.empty, consumers);
+        mbar_init(pp.empty + 8, consumers);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+}
+// producer (one lane): the table pairs of a work item of n steps, regions alternating from 0; src = first pair of the item
+__device__ __forceinline__ void pair_produce_item(PairPipe& pp, uint32_t tab_sm, const int* __restrict__ src, int n, int lane) {
+    const int npairs = (n + 1) >> 1;
+    for (int p = 0; p < npairs; p++) {
+        const int r = p & 1;
+        uint32_t& f = r ? pp.fills1 : pp.fills0;
+        if (lane == 0) {
+            mbar_wait(pp.empty + 8 * r, (f & 1) ^ 1);   // a fresh barrier passes the wait for the phase "before the first"
+            mbar_expect_tx(pp.full + 8 * r, PAIR_REGION);
+            bulk_g2s_plain(tab_sm + r * PAIR_REGION, src + (long)p * (PAIR_REGION / 4), PAIR_REGION, pp.full + 8 * r);
+        }
+        f++;
+    }
+}
+
+
+// ---- pair mode addressing.  address = table region base (link-time constant, LDS immediate) + rgn * 65536 + entry * 256 + half * 128
+// + slot * 4, produced by ONE PRMT per lookup like in the two-buffer form: the per-lane slot registers hold three slot bytes and, in
+// byte 3, the region number; (half * 128) rides in bit 7 of every slot byte.  PRMT picks byte 0 = slot byte, byte 1 = index byte,
+// byte 2 = region byte, byte 3 = sign replication of the region byte (= 0).  One loop body serves every (region, half): after each step
+// the eleven slot registers are XORed with a constant (toggle bit 7 of the slot bytes; after an odd step also the region byte).
+__device__ __forceinline__ void make_spack3(unsigned (&sp)[11], int lane) {
+#pragma unroll
+    for (int j = 0; j < 11; j++) {
+        unsigned x = 0;
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+            if (3 * j + b < 32) x |= ((unsigned)((((3 * j + b) ^ lane) & 31) * 4)) << (8 * b);
+        sp[j] = x;
+    }
+}
+
+template <int MADK, bool TW>
+__device__ __forceinline__ void ax_consume_p(const char* __restrict__ tabc, uint32_t bb, const unsigned (&sp)[11], int one, int (&a32)[4]) {
+#pragma unroll
+    for (int tau = 0; tau < 32; tau++) {
+        const uint32_t w = lds32(bb ^ (uint32_t)(tau << 7));   // row tau ^ lane, column lane
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned prod = TW ? w : (w & (0x03030303u << (2 * k))) * (0x01041040u >> (2 * k));
+            const unsigned a = prmt(prod, sp[tau / 3], (TW ? (0xF700u | (k << 4)) : 0xF730u) | (4 + (tau % 3)));
+            const int val = *reinterpret_cast<const int*>(tabc + a);
+            a32[k] = (k >= 4 - MADK) ? mad_one(val, one, a32[k]) : a32[k] + val;
+        }
+    }
+}
+
+template <bool USE_MAD>
+__device__ __forceinline__ void atx_consume_p(const char* __restrict__ tabc, uint32_t bb, const unsigned (&sp)[11], int one, int (&a32)[4]) {
+#pragma unroll
+    for (int tau = 0; tau < 32; tau++) {
+        const uint32_t w = lds32(bb ^ (uint32_t)(tau << 2));   // row lane, column tau ^ lane
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const unsigned a = prmt(w, sp[tau / 3], 0xF700u | (q << 4) | (4 + (tau % 3)));
+            const int val = *reinterpret_cast<const int*>(tabc + a);
+            a32[q] = USE_MAD ? mad_one(val, one, a32[q]) : a32[q] + val;
+        }
+    }
+}
+
+// one step of a consumer warp in pair mode: step i of the item lives in region (i >> 1) & 1, half i & 1 (both carried by the slot
+// registers, see above: the loop body is the same code for every step, ~1200 instructions = 19 KB, inside the 32 KB L1.5 I-cache)
+#define PAIR_STEP(N_STEPS, CONSUME, FLUSH)                                                       \
+    {                                                                                            \
+        const int rgn = (i >> 1) & 1;                                                            \
+        issue_bed(i + NS - 1);                                                                   \
+        if ((i & 1) == 0) {                                                                      \
+            const uint32_t f = rgn ? pp.fills1 : pp.fills0;                                      \
+            mbar_wait(pp.full + 8 * rgn, f & 1);                                                 \
+            if (rgn) pp.fills1++; else pp.fills0++;                                              \
+        }                                                                                        \
+        const int sh = shifts ? __ldg(shifts + step_lo + i) : 0;                                 \
+        if (active) {                                                                            \
+            const uint32_t s = n_use % NS;                                                       \
+            mbar_wait(bar0 + 8 * s, (n_use / NS) & 1);                                           \
+            n_use++;                                                                             \
+            int a32[4] = {0, 0, 0, 0};                                                           \
+            CONSUME;                                                                             \
+            FLUSH;                                                                               \
+        }                                                                                        \
+        {                                                                                        \
+            const unsigned flip = (i & 1) ? 0x01808080u : 0x00808080u;                           \
+            _Pragma("unroll") for (int j = 0; j < 11; j++) sp[j] ^= flip;                        \
+        }                                                                                        \
+        if ((i & 1) || i == N_STEPS - 1) {                                                       \
+            __syncwarp();                                                                        \
+            if (lane == 0) mbar_arrive(pp.empty + 8 * rgn);                                      \
+        }                                                                                        \
+    }
+
+template <int NW, int NS, int MADK, bool TW>
+__global__ void __launch_bounds__(NW * 32 + 32, 1)
+ax_pair_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, long Mg_pad, long stripe0, long n_stripes, int n_sblocks, int n_gchunks,
+               int tiles_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out, int one, const int* __restrict__ skip,
+               const int* __restrict__ shifts) {
+    if (skip && *skip) return;
+    extern __shared__ __align__(1024) char smem[];
+    __shared__ int s_item;
+    __shared__ __align__(8) unsigned long long s_bar[NW * NS];
+    __shared__ __align__(8) unsigned long long s_tab[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool producer = warp == NW;
+    const uint32_t tab_sm = smem_u32(smem);
+    const uint32_t bed_sm = ((tab_sm + 2 * PAIR_REGION + 4095u) & ~4095u) + (producer ? 0 : warp) * (NS * TILE_BYTES);
+    const uint32_t bar0 = smem_u32(&s_bar[(producer ? 0 : warp) * NS]);
+    if (lane == 0 && !producer) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    PairPipe pp;
+    pair_pipe_init(pp, s_tab, NW);
+    const uint64_t pol = policy_evict_first();
+    unsigned sp[11];
+    const uint32_t lane_off = lane * 132;
+    uint32_t n_fill = 0, n_use = 0;
+    const int n_items = n_sblocks * n_gchunks;
+    const long n_tiles = Mg_pad / 32;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_items) break;
+        const int gc = item / n_sblocks, sb = item % n_sblocks;
+        const long step_lo = (long)gc * tiles_per_chunk;   // even: a chunk starts on a pair boundary
+        const int nt = (int)min((long)tiles_per_chunk, n_tiles - step_lo);
+        if (producer) {
+            pair_produce_item(pp, tab_sm, tabv + (step_lo >> 1) * (PAIR_REGION / 4), nt, lane);
+            continue;
+        }
+        const long t = stripe0 + (long)sb * NW + warp;
+        const bool active = (long)sb * NW + warp < n_stripes;
+        const uint32_t* bsrc = bed + ((active ? t : stripe0) * Mg_pad + step_lo * 32) * 32;
+        auto issue_bed = [&](int i) {
+            if (active && i < nt) {
+                if (lane == 0) {
+                    const uint32_t s = n_fill % NS;
+                    mbar_expect_tx(bar0 + 8 * s, TILE_BYTES);
+                    bulk_g2s(bed_sm + s * TILE_BYTES, bsrc + (long)i * TILE_WORDS, TILE_BYTES, bar0 + 8 * s, pol);
+                }
+                n_fill++;
+            }
+        };
+#pragma unroll
+        for (int s = 0; s < NS - 1; s++) issue_bed(s);
+        long long acc64[4] = {0, 0, 0, 0};
+        make_spack3(sp, lane);   // region 0, half 0
+#define AX_CONSUME ax_consume_p<MADK, TW>(smem, bed_sm + s * TILE_BYTES + lane_off, sp, one, a32)
+#define AX_FLUSH _Pragma("unroll") for (int k = 0; k < 4; k++) acc64[k] += (long long)a32[k] << sh
+#pragma unroll 1
+        for (int i = 0; i < nt; i++) PAIR_STEP(nt, AX_CONSUME, AX_FLUSH)
+#undef AX_CONSUME
+#undef AX_FLUSH
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (acc64[k] != 0) atomicAdd(acc_out + (t * 32 + lane) * 4 + k, (unsigned long long)acc64[k]);
+        }
+    }
+    release_work_counter(work_counter);
+}
+
+template <int NW, int NS, bool USE_MAD, int MODE>
+__global__ void __launch_bounds__(NW * 32 + 32, 1)
+atx_pair_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, long Mg_pad, long n_stripes, int n_gblocks, int n_schunks,
+                int stripes_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out, int one, const int* __restrict__ skip,
+                const int* __restrict__ shifts_in) {
+    if (skip && *skip) return;
+    extern __shared__ __align__(1024) char smem[];
+    __shared__ int s_item;
+    __shared__ __align__(8) unsigned long long s_bar[NW * NS];
+    __shared__ __align__(8) unsigned long long s_tab[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool producer = warp == NW;
+    const uint32_t tab_sm = smem_u32(smem);
+    const uint32_t bed_sm = ((tab_sm + 2 * PAIR_REGION + 4095u) & ~4095u) + (producer ? 0 : warp) * (NS * TILE_BYTES);
+    const uint32_t bar0 = smem_u32(&s_bar[(producer ? 0 : warp) * NS]);
+    if (lane == 0 && !producer) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    PairPipe pp;
+    pair_pipe_init(pp, s_tab, NW);
+    const uint64_t pol = policy_evict_first();
+    unsigned sp[11];
+    const uint32_t lane_off = lane * 132;
+    uint32_t n_fill = 0, n_use = 0;
+    const int n_items = n_gblocks * n_schunks;
+    const long n_tiles = Mg_pad / 32;
+    const int* shifts = MODE == 0 ? shifts_in : nullptr;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_items) break;
+        const int sc = item / n_gblocks, gb = item % n_gblocks;
+        const long step_lo = (long)sc * stripes_per_chunk;   // even
+        const int ns = (int)min((long)stripes_per_chunk, n_stripes - step_lo);
+        if (producer) {
+            pair_produce_item(pp, tab_sm, tab + (step_lo >> 1) * (PAIR_REGION / 4), ns, lane);
+            continue;
+        }
+        const long T = (long)gb * NW + warp;
+        const bool active = T < n_tiles;
+        const uint32_t* bsrc = bed + (step_lo * Mg_pad + (active ? T : 0) * 32) * 32;   // + i * Mg_pad * 32 words per stripe
+        auto issue_bed = [&](int i) {
+            if (active && i < ns) {
+                if (lane == 0) {
+                    const uint32_t s = n_fill % NS;
+                    mbar_expect_tx(bar0 + 8 * s, TILE_BYTES);
+                    bulk_g2s(bed_sm + s * TILE_BYTES, bsrc + (long)i * Mg_pad * 32, TILE_BYTES, bar0 + 8 * s, pol);
+                }
+                n_fill++;
+            }
+        };
+#pragma unroll
+        for (int s = 0; s < NS - 1; s++) issue_bed(s);
+        long long acc64[4] = {0, 0, 0, 0};
+        make_spack3(sp, lane);   // region 0, half 0
+#define ATX_CONSUME atx_consume_p<USE_MAD>(smem, bed_sm + s * TILE_BYTES + lane_off, sp, one, a32)
+#define ATX_FLUSH                                                                                              \
+    _Pragma("unroll") for (int q = 0; q < 4; q++) {                                                            \
+        if (MODE == 0) {                                                                                       \
+            acc64[q] += (long long)a32[q] << sh;                                                               \
+        } else {                                                                                               \
+            const unsigned a = (unsigned)a32[q];                                                               \
+            acc64[q] += (long long)((unsigned long long)(a & 0x3FFu) | ((unsigned long long)((a >> 10) & 0x3FFu) << 21) | \
+                                    ((unsigned long long)(a >> 20) << 42));                                    \
+        }                                                                                                      \
+    }
+#pragma unroll 1
+        for (int i = 0; i < ns; i++) PAIR_STEP(ns, ATX_CONSUME, ATX_FLUSH)
+#undef ATX_CONSUME
+#undef ATX_FLUSH
+        if (active) {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (acc64[q] != 0) atomicAdd(acc_out + (T * 32 + lane) * 4 + q, (unsigned long long)acc64[q]);
+        }
+    }
+    release_work_counter(work_counter);
+}
+#undef PAIR_STEP
+
 struct TileTune {
     int variant;   // 0: 15 consumer warps x 2 stages, 1: 12 consumer warps x 3 stages (+ the producer warp)
     int use_mad;   // X.v: accumulators (0..4) fed by IMAD instead of IADD3; X^T.u: 4 -> all four, else none
@@ -453,9 +744,10 @@ TileTune tune() { return tune_from_env(); }
 // steps (tiles of X.v / stripes of X^T.u) per work item: long enough to amortise the pipeline fill and to let the CTAs
 // of a wave share table tiles in L2 (<= 64), short enough that a small matrix still yields >= 4 items per SM
 int pick_chunk(int requested, long rows, long steps, int sm_count) {
-    if (requested > 0) return requested;
+    if (requested > 0) return requested + (requested & 1);   // even: a chunk starts on a pair boundary of the tables
     long per = (rows * steps + 4l * sm_count - 1) / (4l * sm_count);
-    return (int)std::max(4l, std::min(64l, per));
+    per = std::max(4l, std::min(64l, per));
+    return (int)(per + (per & 1));
 }   // read per launch: the tests vary the chunking within one process
 
 template <int NW, int NS, int MADK, bool TW>
@@ -475,6 +767,46 @@ int launch_ax(gvb_ctx* c, unsigned long long* accN, long stripe0, long n_stripes
     int grid = std::min(n_sblocks * n_gchunks, c->sm_count);
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(TW ? c->bed_twin : c->bed, c->tab_v, c->Mg_pad, stripe0, n_stripes, n_sblocks, n_gchunks, tpc, c->work_counter,
                                                        accN, 1, c->skip, c->shift_v);
+    GVB_LAUNCHED(c);
+    return GVB_OK;
+}
+
+template <int NW, int NS, int MADK, bool TW>
+int launch_ax_pair(gvb_ctx* c, unsigned long long* accN, long stripe0, long n_stripes) {
+    using Cfg = PairCfg<NW, NS>;
+    auto kern = ax_pair_kernel<NW, NS, MADK, TW>;
+    static unsigned long long attr_done = 0;
+    if (!(attr_done >> (c->device & 63) & 1ull)) {
+        GVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        attr_done |= 1ull << (c->device & 63);
+    }
+    if (n_stripes <= 0) return GVB_OK;
+    const long n_tiles = c->Mg_pad / 32;
+    int n_sblocks = (int)((n_stripes + NW - 1) / NW);
+    const int tpc = pick_chunk(tune().ax_tiles_per_chunk, n_sblocks, n_tiles, c->sm_count);
+    int n_gchunks = (int)((n_tiles + tpc - 1) / tpc);
+    int grid = std::min(n_sblocks * n_gchunks, c->sm_count);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(TW ? c->bed_twin : c->bed, c->tab_v, c->Mg_pad, stripe0, n_stripes, n_sblocks, n_gchunks, tpc, c->work_counter,
+                                                       accN, 1, c->skip, c->shift_v);
+    GVB_LAUNCHED(c);
+    return GVB_OK;
+}
+
+template <int NW, int NS, bool USE_MAD, int MODE>
+int launch_atx_pair(gvb_ctx* c, const int* tab, unsigned long long* acc, const int* shifts) {
+    using Cfg = PairCfg<NW, NS>;
+    auto kern = atx_pair_kernel<NW, NS, USE_MAD, MODE>;
+    static unsigned long long attr_done = 0;
+    if (!(attr_done >> (c->device & 63) & 1ull)) {
+        GVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        attr_done |= 1ull << (c->device & 63);
+    }
+    const long n_tiles = c->Mg_pad / 32;
+    int n_gblocks = (int)((n_tiles + NW - 1) / NW);
+    const int spc = pick_chunk(tune().atx_stripes_per_chunk, n_gblocks, c->n_stripes, c->sm_count);
+    int n_schunks = (int)((c->n_stripes + spc - 1) / spc);
+    int grid = std::min(n_gblocks * n_schunks, c->sm_count);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(c->bed, tab, c->Mg_pad, c->n_stripes, n_gblocks, n_schunks, spc, c->work_counter, acc, 1, c->skip, shifts);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }
@@ -590,7 +922,7 @@ __global__ void __launch_bounds__(128) ax_prep_kernel(const double* __restrict__
 // Q_j(c) = rint(val_j(c) * scale), val_j(00) = (2-mu) w, val_j(10) = (1-mu) w, val_j(11) = -mu w, val_j(missing) = 0
 __global__ void __launch_bounds__(256) ax_build_kernel(const double* __restrict__ v, const double* __restrict__ mave, const double* __restrict__ msig,
                                                        double* __restrict__ scal, int* __restrict__ tabv, int mode, const int* __restrict__ skip,
-                                                       int* __restrict__ shifts) {
+                                                       int* __restrict__ shifts, int pairs) {
     if (skip && *skip) return;
     __shared__ int Qs[4][4][32];   // [q][code][slot]: a warp reads one (q, code) row -> conflict free
     __shared__ double s_scale;
@@ -631,10 +963,9 @@ __global__ void __launch_bounds__(256) ax_build_kernel(const double* __restrict_
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int* dst = tabv + T * 8192 + lane;
 #pragma unroll 4
     for (int e = warp; e < 256; e += 8)
-        dst[e * 32] = Qs[0][e & 3][lane] + Qs[1][(e >> 2) & 3][lane] + Qs[2][(e >> 4) & 3][lane] + Qs[3][e >> 6][lane];
+        tabv[gvb_tab_index(T, e, lane, pairs)] = Qs[0][e & 3][lane] + Qs[1][(e >> 2) & 3][lane] + Qs[2][(e >> 4) & 3][lane] + Qs[3][e >> 6][lane];
 }
 
 // out[i] = present_i ? acc_i / scale / sqrt(N) : 0   (the mask m_i of data.cpp:972; pads are never present)
@@ -675,7 +1006,7 @@ __global__ void __launch_bounds__(256) atx_prep_kernel(const double* __restrict_
 // tabm (shards with missing genotypes) holds the same sum over the MISSING codes with weight 1; accumulates sum_i U_i
 __global__ void __launch_bounds__(256) atx_build_kernel(const double* __restrict__ u, double window, double* __restrict__ scal, int* __restrict__ tab,
                                                         int* __restrict__ tabm, long long* __restrict__ usum, int* __restrict__ uq, const int* __restrict__ skip,
-                                                        int* __restrict__ shifts) {
+                                                        int* __restrict__ shifts, int pairs) {
     if (skip && *skip) return;
     __shared__ int Us[4][32];   // [k][position]
     __shared__ double s_scale, s_scale0;
@@ -720,13 +1051,12 @@ __global__ void __launch_bounds__(256) atx_build_kernel(const double* __restrict
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int U0 = Us[0][lane], U1 = Us[1][lane], U2 = Us[2][lane], U3 = Us[3][lane];
-    int* dst = tab + t * 8192 + lane;
-    int* dstm = tabm ? tabm + t * 8192 + lane : nullptr;
 #pragma unroll 4
     for (int B = warp; B < 256; B += 8) {
         const unsigned c0 = B & 3, c1 = (B >> 2) & 3, c2 = (B >> 4) & 3, c3 = B >> 6;
-        dst[B * 32] = dosage_of(c0) * U0 + dosage_of(c1) * U1 + dosage_of(c2) * U2 + dosage_of(c3) * U3;
-        if (dstm) dstm[B * 32] = (c0 == 1u ? U0 : 0) + (c1 == 1u ? U1 : 0) + (c2 == 1u ? U2 : 0) + (c3 == 1u ? U3 : 0);
+        const size_t at = gvb_tab_index(t, B, lane, pairs);
+        tab[at] = dosage_of(c0) * U0 + dosage_of(c1) * U1 + dosage_of(c2) * U2 + dosage_of(c3) * U3;
+        if (tabm) tabm[at] = (c0 == 1u ? U0 : 0) + (c1 == 1u ? U1 : 0) + (c2 == 1u ? U2 : 0) + (c3 == 1u ? U3 : 0);
     }
 }
 
@@ -753,7 +1083,7 @@ __global__ void atx_finish_kernel(const unsigned long long* __restrict__ acc, co
 
 int ensure_scratch(gvb_ctx* c, bool need_tab_u, bool need_tab_v, bool miss) {
     if (need_tab_u) {
-        const size_t tab_ints = (size_t)c->n_stripes * 8192 * (miss ? 2 : 1);
+        const size_t tab_ints = (size_t)gvb_roundup(c->n_stripes, 2) * 8192 * (miss ? 2 : 1);   // whole pairs of steps
         if (c->tab_u_cap < tab_ints) {
             if (c->tab_u) cudaFree(c->tab_u);
             c->tab_u = nullptr;
@@ -762,7 +1092,7 @@ int ensure_scratch(gvb_ctx* c, bool need_tab_u, bool need_tab_v, bool miss) {
         }
     }
     if (need_tab_v) {
-        const size_t tab_ints = (size_t)(c->Mg_pad / 32) * 8192;
+        const size_t tab_ints = (size_t)gvb_roundup(c->Mg_pad / 32, 2) * 8192;
         if (c->tab_v_cap < tab_ints) {
             if (c->tab_v) cudaFree(c->tab_v);
             c->tab_v = nullptr;
@@ -790,6 +1120,7 @@ int ensure_scratch(gvb_ctx* c, bool need_tab_u, bool need_tab_v, bool miss) {
 }
 
 int ax_gather(gvb_ctx* c, unsigned long long* accN, const TileTune& t, long stripe0, long n) {
+    if (c->tab_pairs) return t.use_mad ? launch_ax_pair<11, 2, 1, false>(c, accN, stripe0, n) : launch_ax_pair<11, 2, 0, false>(c, accN, stripe0, n);
     if (t.variant == 1) return t.use_mad ? launch_ax<12, 3, 4, false>(c, accN, stripe0, n) : launch_ax<12, 3, 0, false>(c, accN, stripe0, n);
     switch (t.use_mad) {
         case 0: return launch_ax<15, 2, 0, false>(c, accN, stripe0, n);
@@ -808,7 +1139,9 @@ int ax_main(gvb_ctx* c, unsigned long long* accN) {
     const bool want_twin = !(tw && !strcmp(tw, "0"));
     if (want_twin && c->twin_state == 0) GVB_CHECK(gvb_twin_build(c));
     long T = (want_twin && c->twin_state > 0) ? c->twin_stripes : 0;
-    if (T > 0) {
+    if (T > 0 && c->tab_pairs) {
+        GVB_CHECK((t.twin_mad > 0 ? launch_ax_pair<11, 2, 1, true>(c, accN, 0, T) : launch_ax_pair<11, 2, 0, true>(c, accN, 0, T)));
+    } else if (T > 0) {
         if (t.variant == 1)
             GVB_CHECK((launch_ax<12, 3, 0, true>(c, accN, 0, T)));
         else
@@ -819,6 +1152,7 @@ int ax_main(gvb_ctx* c, unsigned long long* accN) {
 
 int atx_main(gvb_ctx* c, const int* tab, unsigned long long* acc) {
     const TileTune t = tune();
+    if (c->tab_pairs) return t.use_mad >= 4 ? launch_atx_pair<11, 2, true, 0>(c, tab, acc, c->shift_u) : launch_atx_pair<11, 2, false, 0>(c, tab, acc, c->shift_u);
     if (t.variant == 1) return t.use_mad >= 4 ? launch_atx<12, 3, true, 0>(c, tab, acc, c->shift_u) : launch_atx<12, 3, false, 0>(c, tab, acc, c->shift_u);
     return t.use_mad >= 4 ? launch_atx<15, 2, true, 0>(c, tab, acc, c->shift_u) : launch_atx<15, 2, false, 0>(c, tab, acc, c->shift_u);
 }
@@ -833,7 +1167,7 @@ int gvb_ax_tile(gvb_ctx* c, const double* v, double* out, int mode) {
     unsigned long long* accN = c->acc_i64 + 2 * (size_t)c->Mg_pad * 4;
     ax_prep_kernel<<<(unsigned)n_tiles, 128, 0, c->stream>>>(v, c->mave, c->msig, c->scal, accN, c->Npad, mode, c->skip);
     GVB_LAUNCHED(c);
-    ax_build_kernel<<<(unsigned)n_tiles, 256, 0, c->stream>>>(v, c->mave, c->msig, c->scal, c->tab_v, mode, c->skip, c->shift_v);
+    ax_build_kernel<<<(unsigned)n_tiles, 256, 0, c->stream>>>(v, c->mave, c->msig, c->scal, c->tab_v, mode, c->skip, c->shift_v, c->tab_pairs);
     GVB_LAUNCHED(c);
     GVB_CHECK(ax_main(c, accN));
     ax_finish_kernel<<<(unsigned)((c->Npad + 255) / 256), 256, 0, c->stream>>>(accN, c->scal, c->maskw, c->Npad,
@@ -851,7 +1185,7 @@ int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB) {
     const bool list = miss && c->miss_state == 1;
     GVB_CHECK(ensure_scratch(c, true, false, miss && !list));
     const size_t Mpad = (size_t)c->Mg_pad * 4;
-    const long npos = c->n_stripes * 32, total = c->n_stripes * 8192;
+    const long npos = c->n_stripes * 32, total = gvb_roundup(c->n_stripes, 2) * 8192;
     unsigned long long* acc = c->acc_i64;
     unsigned long long* accm = c->acc_i64 + Mpad;
     long long* usum = reinterpret_cast<long long*>(c->acc_i64 + 2 * Mpad + c->Npad);
@@ -859,7 +1193,7 @@ int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB) {
     atx_prep_kernel<<<nb, 256, 0, c->stream>>>(u, npos, c->scal, acc, (long)((miss ? 2 : 1) * Mpad), usum, c->skip);
     GVB_LAUNCHED(c);
     atx_build_kernel<<<(unsigned)c->n_stripes, 256, 0, c->stream>>>(u, 32.0, c->scal, c->tab_u, (miss && !list) ? c->tab_u + total : nullptr, usum,
-                                                                    list ? c->uq : nullptr, c->skip, c->shift_u);
+                                                                    list ? c->uq : nullptr, c->skip, c->shift_u, c->tab_pairs);
     GVB_LAUNCHED(c);
     GVB_CHECK(atx_main(c, c->tab_u, acc));
     if (list)
@@ -875,6 +1209,7 @@ int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB) {
 // the table walk of X^T.u with packed counters (MODE 1): acc[j] = n00 | n10 << 21 | n11 << 42 over the individuals the table weights
 int gvb_count_tile_main(gvb_ctx* c, const int* tab, unsigned long long* acc) {
     const TileTune t = tune();
+    if (c->tab_pairs) return launch_atx_pair<11, 2, false, 1>(c, tab, acc, nullptr);
     if (t.variant == 1) return launch_atx<12, 3, false, 1>(c, tab, acc, nullptr);
     return launch_atx<15, 2, false, 1>(c, tab, acc, nullptr);
 }

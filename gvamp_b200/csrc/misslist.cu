@@ -16,6 +16,14 @@
 //     the groups with 8-byte loads, gather four U's from shared memory each, and a warp reduction per segment
 //     ends in one int64 RED on the marker's accumulator.
 //
+// Bank-aware order inside a segment.  The gather's cost is shared-memory bank conflicts: 32 lanes reading 32 random words of U land
+// 3.5 deep on the busiest bank on average (round 1, ncu: 201 M wavefronts for 54 M requests).  The bank of an entry is its
+// individual's index mod 32 -- known when the list is built -- so the fill kernel writes every segment in an order that deals the
+// banks out evenly over the gather's instructions: a segment is padded to whole passes of 128 entries (32 lanes x 4 entries, one
+// 8-byte group per lane), its entries are ranked by bank, and rank s goes to instruction row (s mod R) of lane (s div R), R = 4 x
+// passes.  The 32 lanes of one LDS then hold ranks R apart in bank order, i.e. (almost always) 32 different banks; the padding
+// (sentinels that all read the one zero word: a broadcast) costs ~17 % more index bytes at 1 % missing.
+//
 // Cost per sweep: 2 bytes per missing genotype (config 5 per GPU: 8.4 GB next to the 105 GB bed) instead of a
 // second 105 GB walk.  Everything is integer, so the result is bit-identical to the two-pass form (tests).
 // If the list does not fit in HBM the sweep falls back to the second walk (ctx->miss_state = -1).
@@ -54,11 +62,14 @@ __global__ void __launch_bounds__(256) miss_count_kernel(const uint32_t* __restr
         int x = cnt[q];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) seg_groups[b * (Mg_pad * 4) + g * 4 + q] = (g * 4 + q < M) ? (unsigned long long)((x + 3) >> 2) : 0ull;
+        // whole passes of 32 groups (128 entries), see "Bank-aware order"
+        if (lane == 0) seg_groups[b * (Mg_pad * 4) + g * 4 + q] = (g * 4 + q < M) ? (unsigned long long)(32 * ((x + 127) >> 7)) : 0ull;
     }
 }
 
-// pass 2: the indices.  Same walk; the order of the entries inside a segment is irrelevant (integer sum).
+// pass 2: the indices, in the bank-aware order.  Same walk, done twice by the same warp: first the per-lane counts of every (marker q,
+// individual k of the byte position) -- an entry's bank is (4 lane + k) mod 32 -- from which every lane derives the rank of its first
+// entry of each kind in the segment's bank-sorted order; then the entries themselves.
 __global__ void __launch_bounds__(256) miss_fill_kernel(const uint32_t* __restrict__ bed, const uint32_t* __restrict__ validw, long M, long Mg,
                                                         long Mg_pad, long n_stripes, const unsigned long long* __restrict__ seg_off,
                                                         uint16_t* __restrict__ idx) {
@@ -67,33 +78,80 @@ __global__ void __launch_bounds__(256) miss_fill_kernel(const uint32_t* __restri
     const long b = blockIdx.y;
     if (g >= Mg) return;
     const long t0 = b * MISS_BLOCK_STRIPES, t1 = min(n_stripes, t0 + MISS_BLOCK_STRIPES);
-    const unsigned lt = (1u << lane) - 1u;
-    unsigned long long cur[4], end[4];
+    unsigned long long seg_lo[4];
+    unsigned rows[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const long seg = b * (Mg_pad * 4) + g * 4 + q;
-        cur[q] = seg_off[seg] * 4ull;
-        end[q] = seg_off[seg + 1] * 4ull;
+        seg_lo[q] = seg_off[seg] * 4ull;
+        const unsigned long long seg_hi = seg_off[seg + 1] * 4ull;
+        rows[q] = (unsigned)((seg_hi - seg_lo[q]) >> 5);                       // entries / 32 = instruction rows of the gather
+        for (unsigned long long p = seg_lo[q] + lane; p < seg_hi; p += 32) idx[p] = (uint16_t)MISS_SENTINEL;
     }
+    __syncwarp();
+    // ---- counts per (q, k) of this lane
+    unsigned cnt[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) cnt[q][k] = 0;
     for (long t = t0; t < t1; t++) {
         const uint32_t m = missing_bits(bed[(t * Mg_pad + g) * 32 + lane], validw[t * 32 + lane]);
-        if (!__any_sync(0xffffffffu, m != 0u)) continue;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) cnt[q][k] += (m >> (8 * q + 2 * k)) & 1u;
+    }
+    // ---- rank of this lane's first (q, k) entry: banks in the order beta = 4 (lane & 7) + k; within a bank the four lanes that share
+    // (lane & 7) in the order of lane >> 3
+    unsigned base[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        unsigned before_in_lane_group = 0;   // sum over k' < k of the bank totals of this lane's (lane & 7)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned own = cnt[q][k];
+            const unsigned a8 = __shfl_xor_sync(0xffffffffu, own, 8);
+            const unsigned s1 = own + a8;
+            const unsigned a16 = __shfl_xor_sync(0xffffffffu, s1, 16);
+            const unsigned bank_tot = s1 + a16;                                  // all four lanes of this bank
+            // entries of the same bank held by lanes with a smaller lane >> 3
+            unsigned prior = 0;
+            if (lane & 8) prior += a8;                                           // lane ^ 8 has the smaller lane >> 3
+            if (lane & 16) prior += a16;                                         // both lanes of the lower half (lane ^ 16, lane ^ 24)
+            base[q][k] = before_in_lane_group + prior;
+            before_in_lane_group += bank_tot;
+        }
+        // exclusive prefix over the eight bank groups (lane & 7): every lane of group m adds the totals of groups m' < m
+        const unsigned group_tot = before_in_lane_group;
+        unsigned incl = group_tot;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const unsigned up = __shfl_up_sync(0xffffffffu, incl, o, 8);
+            if ((lane & 7) >= o) incl += up;
+        }
+        const unsigned excl = incl - group_tot;
+#pragma unroll
+        for (int k = 0; k < 4; k++) base[q][k] += excl;
+    }
+    // ---- the entries
+    for (long t = t0; t < t1; t++) {
+        const uint32_t m = missing_bits(bed[(t * Mg_pad + g) * 32 + lane], validw[t * 32 + lane]);
+        if (m == 0u) continue;
         const unsigned local = (unsigned)((t - t0) * 32 + lane) * 4u;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             if (g * 4 + q >= M) continue;   // padded markers carry the pad byte (all "missing"): not part of the shard
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const bool hit = (m >> (8 * q + 2 * k)) & 1u;
-                const unsigned bal = __ballot_sync(0xffffffffu, hit);
-                if (hit) idx[cur[q] + __popc(bal & lt)] = (uint16_t)(local + k);
-                cur[q] += __popc(bal);
+                if ((m >> (8 * q + 2 * k)) & 1u) {
+                    const unsigned s = base[q][k]++;
+                    const unsigned R = rows[q], row = s % R, ln = s / R;       // s < 32 R: the segment holds every entry
+                    idx[seg_lo[q] + 128u * (row >> 2) + 4u * ln + (row & 3u)] = (uint16_t)(local + k);
+                }
             }
         }
     }
-#pragma unroll
-    for (int q = 0; q < 4; q++)
-        if (cur[q] + lane < end[q]) idx[cur[q] + lane] = (uint16_t)MISS_SENTINEL;   // < 4 padding entries per segment
 }
 
 // accm[j] += sum over the missing individuals i of marker j of U_i.  Persistent CTAs; a CTA owns a contiguous run
@@ -279,8 +337,10 @@ int gvb_misslist_sum(gvb_ctx* c, unsigned long long* accm) {
     const long Mpad = c->Mg_pad * 4;
     const long n_items = c->miss_nblk * (Mpad / 32);
     const int grid = (int)std::max(1l, std::min(n_items, (long)c->sm_count));
-    const char* form = getenv("GVB_MISS_SUM");   // "warp": one warp per segment (the round-1 form, kept as a cross-check); default: one lane per marker
-    if (form && !strcmp(form, "warp"))
+    // default: one warp per segment -- the form whose instruction rows the bank-aware order of the list is built for; "lane": one lane
+    // per marker (measured equal to the round-1 warp form at 1 % missing; kept as a cross-check of the list's content)
+    const char* form = getenv("GVB_MISS_SUM");
+    if (!(form && !strcmp(form, "lane")))
         miss_sum_kernel<<<grid, MISS_THREADS, MISS_SMEM, c->stream>>>(c->miss_idx, c->miss_off, c->uq, c->Npad, Mpad, n_items, accm, c->skip);
     else
         miss_sum_lane_kernel<<<grid, MISS_THREADS, MISS_SMEM, c->stream>>>(c->miss_idx, c->miss_off, c->uq, c->Npad, Mpad, n_items, accm, c->skip);

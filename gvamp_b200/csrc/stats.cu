@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) counts_kernel(const uint32_t* __restrict_
 // ---- gen 2: the counts as a table walk (matvec_tile.cu, MODE 1) -------------------------------------------------
 // tab[(t*256 + B)*32 + l] = sum over the individuals k of position p = 32t+l that the weight word selects of
 // 1 << (10 * class(code_k(B))), class 00 -> 0, 10 -> 1, 11 -> 2; the missing code adds nothing (n01 follows from the total)
-__global__ void __launch_bounds__(256) count_table_kernel(const uint32_t* __restrict__ weightw, long n_stripes, int* __restrict__ tab) {
+__global__ void __launch_bounds__(256) count_table_kernel(const uint32_t* __restrict__ weightw, long n_stripes, int* __restrict__ tab, int pairs) {
     long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (idx >= n_stripes * 8192) return;
     int l = (int)(idx & 31);
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) count_table_kernel(const uint32_t* __rest
         bool present = (mw >> (2 * k)) & 1u;
         if (present && code != 1u) e += 1 << (10 * (code == 0u ? 0 : (code == 2u ? 1 : 2)));
     }
-    tab[idx] = e;
+    tab[gvb_tab_index(t, (int)B, l, pairs)] = e;
 }
 
 // packed n00 | n10 << 21 | n11 << 42 -> counts[j*8 + base + {0,1,2,3}] = n00, n01, n10, n11 (n01 = total - the rest)
@@ -90,7 +90,7 @@ __global__ void unpack_counts_kernel(const unsigned long long* __restrict__ pack
 }
 
 static int counts_tile_run(gvb_ctx* c) {
-    const size_t tab_ints = (size_t)c->n_stripes * 8192;
+    const size_t tab_ints = (size_t)gvb_roundup(c->n_stripes, 2) * 8192;   // whole pairs of steps (pair mode)
     if (c->tab_u_cap < tab_ints) {
         if (c->tab_u) cudaFree(c->tab_u);
         c->tab_u = nullptr;
@@ -109,7 +109,7 @@ static int counts_tile_run(gvb_ctx* c) {
     const bool same = c->mask_present == c->N;
     for (int pass = 0; pass < (same ? 1 : 2); pass++) {
         GVB_CUDA(cudaMemsetAsync(c->acc_i64, 0, Mpad * sizeof(unsigned long long), c->stream));
-        count_table_kernel<<<(unsigned)((tab_ints + 255) / 256), 256, 0, c->stream>>>(pass == 0 ? c->maskw : c->validw, c->n_stripes, c->tab_u);
+        count_table_kernel<<<(unsigned)((tab_ints + 255) / 256), 256, 0, c->stream>>>(pass == 0 ? c->maskw : c->validw, c->n_stripes, c->tab_u, c->tab_pairs);
         GVB_LAUNCHED(c);
         GVB_CHECK(gvb_count_tile_main(c, c->tab_u, c->acc_i64));
         unpack_counts_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, c->stream>>>(c->acc_i64, (long)Mpad, pass == 0 ? c->mask_present : c->N, pass == 0 ? 0 : 4,

@@ -92,8 +92,7 @@ static int ctx_common_init(gvb_ctx* c) {
     GVB_CUDA(gvb_malloc(c, &c->work_counter, sizeof(int) * 16));
     GVB_CUDA(cudaMemset(c->work_counter, 0, sizeof(int) * 16));
     GVB_CHECK(pick_kernel_gen(&c->kernel_gen));
-    const char* tabmode = getenv("GVB_TAB");   // "cpasync": tables staged by the producer warp's cp.async; default "tma": pair-interleaved tables, one bulk copy per pair
-    c->tab_pairs = (c->kernel_gen == 2 && !(tabmode && !strcmp(tabmode, "cpasync"))) ? 1 : 0;
+    c->tab_pairs = c->kernel_gen == 2 ? 1 : 0;   // the tile kernels' tables are pair-interleaved in global memory (matvec_tile.cu)
     return GVB_OK;
 }
 

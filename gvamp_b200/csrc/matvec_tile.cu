@@ -139,11 +139,13 @@ __device__ __forceinline__ void make_spack(unsigned (&spack)[8], int lane) {
     }
 }
 
-// producer warp: table tile (32 KB, contiguous in global) -> interleaved buffer `buf` of the table region, 64 x 16 bytes per lane
+// producer warp: table tile of one step -> interleaved buffer `buf` of the table region, 64 x 16 bytes per lane.  In global memory the
+// tiles of two consecutive steps are interleaved the same way ([pair][256 entries][2 steps][32 slots], gvb_tab_index): `src` points
+// at the step's half of entry 0, entries are 64 ints apart
 __device__ __forceinline__ void stage_table(uint32_t tab_sm, int buf, const int* __restrict__ src, int lane) {
     const uint32_t dst = tab_sm + buf * 128;
 #pragma unroll 8
-    for (int c = lane; c < 2048; c += 32) cp_async16(dst + (c >> 3) * 256 + (c & 7) * 16, src + c * 4);
+    for (int c = lane; c < 2048; c += 32) cp_async16(dst + (c >> 3) * 256 + (c & 7) * 16, src + (c >> 3) * 64 + (c & 7) * 4);
 }
 __device__ __forceinline__ void tab_pipe_init(TabPipe& tp, unsigned long long* s_tab, int consumers) {
     tp.full = smem_u32(&s_tab[0]);
@@ -165,11 +167,11 @@ __device__ __forceinline__ void tab_produce(TabPipe& tp, uint32_t tab_sm, const 
     cp_async_arrive_on(tp.full + 8 * B);
     tp.fills<B>()++;
 }
-// producer warp: the tables of the n steps of a work item, buffers alternating from 0
+// producer warp: the tables of the n steps of a work item (it starts on a pair boundary), buffers alternating from 0
 __device__ __forceinline__ void tab_produce_item(TabPipe& tp, uint32_t tab_sm, const int* __restrict__ src, int n, int lane) {
     for (int i = 0; i < n; i += 2) {
-        tab_produce<0>(tp, tab_sm, src + (long)i * 8192, lane);
-        if (i + 1 < n) tab_produce<1>(tp, tab_sm, src + (long)(i + 1) * 8192, lane);
+        tab_produce<0>(tp, tab_sm, src + (long)i * 8192, lane);               // pair i/2, half 0
+        if (i + 1 < n) tab_produce<1>(tp, tab_sm, src + (long)i * 8192 + 32, lane);   // pair i/2, half 1
     }
 }
 
@@ -723,7 +725,15 @@ atx_pair_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
 }
 #undef PAIR_STEP
 
+// measured defaults (profiles/r02_sweep_tuning.txt)
+#define GVB_DEFAULT_TMA_WALK 1
+#define GVB_DEFAULT_TMA_GATHER 0
+#define GVB_DEFAULT_PAIR_SHAPE 0
+
 struct TileTune {
+    int tma_walk;    // X^T.u and X.v on the twin: 1 = pair mode (tables by TMA bulk copy), 0 = producer-warp cp.async (two 32 KB buffers)
+    int tma_gather;  // the gathering X.v kernel, likewise
+    int pair_shape;  // pair mode: 0 = 11 consumer warps x 2 bed stages, 1 = 7 x 3, 2 = 5 x 4 (128 KB of tables leave room for 23 bed tiles)
     int variant;   // 0: 15 consumer warps x 2 stages, 1: 12 consumer warps x 3 stages (+ the producer warp)
     int use_mad;   // X.v: accumulators (0..4) fed by IMAD instead of IADD3; X^T.u: 4 -> all four, else none
     int ax_tiles_per_chunk, atx_stripes_per_chunk;
@@ -731,7 +741,10 @@ struct TileTune {
 };
 
 TileTune tune_from_env() {
-    TileTune t{0, 1, 0, 0, 0};   // one IMAD-fed accumulator measured best for X.v on B200 (5.30 vs 5.17 TB/s with none)   // chunk lengths 0: chosen per launch from the problem size (pick_chunk)
+    TileTune t{GVB_DEFAULT_TMA_WALK, GVB_DEFAULT_TMA_GATHER, GVB_DEFAULT_PAIR_SHAPE, 0, 1, 0, 0, 0};   // one IMAD-fed accumulator measured best for X.v on B200 (5.30 vs 5.17 TB/s with none)   // chunk lengths 0: chosen per launch from the problem size (pick_chunk)
+    if (const char* e = getenv("GVB_TAB")) t.tma_walk = t.tma_gather = strcmp(e, "cpasync") != 0;
+    if (const char* e = getenv("GVB_GATHER_TAB")) t.tma_gather = strcmp(e, "cpasync") != 0;
+    if (const char* e = getenv("GVB_PAIR_SHAPE")) t.pair_shape = std::max(0, std::min(2, atoi(e)));
     if (const char* e = getenv("GVB_TILE_VARIANT")) t.variant = atoi(e);
     if (const char* e = getenv("GVB_TILE_MAD")) t.use_mad = std::max(0, std::min(4, atoi(e)));
     if (const char* e = getenv("GVB_TWIN_MAD")) t.twin_mad = atoi(e);
@@ -1120,7 +1133,13 @@ int ensure_scratch(gvb_ctx* c, bool need_tab_u, bool need_tab_v, bool miss) {
 }
 
 int ax_gather(gvb_ctx* c, unsigned long long* accN, const TileTune& t, long stripe0, long n) {
-    if (c->tab_pairs) return t.use_mad ? launch_ax_pair<11, 2, 1, false>(c, accN, stripe0, n) : launch_ax_pair<11, 2, 0, false>(c, accN, stripe0, n);
+    if (t.tma_gather) {
+        switch (t.pair_shape) {
+            case 1: return t.use_mad ? launch_ax_pair<7, 3, 1, false>(c, accN, stripe0, n) : launch_ax_pair<7, 3, 0, false>(c, accN, stripe0, n);
+            case 2: return t.use_mad ? launch_ax_pair<5, 4, 1, false>(c, accN, stripe0, n) : launch_ax_pair<5, 4, 0, false>(c, accN, stripe0, n);
+            default: return t.use_mad ? launch_ax_pair<11, 2, 1, false>(c, accN, stripe0, n) : launch_ax_pair<11, 2, 0, false>(c, accN, stripe0, n);
+        }
+    }
     if (t.variant == 1) return t.use_mad ? launch_ax<12, 3, 4, false>(c, accN, stripe0, n) : launch_ax<12, 3, 0, false>(c, accN, stripe0, n);
     switch (t.use_mad) {
         case 0: return launch_ax<15, 2, 0, false>(c, accN, stripe0, n);
@@ -1139,8 +1158,12 @@ int ax_main(gvb_ctx* c, unsigned long long* accN) {
     const bool want_twin = !(tw && !strcmp(tw, "0"));
     if (want_twin && c->twin_state == 0) GVB_CHECK(gvb_twin_build(c));
     long T = (want_twin && c->twin_state > 0) ? c->twin_stripes : 0;
-    if (T > 0 && c->tab_pairs) {
-        GVB_CHECK((t.twin_mad > 0 ? launch_ax_pair<11, 2, 1, true>(c, accN, 0, T) : launch_ax_pair<11, 2, 0, true>(c, accN, 0, T)));
+    if (T > 0 && t.tma_walk) {
+        switch (t.pair_shape) {
+            case 1: GVB_CHECK((launch_ax_pair<7, 3, 0, true>(c, accN, 0, T))); break;
+            case 2: GVB_CHECK((launch_ax_pair<5, 4, 0, true>(c, accN, 0, T))); break;
+            default: GVB_CHECK((launch_ax_pair<11, 2, 0, true>(c, accN, 0, T))); break;
+        }
     } else if (T > 0) {
         if (t.variant == 1)
             GVB_CHECK((launch_ax<12, 3, 0, true>(c, accN, 0, T)));
@@ -1152,7 +1175,13 @@ int ax_main(gvb_ctx* c, unsigned long long* accN) {
 
 int atx_main(gvb_ctx* c, const int* tab, unsigned long long* acc) {
     const TileTune t = tune();
-    if (c->tab_pairs) return t.use_mad >= 4 ? launch_atx_pair<11, 2, true, 0>(c, tab, acc, c->shift_u) : launch_atx_pair<11, 2, false, 0>(c, tab, acc, c->shift_u);
+    if (t.tma_walk) {
+        switch (t.pair_shape) {
+            case 1: return launch_atx_pair<7, 3, false, 0>(c, tab, acc, c->shift_u);
+            case 2: return launch_atx_pair<5, 4, false, 0>(c, tab, acc, c->shift_u);
+            default: return launch_atx_pair<11, 2, false, 0>(c, tab, acc, c->shift_u);
+        }
+    }
     if (t.variant == 1) return t.use_mad >= 4 ? launch_atx<12, 3, true, 0>(c, tab, acc, c->shift_u) : launch_atx<12, 3, false, 0>(c, tab, acc, c->shift_u);
     return t.use_mad >= 4 ? launch_atx<15, 2, true, 0>(c, tab, acc, c->shift_u) : launch_atx<15, 2, false, 0>(c, tab, acc, c->shift_u);
 }
@@ -1209,7 +1238,7 @@ int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB) {
 // the table walk of X^T.u with packed counters (MODE 1): acc[j] = n00 | n10 << 21 | n11 << 42 over the individuals the table weights
 int gvb_count_tile_main(gvb_ctx* c, const int* tab, unsigned long long* acc) {
     const TileTune t = tune();
-    if (c->tab_pairs) return launch_atx_pair<11, 2, false, 1>(c, tab, acc, nullptr);
+    if (t.tma_walk) return launch_atx_pair<11, 2, false, 1>(c, tab, acc, nullptr);
     if (t.variant == 1) return launch_atx<12, 3, false, 1>(c, tab, acc, nullptr);
     return launch_atx<15, 2, false, 1>(c, tab, acc, nullptr);
 }

@@ -1,4 +1,5 @@
-"""Parity at BASELINE.json's FULL per-GPU sizes (configs 2, 4-shard, 5-like with 1 % missing), where the oracle cannot
+"""Parity at BASELINE.json's FULL per-GPU sizes (configs 2, 3, 4-shard, the 160 GB single-GPU cut of config 4, the 105 GB shard of
+config 5 with 1 % missing), where the oracle cannot
 sweep the whole matrix: the matrix is generated directly in HBM by the counter-based generator, which the oracle can
 regenerate marker by marker (gvamp_oracle.c:orc_synth_bed is byte-identical), so
 
@@ -32,6 +33,10 @@ CASES = [
     pytest.param(100_000, 500_000, 0.0, id="config2-100kx500k"),
     pytest.param(400_000, 275_000, 0.0, id="config4-shard-400kx275k"),
     pytest.param(400_000, 120_000, 0.01, id="config5-like-400kx120k-1pct-missing"),
+    pytest.param(200_000, 1_000_000, 0.0, id="config3-200kx1M"),
+    # the two shards that do not leave room for a whole individual-major twin: X.v runs on a partial twin + the gathering kernel
+    pytest.param(400_000, 1_050_000, 0.01, id="config5-shard-400kx1.05M-1pct-missing-105GB"),
+    pytest.param(400_000, 1_600_000, 0.0, id="config4-single-gpu-cut-400kx1.6M-160GB"),
 ]
 
 

@@ -445,11 +445,37 @@ atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
 // ===================================================================================================
 constexpr int PAIR_REGION = 65536;   // [256 entries][2 steps][32 slots] int32
 
+// Shared memory of a pair-mode CTA, all of it dynamic so that 128 KB of tables + 24 bed tiles (12 consumer warps x 2) fit the 227 KB:
+//   [2 table regions at the start of the segment: a link-time constant base, so the lookups are LDS [R + UR]]
+//   [pad up to the next 4 KB boundary][NW x NS bed tiles, 4 KB aligned: XOR addressing][control block]
+// the 256-byte control block (work item, table barriers, bed barriers) sits in the pad when the pad is large enough (the dynamic
+// segment starts 1 KB into the window: 3 KB of pad), behind the bed tiles otherwise.
+constexpr int PAIR_CTRL = 256;
+constexpr int SMEM_MAX = 232448;   // 227 KB
 template <int NW, int NS>
 struct PairCfg {
+    static_assert(NW * NS <= 24, "control block holds 24 bed barriers");
     static constexpr int THREADS = NW * 32 + 32;
-    static constexpr int SMEM = 2 * PAIR_REGION + NW * NS * TILE_BYTES + TILE_BYTES;
+    static constexpr int WANT = 2 * PAIR_REGION + NW * NS * TILE_BYTES + TILE_BYTES + PAIR_CTRL;
+    static constexpr int SMEM = WANT < SMEM_MAX ? WANT : SMEM_MAX;
 };
+struct PairLayout {
+    uint32_t bed, tab, ctrl;   // shared-memory addresses
+    uint32_t tab_off, ctrl_off;   // the same as offsets from the dynamic segment (generic pointers)
+};
+template <int NW, int NS>
+__device__ __forceinline__ PairLayout pair_layout(const char* smem) {
+    PairLayout L;
+    const uint32_t base = smem_u32(smem);
+    L.tab = base;
+    const uint32_t tab_end = base + 2 * PAIR_REGION;
+    L.bed = (tab_end + 4095u) & ~4095u;
+    L.ctrl = (L.bed - tab_end >= (uint32_t)PAIR_CTRL) ? tab_end : L.bed + NW * NS * TILE_BYTES;
+    if (L.ctrl + PAIR_CTRL > base + PairCfg<NW, NS>::SMEM || L.bed + NW * NS * TILE_BYTES > base + PairCfg<NW, NS>::SMEM) __trap();   // layout does not fit
+    L.tab_off = 0;
+    L.ctrl_off = L.ctrl - base;
+    return L;
+}
 
 __device__ __forceinline__ void bulk_g2s_plain(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -463,9 +489,9 @@ struct PairPipe {
     template <int R>
     __device__ __forceinline__ uint32_t& fills() { return R ? fills1 : fills0; }
 };
-__device__ __forceinline__ void pair_pipe_init(PairPipe& pp, unsigned long long* s_tab, int consumers) {
-    pp.full = smem_u32(&s_tab[0]);
-    pp.empty = smem_u32(&s_tab[2]);
+__device__ __forceinline__ void pair_pipe_init(PairPipe& pp, uint32_t s_tab, int consumers) {
+    pp.full = s_tab;
+    pp.empty = s_tab + 16;
     pp.fills0 = pp.fills1 = 0;
     if (threadIdx.x == 0) {
         mbar_init(pp.full, 1);
@@ -573,21 +599,21 @@ ax_pair_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, l
                const int* __restrict__ shifts) {
     if (skip && *skip) return;
     extern __shared__ __align__(1024) char smem[];
-    __shared__ int s_item;
-    __shared__ __align__(8) unsigned long long s_bar[NW * NS];
-    __shared__ __align__(8) unsigned long long s_tab[4];
+    const PairLayout lay = pair_layout<NW, NS>(smem);
+    volatile int* s_item_p = reinterpret_cast<volatile int*>(smem + lay.ctrl_off);       // control block: work item at +0,
+    const char* tabs = smem;                                                                // table barriers at +8, bed barriers at +64
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool producer = warp == NW;
-    const uint32_t tab_sm = smem_u32(smem);
-    const uint32_t bed_sm = ((tab_sm + 2 * PAIR_REGION + 4095u) & ~4095u) + (producer ? 0 : warp) * (NS * TILE_BYTES);
-    const uint32_t bar0 = smem_u32(&s_bar[(producer ? 0 : warp) * NS]);
+    const uint32_t tab_sm = lay.tab;
+    const uint32_t bed_sm = lay.bed + (producer ? 0 : warp) * (NS * TILE_BYTES);
+    const uint32_t bar0 = lay.ctrl + 64 + 8 * ((producer ? 0 : warp) * NS);
     if (lane == 0 && !producer) {
 #pragma unroll
         for (int s = 0; s < NS; s++) mbar_init(bar0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     PairPipe pp;
-    pair_pipe_init(pp, s_tab, NW);
+    pair_pipe_init(pp, lay.ctrl + 8, NW);
     const uint64_t pol = policy_evict_first();
     unsigned sp[11];
     const uint32_t lane_off = lane * 132;
@@ -597,9 +623,9 @@ ax_pair_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, l
 
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
+        if (threadIdx.x == 0) *s_item_p = atomicAdd(work_counter, 1);
         __syncthreads();
-        const int item = s_item;
+        const int item = *s_item_p;
         if (item >= n_items) break;
         const int gc = item / n_sblocks, sb = item % n_sblocks;
         const long step_lo = (long)gc * tiles_per_chunk;   // even: a chunk starts on a pair boundary
@@ -625,7 +651,7 @@ ax_pair_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv, l
         for (int s = 0; s < NS - 1; s++) issue_bed(s);
         long long acc64[4] = {0, 0, 0, 0};
         make_spack3(sp, lane);   // region 0, half 0
-#define AX_CONSUME ax_consume_p<MADK, TW>(smem, bed_sm + s * TILE_BYTES + lane_off, sp, one, a32)
+#define AX_CONSUME ax_consume_p<MADK, TW>(tabs, bed_sm + s * TILE_BYTES + lane_off, sp, one, a32)
 #define AX_FLUSH _Pragma("unroll") for (int k = 0; k < 4; k++) acc64[k] += (long long)a32[k] << sh
 #pragma unroll 1
         for (int i = 0; i < nt; i++) PAIR_STEP(nt, AX_CONSUME, AX_FLUSH)
@@ -647,21 +673,21 @@ atx_pair_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
                 const int* __restrict__ shifts_in) {
     if (skip && *skip) return;
     extern __shared__ __align__(1024) char smem[];
-    __shared__ int s_item;
-    __shared__ __align__(8) unsigned long long s_bar[NW * NS];
-    __shared__ __align__(8) unsigned long long s_tab[4];
+    const PairLayout lay = pair_layout<NW, NS>(smem);
+    volatile int* s_item_p = reinterpret_cast<volatile int*>(smem + lay.ctrl_off);       // control block: work item at +0,
+    const char* tabs = smem;                                                                // table barriers at +8, bed barriers at +64
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool producer = warp == NW;
-    const uint32_t tab_sm = smem_u32(smem);
-    const uint32_t bed_sm = ((tab_sm + 2 * PAIR_REGION + 4095u) & ~4095u) + (producer ? 0 : warp) * (NS * TILE_BYTES);
-    const uint32_t bar0 = smem_u32(&s_bar[(producer ? 0 : warp) * NS]);
+    const uint32_t tab_sm = lay.tab;
+    const uint32_t bed_sm = lay.bed + (producer ? 0 : warp) * (NS * TILE_BYTES);
+    const uint32_t bar0 = lay.ctrl + 64 + 8 * ((producer ? 0 : warp) * NS);
     if (lane == 0 && !producer) {
 #pragma unroll
         for (int s = 0; s < NS; s++) mbar_init(bar0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     PairPipe pp;
-    pair_pipe_init(pp, s_tab, NW);
+    pair_pipe_init(pp, lay.ctrl + 8, NW);
     const uint64_t pol = policy_evict_first();
     unsigned sp[11];
     const uint32_t lane_off = lane * 132;
@@ -672,9 +698,9 @@ atx_pair_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
 
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
+        if (threadIdx.x == 0) *s_item_p = atomicAdd(work_counter, 1);
         __syncthreads();
-        const int item = s_item;
+        const int item = *s_item_p;
         if (item >= n_items) break;
         const int sc = item / n_gblocks, gb = item % n_gblocks;
         const long step_lo = (long)sc * stripes_per_chunk;   // even
@@ -700,7 +726,7 @@ atx_pair_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
         for (int s = 0; s < NS - 1; s++) issue_bed(s);
         long long acc64[4] = {0, 0, 0, 0};
         make_spack3(sp, lane);   // region 0, half 0
-#define ATX_CONSUME atx_consume_p<USE_MAD>(smem, bed_sm + s * TILE_BYTES + lane_off, sp, one, a32)
+#define ATX_CONSUME atx_consume_p<USE_MAD>(tabs, bed_sm + s * TILE_BYTES + lane_off, sp, one, a32)
 #define ATX_FLUSH                                                                                              \
     _Pragma("unroll") for (int q = 0; q < 4; q++) {                                                            \
         if (MODE == 0) {                                                                                       \
@@ -728,12 +754,12 @@ atx_pair_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
 // measured defaults (profiles/r02_sweep_tuning.txt)
 #define GVB_DEFAULT_TMA_WALK 1
 #define GVB_DEFAULT_TMA_GATHER 0
-#define GVB_DEFAULT_PAIR_SHAPE 0
+#define GVB_DEFAULT_PAIR_SHAPE 1
 
 struct TileTune {
     int tma_walk;    // X^T.u and X.v on the twin: 1 = pair mode (tables by TMA bulk copy), 0 = producer-warp cp.async (two 32 KB buffers)
     int tma_gather;  // the gathering X.v kernel, likewise
-    int pair_shape;  // pair mode: 0 = 11 consumer warps x 2 bed stages, 1 = 7 x 3, 2 = 5 x 4 (128 KB of tables leave room for 23 bed tiles)
+    int pair_shape;  // pair mode: 0 = 11 consumer warps x 2 bed stages, 1 = 12 x 2, 2 = 7 x 3 (128 KB of tables leave room for 24 bed tiles)
     int variant;   // 0: 15 consumer warps x 2 stages, 1: 12 consumer warps x 3 stages (+ the producer warp)
     int use_mad;   // X.v: accumulators (0..4) fed by IMAD instead of IADD3; X^T.u: 4 -> all four, else none
     int ax_tiles_per_chunk, atx_stripes_per_chunk;
@@ -1135,8 +1161,8 @@ int ensure_scratch(gvb_ctx* c, bool need_tab_u, bool need_tab_v, bool miss) {
 int ax_gather(gvb_ctx* c, unsigned long long* accN, const TileTune& t, long stripe0, long n) {
     if (t.tma_gather) {
         switch (t.pair_shape) {
-            case 1: return t.use_mad ? launch_ax_pair<7, 3, 1, false>(c, accN, stripe0, n) : launch_ax_pair<7, 3, 0, false>(c, accN, stripe0, n);
-            case 2: return t.use_mad ? launch_ax_pair<5, 4, 1, false>(c, accN, stripe0, n) : launch_ax_pair<5, 4, 0, false>(c, accN, stripe0, n);
+            case 1: return t.use_mad ? launch_ax_pair<12, 2, 1, false>(c, accN, stripe0, n) : launch_ax_pair<12, 2, 0, false>(c, accN, stripe0, n);
+            case 2: return t.use_mad ? launch_ax_pair<7, 3, 1, false>(c, accN, stripe0, n) : launch_ax_pair<7, 3, 0, false>(c, accN, stripe0, n);
             default: return t.use_mad ? launch_ax_pair<11, 2, 1, false>(c, accN, stripe0, n) : launch_ax_pair<11, 2, 0, false>(c, accN, stripe0, n);
         }
     }
@@ -1160,8 +1186,8 @@ int ax_main(gvb_ctx* c, unsigned long long* accN) {
     long T = (want_twin && c->twin_state > 0) ? c->twin_stripes : 0;
     if (T > 0 && t.tma_walk) {
         switch (t.pair_shape) {
-            case 1: GVB_CHECK((launch_ax_pair<7, 3, 0, true>(c, accN, 0, T))); break;
-            case 2: GVB_CHECK((launch_ax_pair<5, 4, 0, true>(c, accN, 0, T))); break;
+            case 1: GVB_CHECK((launch_ax_pair<12, 2, 0, true>(c, accN, 0, T))); break;
+            case 2: GVB_CHECK((launch_ax_pair<7, 3, 0, true>(c, accN, 0, T))); break;
             default: GVB_CHECK((launch_ax_pair<11, 2, 0, true>(c, accN, 0, T))); break;
         }
     } else if (T > 0) {
@@ -1177,8 +1203,8 @@ int atx_main(gvb_ctx* c, const int* tab, unsigned long long* acc) {
     const TileTune t = tune();
     if (t.tma_walk) {
         switch (t.pair_shape) {
-            case 1: return launch_atx_pair<7, 3, false, 0>(c, tab, acc, c->shift_u);
-            case 2: return launch_atx_pair<5, 4, false, 0>(c, tab, acc, c->shift_u);
+            case 1: return launch_atx_pair<12, 2, false, 0>(c, tab, acc, c->shift_u);
+            case 2: return launch_atx_pair<7, 3, false, 0>(c, tab, acc, c->shift_u);
             default: return launch_atx_pair<11, 2, false, 0>(c, tab, acc, c->shift_u);
         }
     }

@@ -17,7 +17,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gvamp_b200 import capi  # noqa: E402
 
-DEFAULT = ["cpasync15x2=GVB_TAB:cpasync", "tma11x2=GVB_TAB:tma,GVB_PAIR_SHAPE:0", "tma7x3=GVB_TAB:tma,GVB_PAIR_SHAPE:1", "tma5x4=GVB_TAB:tma,GVB_PAIR_SHAPE:2"]
+DEFAULT = ["cpasync15x2=GVB_TAB:cpasync", "tma11x2=GVB_TAB:tma,GVB_PAIR_SHAPE:0", "tma12x2=GVB_TAB:tma,GVB_PAIR_SHAPE:1", "tma7x3=GVB_TAB:tma,GVB_PAIR_SHAPE:2"]
 ap = argparse.ArgumentParser()
 ap.add_argument("--N", type=int, default=400_000)
 ap.add_argument("--M", type=int, default=275_000)

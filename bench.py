@@ -482,8 +482,8 @@ def ours_arm(args):
     dom = max(per, key=lambda k: per[k][0])
     gbs = {k: (bed_bytes_local / 1e9) / (ms / n / 1e3) if n else None for k, (ms, n) in per.items()}
     twin = ctx.twin_state()
-    kname = {"X.v": "ax_tile_kernel<twin>" if twin == 1 else ("ax_tile_kernel<twin+gather>" if twin == 2 else "ax_tile_kernel<gather>"),
-             "X^T.u": "atx_tile_kernel" + ("+miss_sum_kernel" if miss > 0 else "")}[dom]
+    kname = {"X.v": "ax_pair_kernel<twin>" if twin == 1 else ("ax_pair_kernel<twin>+ax_tile_kernel<gather>" if twin == 2 else "ax_tile_kernel<gather>"),
+             "X^T.u": "atx_pair_kernel" + ("+miss_sum_kernel" if miss > 0 else "")}[dom]
     traffic, traffic_src = ncu_traffic(f"{kname}@{bed_bytes_local}")
     n_sw = prof["ax_n"] + prof["atx_n"]
     roofline = {"bound": "hbm", "kernel": f"{dom}: {kname}", "achieved": gbs[dom], "peak": peak, "unit": "GB/s",

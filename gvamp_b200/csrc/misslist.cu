@@ -183,16 +183,39 @@ miss_sum_kernel(const uint16_t* __restrict__ idx, const unsigned long long* __re
             const unsigned long long o_lo = seg_off[seg0 + lane], o_hi = seg_off[seg0 + lane + 1];
             if (!__any_sync(0xffffffffu, o_hi > o_lo)) continue;
             const uint2* groups = reinterpret_cast<const uint2*>(idx);
+            // software pipeline over the 32 segments: the first four passes (512 entries: a whole segment up to 1.5 % missing) of
+            // segment s + 1 are in flight while segment s is gathered -- the kernel is bound by the latency of these loads (ncu:
+            // long_scoreboard 5.6 per issue with one segment in flight)
+            const uint2 kSentinel = make_uint2(0x80008000u, 0x80008000u);
+            uint2 nxt[4];
+            unsigned long long nbeg = __shfl_sync(0xffffffffu, o_lo, 0), nend = __shfl_sync(0xffffffffu, o_hi, 0);
+#pragma unroll
+            for (int r = 0; r < 4; r++) nxt[r] = (nbeg + lane + 32 * r < nend) ? __ldg(groups + nbeg + lane + 32 * r) : kSentinel;
 #pragma unroll 1
             for (int s = 0; s < 32; s++) {
-                const unsigned long long beg = __shfl_sync(0xffffffffu, o_lo, s), end = __shfl_sync(0xffffffffu, o_hi, s);
+                const unsigned long long beg = nbeg, end = nend;
+                uint2 e[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) e[r] = nxt[r];
+                if (s + 1 < 32) {
+                    nbeg = __shfl_sync(0xffffffffu, o_lo, s + 1);
+                    nend = __shfl_sync(0xffffffffu, o_hi, s + 1);
+#pragma unroll
+                    for (int r = 0; r < 4; r++) nxt[r] = (nbeg + lane + 32 * r < nend) ? __ldg(groups + nbeg + lane + 32 * r) : kSentinel;
+                }
                 if (beg == end) continue;
                 long long acc = 0;
-                for (unsigned long long gidx = beg + lane; gidx < end; gidx += 128) {
-                    // up to 4 groups (16 gathers) in flight per lane; |U| < 2^24, so 16 of them fit an int32
-                    uint2 e[4];
+                {
+                    // 4 groups (16 gathers) per lane; |U| < 2^24, so 16 of them fit an int32
+                    int a32 = 0;
 #pragma unroll
-                    for (int r = 0; r < 4; r++) e[r] = (gidx + 32 * r < end) ? __ldg(groups + gidx + 32 * r) : make_uint2(0x80008000u, 0x80008000u);
+                    for (int r = 0; r < 4; r++)
+                        a32 += U[e[r].x & 0xFFFFu] + U[e[r].x >> 16] + U[e[r].y & 0xFFFFu] + U[e[r].y >> 16];
+                    acc += a32;
+                }
+                for (unsigned long long gidx = beg + lane + 128; gidx < end; gidx += 128) {   // longer segments: the rest, unpipelined
+#pragma unroll
+                    for (int r = 0; r < 4; r++) e[r] = (gidx + 32 * r < end) ? __ldg(groups + gidx + 32 * r) : kSentinel;
                     int a32 = 0;
 #pragma unroll
                     for (int r = 0; r < 4; r++)

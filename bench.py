@@ -572,14 +572,15 @@ def run_linear(args, D, ctx, H, N, Mt, S, M, logf):
             os.environ["GVB_NO_FILES"] = "0" if files else "1"
             vmp = H.gvbh_vamp_create(opt, M, 1e-6, 1.0 / (1.0 - H2))
             H.gvbh_vamp_linear_begin(vmp, dat)
-            sweeps, cg = [], []
+            sweeps, cg, wall = [], [], []
             D.barrier()
             ctx.sync()
             ctx.timer_start(timer)
             for it in range(1, steps + 1):
-                s0 = ctx.sweeps()
+                s0, t0 = ctx.sweeps(), time.perf_counter()
                 H.gvbh_vamp_linear_iteration(vmp, dat, it, yptr if upload else None, None)
                 H.gvbh_vamp_cg_iters(vmp, cg_iters)
+                wall.append(1e3 * (time.perf_counter() - t0))   # an iteration ends with a host-visible reduction: wall clock ~ device time
                 sweeps.append(ctx.sweeps() - s0)
                 cg.append((cg_iters[0], cg_iters[1]))
             H.gvbh_vamp_linear_end(vmp, None, 0)       # waits for the last iteration's files
@@ -589,7 +590,7 @@ def run_linear(args, D, ctx, H, N, Mt, S, M, logf):
             ms = ctx.timer_ms(timer)
             gamw = H.gvbh_vamp_gamw(vmp)
             H.gvbh_vamp_destroy(vmp)
-            return sweeps, cg, ms, gamw
+            return sweeps, cg, ms, gamw, wall
 
         if W > 0:
             fresh_run(W, False, False, 2)
@@ -600,20 +601,23 @@ def run_linear(args, D, ctx, H, N, Mt, S, M, logf):
             time.sleep(0.3)
         ctx.profile(True)
         launches0, syncs0 = ctx.launches(), ctx.host_syncs()
-        out["sweeps"], out["cg"], out["ms_dev"], gamw = fresh_run(K, False, False, 0)
+        out["sweeps"], out["cg"], out["ms_dev"], gamw, wall = fresh_run(K, False, False, 0)
         out["launches"] = ctx.launches() - launches0
         out["host_syncs"] = ctx.host_syncs() - syncs0
         out["prof"] = ctx.profile_read()
         ctx.profile(False)
         out["clocks"] = sampler.stop() if sampler else None
         # ---- timed region 2: the same iterations end to end
-        out["e2e_sweeps"], _, out["ms_e2e"], gamw2 = fresh_run(K, True, True, 1)
+        out["e2e_sweeps"], _, out["ms_e2e"], gamw2, _ = fresh_run(K, True, True, 1)
         H.gvbh_data_destroy(dat)
     nfiles = len([f for f in os.listdir(outdir) if "_it_" in f]) if D.rank == 0 else 0
     out["files"] = nfiles / K
     out["h2d"] = 8 * N
     out["d2h"] = 8 * (4 * M + 4 * mbytes)
-    out["extra"] = {"final_gamw": gamw, "final_gamw_e2e": gamw2}
+    out["extra"] = {"final_gamw": gamw, "final_gamw_e2e": gamw2, "ms_per_step_each_host_clock": [round(w, 2) for w in wall],
+                    "ms_per_step_median_host_clock": float(np.median(wall)),
+                    "note_on_K": "iterations/s of a run timed from its iteration 1 depends on K by construction (iteration 1 solves from zero: 4x the sweeps of a "
+                                 "late iteration); ms_per_sweep and the per-step list are the K-independent figures"}
     out["e2e_note"] = ("a fresh run of the same iterations: y re-uploaded from pinned host memory every step (A^T y recomputed: one more sweep per step), "
                        "x1_hat / r1 / r2 / x2_hat / z1 read back every step and written to the reference's per-iteration files")
     return out

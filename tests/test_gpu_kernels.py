@@ -648,3 +648,18 @@ def test_product_library_refuses_cross_check_kernels(C, monkeypatch):
     assert "not part of the product library" in str(e.value)
     monkeypatch.setenv("GVB_KERNELS", "lut")
     C.Context(0).close()
+
+
+def test_layout_generation_counts_reloads(C, oracle):
+    """gvb_layout_generation is bumped by every (re)load of the matrix and every gvb_set_mask: the host layer drops its cached
+    by-products (A mu, A^T A mu, A^T y) and re-creates its device vectors when it changes (vamp::dev_open)."""
+    bed = oracle.synth_bed(2, 0, 300, 500)
+    with C.Context(0) as ctx:
+        g0 = ctx.layout_generation()
+        ctx.load_host(bed, 500)
+        g1 = ctx.layout_generation()
+        ctx.set_mask(oracle.make_mask4(500, np.arange(500) % 7 != 0), int((np.arange(500) % 7 != 0).sum()))
+        g2 = ctx.layout_generation()
+        ctx.load_host(bed[:200], 500)
+        g3 = ctx.layout_generation()
+    assert g0 < g1 < g2 < g3

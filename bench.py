@@ -610,7 +610,10 @@ def run_linear(args, D, ctx, H, N, Mt, S, M, logf):
         # ---- timed region 2: the same iterations end to end
         out["e2e_sweeps"], _, out["ms_e2e"], gamw2, _ = fresh_run(K, True, True, 1)
         H.gvbh_data_destroy(dat)
+    D.barrier()
     nfiles = len([f for f in os.listdir(outdir) if "_it_" in f]) if D.rank == 0 else 0
+    if D.rank == 0:
+        shutil.rmtree(outdir, ignore_errors=True)     # ~1 GB of per-iteration files at the default workload
     out["files"] = nfiles / K
     out["h2d"] = 8 * N
     out["d2h"] = 8 * (4 * M + 4 * mbytes)

@@ -132,7 +132,8 @@ int gvb_twin_release(gvb_ctx* ctx);
  * also under adversarial dynamic range (one entry 10^6 x the rest in u or v, stripes 10^4 apart, 128 clustered large effects in one
  * tile over a tiny background, 99.9 % sparse v, |u| ~ 1e-150 with |v| ~ 1e150; tests/test_gpu_kernels.py::
  * test_fixed_point_dynamic_range); typical inputs give 5e-8 (X.v) / 7e-8 (X^T.u).  On shards with missing genotypes the
- * missing-genotype term of X^T.u (1 % of the individuals at 1 % missing) keeps the common scale of the whole vector.  Outputs that
+ * missing-genotype term of X^T.u keeps the common scale of the whole vector: with a fraction p of missing genotypes the bound
+ * holds while max|u| / rms(u) stays below ~30 / sqrt(p) (300 at 1 % missing; a Gaussian u of 400k entries has 4.8).  Outputs that
  * nearly cancel are accurate to that absolute error, not to 1e-6 of their own value.  Results do not depend on the tiling, the
  * table staging mode or the amount of twin (bit-identical), and are the same on every run.  A NaN / infinity in the input turns every
  * output into NaN, like the reference's sums. */

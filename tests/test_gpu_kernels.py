@@ -141,11 +141,15 @@ def test_ax_atx_vs_oracle(C, oracle, gen, N, M, miss):
     assert abs(lhs - rhs) <= 1e-6 * (np.linalg.norm(ax) * np.linalg.norm(u))
 
 
-@pytest.mark.parametrize("variant,tpc,spc", [(0, 3, 5), (1, 2, 7), (0, 64, 64)])
-def test_tile_kernels_many_work_items(C, oracle, variant, tpc, spc, monkeypatch):
-    """gen-2 tile kernels with small work items: several marker chunks / stripe chunks per CTA, partial last chunks,
-    inactive warps (stripes and marker tiles that are not multiples of the CTA shape), both CTA shapes."""
-    monkeypatch.setenv("GVB_TILE_VARIANT", str(variant))
+@pytest.mark.parametrize("staging,shape", [("tma", 0), ("tma", 1), ("tma", 2), ("cpasync", 0), ("cpasync", 1)])
+@pytest.mark.parametrize("tpc,spc", [(3, 5), (2, 7), (64, 64)])
+def test_tile_kernels_many_work_items(C, oracle, staging, shape, tpc, spc, monkeypatch):
+    """The tile kernels with small work items: several marker chunks / stripe chunks per CTA, partial last chunks (odd numbers of steps:
+    a half-filled table pair), inactive warps (stripes and marker tiles that are not multiples of the CTA shape), in both table staging
+    modes and every CTA shape: pair mode (tables by TMA bulk copy) with 11x2 / 12x2 / 7x3 consumer warps x bed stages, producer-warp
+    cp.async with 15x2 / 12x3; X.v on the twin and (second context) gathering from the one matrix."""
+    monkeypatch.setenv("GVB_TAB", staging)
+    monkeypatch.setenv("GVB_PAIR_SHAPE" if staging == "tma" else "GVB_TILE_VARIANT", str(shape))
     monkeypatch.setenv("GVB_AX_TPC", str(tpc))
     monkeypatch.setenv("GVB_ATX_SPC", str(spc))
     N, M = 6100, 9000          # 48 stripes (3 CTA rows of 16), 71 marker tiles
@@ -157,9 +161,13 @@ def test_tile_kernels_many_work_items(C, oracle, variant, tpc, spc, monkeypatch)
         ctx.load_host(bed, N).compute_stats(1.0)
         ax, atx = ctx.Ax(v), ctx.ATx(u)
         ax_again, atx_again = ctx.Ax(v), ctx.ATx(u)
+    monkeypatch.setenv("GVB_TWIN", "0")
+    with make_ctx(C, "lut") as ctx:
+        ctx.load_host(bed, N).compute_stats(1.0)
+        ax_gather = ctx.Ax(v)
     assert relerr(ax, ds.Ax(v)) < TOL_MATVEC and relerr(atx, ds.ATx(u)) < TOL_MATVEC
-    # fixed-point accumulation: bit-reproducible, whatever order the work items ran in
-    assert np.array_equal(ax, ax_again) and np.array_equal(atx, atx_again)
+    # fixed-point accumulation: bit-reproducible, whatever order the work items ran in and whichever kernel walked the matrix
+    assert np.array_equal(ax, ax_again) and np.array_equal(atx, atx_again) and np.array_equal(ax, ax_gather)
 
 
 def test_tile_kernels_reproducible_across_chunking(C, oracle, monkeypatch):
@@ -169,8 +177,9 @@ def test_tile_kernels_reproducible_across_chunking(C, oracle, monkeypatch):
     rng = np.random.default_rng(2)
     v, u = rng.normal(size=M), rng.normal(size=N)
     res = []
-    for variant, tpc, spc in ((0, 64, 64), (1, 1, 1), (0, 5, 3)):
-        monkeypatch.setenv("GVB_TILE_VARIANT", str(variant))
+    for staging, shape, tpc, spc in (("tma", 1, 64, 64), ("tma", 0, 1, 1), ("cpasync", 0, 5, 3), ("cpasync", 1, 2, 2), ("tma", 2, 7, 9)):
+        monkeypatch.setenv("GVB_TAB", staging)
+        monkeypatch.setenv("GVB_PAIR_SHAPE" if staging == "tma" else "GVB_TILE_VARIANT", str(shape))
         monkeypatch.setenv("GVB_AX_TPC", str(tpc))
         monkeypatch.setenv("GVB_ATX_SPC", str(spc))
         with make_ctx(C, "lut") as ctx:

@@ -230,3 +230,27 @@ def test_vamp_stress_case(oracle):
         assert relerr(tr.x2_hat[it - 1], g[f"x2_{it}"]) < 1e-8, it
     assert np.allclose(tr.gamw, g["gamw_log"][1::2], rtol=1e-5) and np.allclose(tr.alpha2, g["alpha2_log"], rtol=1e-5)
     assert np.allclose(tr.gam1s, g["gam1s"], rtol=1e-5) and np.allclose(tr.R2trains, g["R2trains"], rtol=1e-5, atol=1e-6)
+
+
+def test_emulated_multi_rank_run(oracle):
+    """oracle.infere_linear(nranks = R) is the pin of the multi-GPU parity tests: its probe is the per-shard probes of an R-rank run of
+    the reference laid end to end (mt19937{seed + S_r} per shard, vamp.cpp:875-882).  The parameter must be live (the two-rank probe
+    moves the result by percents, far above the 1e-4 the GPU run is held to), nranks = 1 must reproduce the golden single-rank run,
+    and the shards must tile the marker range by the divide_work rule."""
+    g = golden("vamp_linear.npz")
+    N, M, iters = int(g["N"]), int(g["M"]), 3
+    bed = oracle.synth_bed(int(g["seed"]), 0, M, N)
+    y = g["y"]
+    avg = float(np.cumsum(y)[-1]) / N
+    sqn = math.sqrt((N - 1) / float(np.cumsum((y - avg) * (y - avg))[-1]))
+    ds = oracle.Dataset(bed, N, phen=y * sqn)
+    res = {}
+    for R in (1, 2, 3):
+        cfg = oracle.VampConfig(iterations=iters, rho=0.5, probs=(0.9, 0.06, 0.04), vars=(0, 1e-4, 1e-3), CG_max_iter=20,
+                                gamw=1.0 / (1.0 - float(g["h2"])), seed=1, nranks=R)
+        res[R] = oracle.infere_linear(ds, cfg).x1_hat[-1]
+    assert relerr(res[1], g[f"x1_{iters}"]) < 1e-8
+    assert relerr(res[2], res[1]) > 1e-3 and relerr(res[3], res[1]) > 1e-3 and relerr(res[3], res[2]) > 1e-3
+    probe = oracle.sharded_probe(1, 0, M, M, 3)
+    parts = [oracle.bernoulli_probe(1, oracle.divide_work(M, 3, r)[1], oracle.divide_work(M, 3, r)[0], M) for r in range(3)]
+    assert np.array_equal(probe, np.concatenate(parts)) and np.all(np.abs(probe) == 1 / math.sqrt(M))

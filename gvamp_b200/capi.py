@@ -78,6 +78,7 @@ SIGNATURES = {
     "gvb_cg_solve": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p]),
     "gvb_cg_solve_ex": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, c_f64p]),
     "gvb_cg_solve_warm": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, vp, ci, c_f64p]),
+    "gvb_cg_solve_cached": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, ctypes.POINTER(ci), c_f64p]),
     "gvb_people_stats": (ci, [vp, vp, vp, vp]),
     "gvb_cg_solve_aat": (ci, [vp, vp, vp, cd, cd, vp, vp, vp, ci, ctypes.POINTER(ci), c_f64p]),
     "gvb_probit_denoise": (ci, [vp, vp, vp, vp, cd, cd, vp, c_f64p]),
@@ -393,6 +394,16 @@ class Context:
         dots3 = np.zeros(3)
         _chk(self.L.gvb_cg_solve_warm(self.h, rhs.h, mu.h, tau, gam2, max_iter, denoiser, ctypes.byref(it), log.ctypes.data_as(c_f64p),
                                       ax_mu.h, ata_mu.h, int(have_start), dots3.ctypes.data_as(c_f64p)))
+        return it.value, log.reshape(max_iter, 4)[: it.value], dots3
+
+    def cg_solve_cached(self, rhs, mu, tau, gam2, max_iter, denoiser, ata_rhs, state):
+        """state: a one-element list holding 0 (cache empty) or 1 (filled); updated in place"""
+        it, st = ci(0), ci(int(state[0]))
+        log = np.zeros(4 * max_iter)
+        dots3 = np.zeros(3)
+        _chk(self.L.gvb_cg_solve_cached(self.h, rhs.h, mu.h, tau, gam2, max_iter, denoiser, ctypes.byref(it), log.ctypes.data_as(c_f64p),
+                                        ata_rhs.h, ctypes.byref(st), dots3.ctypes.data_as(c_f64p)), self.L)
+        state[0] = st.value
         return it.value, log.reshape(max_iter, 4)[: it.value], dots3
 
     def people_stats(self):

@@ -135,6 +135,16 @@ __global__ void cg_update_p_kernel(double* __restrict__ p, const double* __restr
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = r[i] / diag + beta * p[i];
 }
 
+// zero-start solve with a cached A^T A rhs (see cg_solve_impl, `ata_rhs`): the first search direction is p0 = rhs / diag, so
+// A^T A p0 = (A^T A rhs) / diag -- d receives what the two sweeps of iteration 0 would have left there (before the combine kernel)
+__global__ void cg_d_from_cached_kernel(double* __restrict__ d, const double* __restrict__ ata_rhs, double diag, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) d[i] = ata_rhs[i] / diag;
+}
+// ... and the way in: after the sweeps of iteration 0 of a zero-start solve, d = A^T A (rhs / diag)
+__global__ void cg_cache_from_d_kernel(double* __restrict__ ata_rhs, const double* __restrict__ d, double diag, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) ata_rhs[i] = d[i] * diag;
+}
+
 // ---- the scalar steps, one thread each; R = c->red_result (already summed over blocks and ranks) ----
 __global__ void cg_scal_init_kernel(double* __restrict__ S, int* __restrict__ flags, const double* __restrict__ R) {
     S[CG_RZ] = R[0];
@@ -247,14 +257,23 @@ extern "C" int gvb_lmmse_mult(gvb_ctx* c, gvb_vec v, double tau, double gam2, gv
 // A^T A mu of the start vector (the by-products of the solve that produced it, whatever its tau / gam2 were): the initial residual
 // needs no sweep; 2 = the caller states that the start vector is zero (it is cleared here): no sweep either -- the reference's
 // zero-vector shortcut of lmmse_mult (vamp.cpp:1079-1080) without a host-visible norm.
+//
+// ata_rhs / ata_rhs_state (optional, zero-start solves without by-product vectors only): a cache of A^T A rhs for a right-hand side that
+// the caller solves against again and again -- the Onsager probe, which is the same vector in every VAMP iteration (mt19937{seed + S},
+// vamp.cpp:875-882).  With a zero start the first search direction is rhs / diag, so the operator product of iteration 0 is
+// (tau A^T A rhs + gam2 rhs) / diag and needs no sweep once A^T A rhs is known.  *state == 0: iteration 0 sweeps and fills the cache
+// (*state becomes 1); *state == 1: iteration 0 takes it from the cache.  Like the by-products this is an identity of exact arithmetic;
+// in FP64 it differs from the sweeps by their own fixed-point error (linearity of the sweeps holds to ~1e-7).
 static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
-                         gvb_vec ax_mu, double* dots3, gvb_vec ata_mu, int have_start) {
+                         gvb_vec ax_mu, double* dots3, gvb_vec ata_mu, int have_start, gvb_vec ata_rhs = nullptr, int* ata_rhs_state = nullptr) {
     GVB_ARG(c && rhs && mu && rhs != mu, "vectors");
     GVB_ARG(max_iter >= 0, "max_iter");
     GVB_ARG(rhs->cap >= c->Mg_pad * 4 && mu->cap >= c->Mg_pad * 4, "M-vectors from gvb_vec_alloc_M");
     GVB_ARG(!ax_mu || ax_mu->cap >= c->Npad, "ax_mu must be an N-vector from gvb_vec_alloc_N");
     GVB_ARG(!ata_mu || (ax_mu && ata_mu->cap >= c->Mg_pad * 4 && ata_mu != mu && ata_mu != rhs), "ata_mu needs ax_mu and must be its own M-vector");
     GVB_ARG(have_start != 1 || ata_mu, "have_start = 1 needs ax_mu and ata_mu of the start vector");
+    GVB_ARG(!ata_rhs || (ata_rhs_state && have_start == 2 && !ax_mu && !ata_mu && ata_rhs->cap >= c->Mg_pad * 4 && ata_rhs != rhs && ata_rhs != mu),
+            "the A^T A rhs cache serves zero-start solves without by-product vectors");
     const long n = c->M;
     for (int k = 0; k < 3; k++) {
         if (c->cg_ws[k] && c->cg_ws[k]->cap != c->Mg_pad * 4) {   // matrix was reloaded with another shape
@@ -308,8 +327,18 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
         SkipGuard guard(c);
         c->skip = flags;
         for (int i = 0; i < max_iter && !stopped; i++) {
-            GVB_CHECK(gvb_ax_dev(c, p->d, c->tmpN2, true));   // d = Q p
-            GVB_CHECK(gvb_atx_dev(c, c->tmpN2, d->d));
+            if (i == 0 && ata_rhs && *ata_rhs_state == 1) {       // p0 = rhs / diag: A^T A p0 from the cache, no sweep
+                cg_d_from_cached_kernel<<<nbm, 256, 0, c->stream>>>(d->d, ata_rhs->d, diag, n);
+                GVB_LAUNCHED(c);
+            } else {
+                GVB_CHECK(gvb_ax_dev(c, p->d, c->tmpN2, true));   // d = Q p
+                GVB_CHECK(gvb_atx_dev(c, c->tmpN2, d->d));
+                if (i == 0 && ata_rhs) {
+                    cg_cache_from_d_kernel<<<nbm, 256, 0, c->stream>>>(ata_rhs->d, d->d, diag, n);
+                    GVB_LAUNCHED(c);
+                    *ata_rhs_state = 1;
+                }
+            }
             cg_combine_dot_kernel<<<nb, 256, 0, c->stream>>>(d->d, tau, gam2, p->d, n, c->red_partial, flags);
             GVB_LAUNCHED(c);
             GVB_CHECK(gvb_reduce_device(c, nb, 1, true));
@@ -398,6 +427,11 @@ extern "C" int gvb_cg_solve_ex(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, 
     int mode = 0;
     GVB_CHECK(start_mode(c, mu, 0, &mode));
     return cg_solve_impl(c, rhs, mu, tau, gam2, max_iter, denoiser, iters, log4, ax_mu, dots3, nullptr, mode);
+}
+extern "C" int gvb_cg_solve_cached(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
+                                   gvb_vec ata_rhs, int* ata_rhs_state, double* dots3) {
+    GVB_ARG(ata_rhs && ata_rhs_state && (*ata_rhs_state == 0 || *ata_rhs_state == 1), "cache vector and its state (0 or 1)");
+    return cg_solve_impl(c, rhs, mu, tau, gam2, max_iter, denoiser, iters, log4, nullptr, dots3, nullptr, 2, ata_rhs, ata_rhs_state);
 }
 extern "C" int gvb_cg_solve_warm(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
                                  gvb_vec ax_mu, gvb_vec ata_mu, int have_start, double* dots3) {

@@ -77,6 +77,8 @@ vamp::vamp(int N, int M, int Mt, double gam1, double gamw, int max_iter, double 
     onsager_warm = (ow && ow[0] == '1') && !reference_sweeps;   // opt-in: the default is the reference's zero start
     const char* ao = getenv("GVB_ASYNC_OUT");
     async_outputs = !(ao && ao[0] == '0');
+    const char* ol = getenv("GVB_ONSAGER_LANCZOS");
+    onsager_lanczos = !(ol && ol[0] == '0') && !reference_sweeps && !onsager_warm;
 }
 
 vamp::vamp(int M, double gam1, double gamw, std::vector<double> true_signal, int rank, Options opt)
@@ -108,6 +110,8 @@ vamp::vamp(int M, double gam1, double gamw, std::vector<double> true_signal, int
     onsager_warm = (ow && ow[0] == '1') && !reference_sweeps;   // opt-in: the default is the reference's zero start
     const char* ao = getenv("GVB_ASYNC_OUT");
     async_outputs = !(ao && ao[0] == '0');
+    const char* ol = getenv("GVB_ONSAGER_LANCZOS");
+    onsager_lanczos = !(ol && ol[0] == '0') && !reference_sweeps && !onsager_warm;
 }
 
 vamp::~vamp() {
@@ -123,7 +127,7 @@ void vamp::dev_open(data* dataset) {
     dev_close();
     dev.ctx = dataset->device();
     dev.layout_gen = gvb_layout_generation(dev.ctx);
-    gvb_vec* mvecs[] = {&dev.r1, &dev.r2, &dev.r2_prev, &dev.x1, &dev.x1_prev, &dev.x2, &dev.mu_last, &dev.rhs, &dev.bern, &dev.invq, &dev.tmpM, &dev.truth, &dev.aty, &dev.ata_x2, &dev.ata_invq};
+    gvb_vec* mvecs[] = {&dev.r1, &dev.r2, &dev.r2_prev, &dev.x1, &dev.x1_prev, &dev.x2, &dev.mu_last, &dev.rhs, &dev.bern, &dev.invq, &dev.tmpM, &dev.truth, &dev.aty, &dev.ata_x2, &dev.ata_invq, &dev.ata_bern, &dev.lz_prev, &dev.lz_cur, &dev.lz_w};
     for (gvb_vec* v : mvecs) DEV(gvb_vec_alloc_M(dev.ctx, v));
     gvb_vec* nvecs[] = {&dev.y, &dev.z1, &dev.tmpN, &dev.tmpN2, &dev.ax_invq};
     for (gvb_vec* v : nvecs) DEV(gvb_vec_alloc_N(dev.ctx, v));
@@ -131,8 +135,11 @@ void vamp::dev_open(data* dataset) {
 }
 
 void vamp::dev_close() {
+    lz_started = lz_exhausted = false;   // the Lanczos vectors go with the device state
+    lz_a.clear();
+    lz_b.clear();
     if (!dev.ctx) return;
-    gvb_vec all[] = {dev.r1, dev.r2, dev.r2_prev, dev.x1, dev.x1_prev, dev.x2, dev.mu_last, dev.rhs, dev.bern, dev.invq, dev.tmpM, dev.truth, dev.aty, dev.ata_x2, dev.ata_invq, dev.ax_invq,
+    gvb_vec all[] = {dev.r1, dev.r2, dev.r2_prev, dev.x1, dev.x1_prev, dev.x2, dev.mu_last, dev.rhs, dev.bern, dev.invq, dev.tmpM, dev.truth, dev.aty, dev.ata_x2, dev.ata_invq, dev.ata_bern, dev.lz_prev, dev.lz_cur, dev.lz_w, dev.ax_invq,
                      dev.y, dev.z1, dev.tmpN, dev.tmpN2, dev.p1, dev.p2, dev.z1h, dev.z2h, dev.mcov, dev.p1_prev};
     for (gvb_vec v : all)
         if (v) gvb_vec_free(dev.ctx, v);
@@ -245,19 +252,27 @@ void vamp::dev_denoise(double g1_prec, double* sum_d, double* dist2) {
     *dist2 = sums[1];
 }
 
-int vamp::dev_cg(gvb_vec rhs, gvb_vec mu, double tau, int denoiser, gvb_vec ax_mu, double* dots3, gvb_vec ata_mu, int have_start) {
+// the solver's log in the reference's words (vamp.cpp:1185-1191, 1217-1220)
+void vamp::print_cg_log(const std::vector<double>& log, int iters, int denoiser) {
+    if (rank != 0) return;
+    for (int i = 0; i < iters; i++) {
+        if (denoiser == 0 && log[4 * i + 3] >= 0 && log[4 * i + 0] >= 0)
+            std::cout << "[CG onsager] it = " << i << ": relative error for onsager is " << std::setprecision(10) << log[4 * i + 3] << std::endl;
+        if (log[4 * i + 0] >= 0)
+            std::cout << "[CG] it = " << i << ": ||r_it|| / ||RHS|| = " << std::setprecision(10) << log[4 * i + 0] << ", ||x_it|| = " << log[4 * i + 1]
+                      << ", ||z|| / ||RHS|| = " << log[4 * i + 2] << std::endl;
+    }
+}
+
+int vamp::dev_cg(gvb_vec rhs, gvb_vec mu, double tau, int denoiser, gvb_vec ax_mu, double* dots3, gvb_vec ata_mu, int have_start, gvb_vec ata_rhs,
+                 int* ata_rhs_state) {
     std::vector<double> log(4 * (size_t)CG_max_iter, 0.0);
     int iters = 0;
-    DEV(gvb_cg_solve_warm(dev.ctx, rhs, mu, tau, gam2, CG_max_iter, denoiser, &iters, log.data(), ax_mu, ata_mu, have_start, dots3));
-    if (rank == 0) {
-        for (int i = 0; i < iters; i++) {
-            if (denoiser == 0 && log[4 * i + 3] >= 0 && log[4 * i + 0] >= 0)
-                std::cout << "[CG onsager] it = " << i << ": relative error for onsager is " << std::setprecision(10) << log[4 * i + 3] << std::endl;
-            if (log[4 * i + 0] >= 0)
-                std::cout << "[CG] it = " << i << ": ||r_it|| / ||RHS|| = " << std::setprecision(10) << log[4 * i + 0] << ", ||x_it|| = " << log[4 * i + 1]
-                          << ", ||z|| / ||RHS|| = " << log[4 * i + 2] << std::endl;
-        }
-    }
+    if (ata_rhs)
+        DEV(gvb_cg_solve_cached(dev.ctx, rhs, mu, tau, gam2, CG_max_iter, denoiser, &iters, log.data(), ata_rhs, ata_rhs_state, dots3));
+    else
+        DEV(gvb_cg_solve_warm(dev.ctx, rhs, mu, tau, gam2, CG_max_iter, denoiser, &iters, log.data(), ax_mu, ata_mu, have_start, dots3));
+    print_cg_log(log, iters, denoiser);
     return iters;
 }
 
@@ -649,20 +664,128 @@ double vamp::g2d_onsager(double gam2, double tau, data* dataset) {
         DEV(gvb_vec_upload(dev.ctx, dev.bern, bern_vec.data(), M));
         dev.bern_valid = true;
         dev.bern_key = bern_key;
+        dev.ata_bern_state = 0;   // another probe: its A^T A product is not cached yet
     }
     this->gam2 = gam2;
     double d3[3] = {0, 0, 0};
-    if (onsager_warm) {   // GVB_ONSAGER_WARM=1: start from the previous iteration's Q^-1 u (same probe); the solve then stops on the residual only
+    if (onsager_lanczos) {
+        if (lz_key != bern_key) {   // another probe (or another shard): its Krylov space starts over
+            lz_started = lz_exhausted = false;
+            lz_a.clear();
+            lz_b.clear();
+            lz_key = bern_key;
+        }
+        last_cg_iters[1] = onsager_projected(gam2, tau, d3);
+    } else if (onsager_warm) {   // GVB_ONSAGER_WARM=1: start from the previous iteration's Q^-1 u (same probe); the solve then stops on the residual only
         const int warm = (dev.onsager_age >= 0 && dev.onsager_age < 8) ? 1 : 2;
         last_cg_iters[1] = dev_cg(dev.bern, dev.invq, tau, 0, dev.ax_invq, d3, dev.ata_invq, warm);
         dev.onsager_age = warm == 1 ? dev.onsager_age + 1 : 0;
-    } else {              // the reference: from zero (vamp.cpp:884, 1120-1127)
+    } else if (reference_sweeps) {   // the reference: from zero (vamp.cpp:884, 1120-1127), every operator product by its own sweeps
         last_cg_iters[1] = dev_cg(dev.bern, dev.invq, tau, 0, nullptr, d3, nullptr, 2);
+    } else {              // from zero; the probe recurs, so A^T A probe is cached and CG iteration 0 needs no sweep (gvb_cg_solve_cached)
+        last_cg_iters[1] = dev_cg(dev.bern, dev.invq, tau, 0, nullptr, d3, nullptr, 2, dev.ata_bern, &dev.ata_bern_state);
     }
     // <u, A^T A Q^-1 u> from the solver's own residual: Q mu = u - r  =>  tau A^T A mu = u - r - gam2 mu
     onsager_u_AtA_invq = (d3[0] - gam2 * d3[1] - d3[2]) / tau;
     onsager_valid = true;
     return gam2 * d3[1];   // gam2 * <u, Q^-1 u> = gam2 * Tr[(tau X^T X + gam2 I)^-1] / Mt; <u, mu> is the solver's own last sum
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Onsager solve on the Lanczos projection (see vamp.hpp).  Lanczos on B = A^T A from v_0 = u / ||u||:
+//   w = B v_K ; a_K = <w, v_K> ; w -= a_K v_K + b_{K-1} v_{K-1} ; b_K = ||w|| ; v_{K+1} = w / b_K          (two bed sweeps per step)
+// All dots are rank sums, so every rank holds the same T.
+// ---------------------------------------------------------------------------------------------------
+void vamp::lanczos_extend(int K_needed) {
+    gvb_ctx* ctx = dev.ctx;
+    if (!lz_started) {
+        gvb_vec xs[1] = {dev.bern};
+        double uu = 0;
+        DEV(gvb_vec_dots(ctx, 1, xs, nullptr, 1, &uu));
+        lz_unorm = sqrt(uu);
+        DEV(gvb_vec_axpby(ctx, dev.lz_cur, 1.0 / lz_unorm, dev.bern, 0.0, nullptr));
+        DEV(gvb_vec_fill(ctx, dev.lz_prev, 0.0));
+        lz_started = true;
+    }
+    while ((int)lz_a.size() < K_needed && !lz_exhausted) {
+        const int K = (int)lz_a.size();
+        DEV(gvb_dAx(ctx, dev.lz_cur, dev.tmpN));
+        DEV(gvb_dATx(ctx, dev.tmpN, dev.lz_w));
+        gvb_vec xs[1] = {dev.lz_w}, ys[1] = {dev.lz_cur};
+        double a = 0;
+        DEV(gvb_vec_dots(ctx, 1, xs, ys, 1, &a));
+        DEV(gvb_vec_axpby(ctx, dev.lz_w, 1.0, dev.lz_w, -a, dev.lz_cur));
+        if (K > 0) DEV(gvb_vec_axpby(ctx, dev.lz_w, 1.0, dev.lz_w, -lz_b[K - 1], dev.lz_prev));
+        double ww = 0;
+        DEV(gvb_vec_dots(ctx, 1, xs, nullptr, 1, &ww));
+        const double b = sqrt(ww);
+        lz_a.push_back(a);
+        lz_b.push_back(b);
+        if (!(b > 1e-13 * std::fabs(a))) {   // the Krylov space is exhausted (tiny shards): T is complete
+            lz_b.back() = 0.0;
+            lz_exhausted = true;
+            break;
+        }
+        std::swap(dev.lz_prev, dev.lz_cur);                                               // v_{K-1} <- v_K
+        DEV(gvb_vec_axpby(ctx, dev.lz_cur, 1.0 / b, dev.lz_w, 0.0, nullptr));     // v_K <- w / b
+    }
+}
+
+// vamp::precondCG_solver(u, 0, tau, denoiser = 0) (vamp.cpp:1130-1229) in the coordinates of the Lanczos basis: u = ||u|| e_0, the operator is
+// tau T + gam2 I, inner products are Euclidean; iteration i touches coordinates <= i + 1.  Returns the iterations run and
+// d3 = {<u,u>, <u,mu>, <u,r>} with r the residual of the returned mu.
+int vamp::onsager_projected(double gam2, double tau, double* d3) {
+    const int n = CG_max_iter + 2;
+    std::vector<double> mu(n, 0.0), r(n, 0.0), z(n, 0.0), p(n, 0.0), d(n, 0.0), log(4 * (size_t)std::max(CG_max_iter, 1), 0.0);
+    const double diag = tau * (double)(N - 1) / (double)N + gam2;
+    lanczos_extend(2);
+    r[0] = lz_unorm;
+    auto dot = [&](const std::vector<double>& x, const std::vector<double>& y, int m) {
+        double s = 0;
+        for (int j = 0; j < m; j++) s += x[j] * y[j];
+        return s;
+    };
+    const double norm_v = lz_unorm;
+    for (int j = 0; j < n; j++) p[j] = z[j] = r[j] / diag;
+    double prev_onsager = 0;
+    int iters = 0;
+    for (int i = 0; i < CG_max_iter; i++) {
+        iters = i + 1;
+        lanczos_extend(i + 2);
+        const int K = (int)lz_a.size();
+        const int m = std::min(n, K);                                  // coordinates in play
+        for (int j = 0; j < m; j++) {                                   // d = (tau T + gam2) p   (lmmse_mult, vamp.cpp:1074-1118)
+            double t = lz_a[j] * p[j];
+            if (j > 0) t += lz_b[j - 1] * p[j - 1];
+            if (j + 1 < m) t += lz_b[j] * p[j + 1];
+            d[j] = t * tau + gam2 * p[j];
+        }
+        const double rz = dot(r, z, m);
+        const double alpha = rz / dot(d, p, m);
+        for (int j = 0; j < m; j++) mu[j] += alpha * p[j];
+        const double norm_mu = sqrt(dot(mu, mu, m));
+        const double onsager = gam2 * (lz_unorm * mu[0]);             // gam2 <u, mu>
+        const double ons_rel = (onsager != 0.0) ? std::fabs((onsager - prev_onsager) / onsager) : 1.0;
+        for (int j = 0; j < m; j++) r[j] -= d[j] * alpha;              // the residual of the returned mu in every exit path
+        if (ons_rel < 1e-8) {                                          // vamp.cpp:1174-1193
+            log[4 * i + 0] = -1.0; log[4 * i + 1] = norm_mu; log[4 * i + 2] = -1.0; log[4 * i + 3] = ons_rel;
+            break;
+        }
+        prev_onsager = onsager;
+        double beta = 1.0 / rz;
+        for (int j = 0; j < m; j++) z[j] = r[j] / diag;
+        beta *= dot(r, z, m);
+        for (int j = 0; j < m; j++) p[j] = z[j] + beta * p[j];
+        const double rr = dot(r, r, m);
+        const double rel_err = sqrt(rr) / norm_v;
+        log[4 * i + 0] = rel_err; log[4 * i + 1] = norm_mu; log[4 * i + 2] = sqrt(rr) / diag / norm_v; log[4 * i + 3] = ons_rel;
+        if (rel_err < 1e-5) break;                                     // vamp.cpp:1217-1223
+    }
+    print_cg_log(log, iters, 0);
+    d3[0] = lz_unorm * lz_unorm;
+    d3[1] = lz_unorm * mu[0];
+    d3[2] = lz_unorm * r[0];
+    return iters;
 }
 
 // ---------------------------------------------------------------------------------------------------

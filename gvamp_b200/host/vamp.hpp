@@ -78,6 +78,20 @@ private:
     // start the reference gives its LMMSE solve (vamp.cpp:591-600), applied to its second solve.  It changes the solver's path: the
     // successive-difference Onsager exit presumes a zero start, so such a solve stops on ||r||/||rhs|| < 1e-5 only (cg.cu).
     bool onsager_warm = false;
+    // The Onsager solve on the Lanczos projection of A^T A (default; GVB_ONSAGER_LANCZOS=0 or GVB_REFERENCE_SWEEPS=1: by bed sweeps).
+    // The probe u is the same vector in every VAMP iteration and Krylov spaces are shift-invariant, K(tau B + gam2 I, u) = K(B, u), so ALL
+    // of the reference's Onsager solves live in one Krylov space of B = A^T A.  Its Lanczos tridiagonal T (lz_a, lz_b) is built once, two
+    // sweeps per step, and extended only when a solve needs more steps than any before; every solve is then the reference's
+    // preconditioned CG recurrences, exit tests and log lines run literally on the (K x K) projected operator tau T + gam2 I in host
+    // memory: no bed sweep.  Only scalars leave the solve (alpha2 and the trace term of updateNoisePrec), exactly what the loop consumes.
+    bool onsager_lanczos = true;
+    std::vector<double> lz_a, lz_b;   // T = tridiag(lz_b, lz_a, lz_b), K = lz_a.size()
+    double lz_unorm = 0;              // ||u||
+    bool lz_started = false, lz_exhausted = false;
+    long lz_key = -1;
+    void lanczos_extend(int K_needed);
+    int onsager_projected(double gam2, double tau, double* d3);
+    void print_cg_log(const std::vector<double>& log, int iters, int denoiser);
     bool onsager_valid = false;
     double onsager_u_AtA_invq = 0;
     // sums of the iteration's batched reductions (gvb_vec_reduce_batch), consumed by err_measures / updateNoisePrec:
@@ -103,6 +117,9 @@ private:
         int onsager_age = -1;
         gvb_vec aty = nullptr;      // A^T y: y is constant over the linear model's iterations, so the reference's per-iteration
         bool aty_valid = false;     // sweep (vamp.cpp:588) is done once and reused until y is uploaded again
+        gvb_vec lz_prev = nullptr, lz_cur = nullptr, lz_w = nullptr;   // Lanczos vectors v_{K-1}, v_K and scratch (onsager_projected)
+        gvb_vec ata_bern = nullptr; // A^T A bern: the probe is the same vector in every iteration, so the operator product of the first CG
+        int ata_bern_state = 0;     // iteration of the zero-started Onsager solve comes from this cache (gvb_cg_solve_cached): 2 sweeps less
         bool bern_valid = false;    // dev.bern holds the Onsager probe of (seed, shard): the reference re-draws the SAME probe every
         long bern_key = -1;         // iteration (mt19937{seed + S}, vamp.cpp:875-882), so it is drawn and uploaded once
     } dev;
@@ -129,7 +146,7 @@ private:
     void dev_close();
     void dev_denoise(double g1_prec, double* sum_d, double* dist2);
     int dev_cg(gvb_vec rhs, gvb_vec mu, double tau, int denoiser, gvb_vec ax_mu = nullptr, double* dots3 = nullptr, gvb_vec ata_mu = nullptr,
-               int have_start = 0);
+               int have_start = 0, gvb_vec ata_rhs = nullptr, int* ata_rhs_state = nullptr);
     void sync_host(gvb_vec v, std::vector<double>& h, size_t n);
     void store_scaled(gvb_vec v, const std::string& path, double div, int S);
 

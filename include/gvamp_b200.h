@@ -243,6 +243,15 @@ int gvb_cg_solve_ex(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double ga
 int gvb_cg_solve_warm(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters,
                       double* rel_res, gvb_vec ax_mu, gvb_vec ata_mu, int have_start, double* dots3);
 
+/* Zero-start solve against a right-hand side that recurs (the Onsager probe: the same Rademacher vector in every VAMP iteration,
+ * vamp.cpp:875-882).  mu is cleared.  ata_rhs (M-vector) caches A^T A rhs: with a zero start the first search direction is rhs / diag,
+ * so the operator product of CG iteration 0 is (tau * ata_rhs + gam2 * rhs) / diag and needs no bed sweep.  *ata_rhs_state: 0 = the
+ * cache is empty (iteration 0 sweeps and fills it, the state becomes 1), 1 = filled for THIS rhs and THIS matrix / mask (the caller
+ * resets it to 0 when either changes, see gvb_layout_generation).  Same iterates as gvb_cg_solve up to the fixed-point error of the
+ * sweeps; two sweeps less per solve. */
+int gvb_cg_solve_cached(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters,
+                        double* rel_res, gvb_vec ata_rhs, int* ata_rhs_state, double* dots3);
+
 /* ---- XXT form of the LMMSE step (--use-XXT-denoiser 1) ---------------------------------------------- */
 /* data::compute_people_statistics, data.cpp:548-640: per individual, over ALL markers (summed over the ranks): number of
  * non-missing genotypes, mean and inverse-variance-like scale sqrt((n-1)/(S2 - n mean^2)) of the standardised genotypes;

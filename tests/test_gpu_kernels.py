@@ -672,3 +672,32 @@ def test_layout_generation_counts_reloads(C, oracle):
         ctx.load_host(bed[:200], 500)
         g3 = ctx.layout_generation()
     assert g0 < g1 < g2 < g3
+
+
+def test_cg_cached_operator_product(C, oracle):
+    """gvb_cg_solve_cached: a zero-start solve against a recurring right-hand side (the Onsager probe) takes the operator product of
+    its first iteration from a cache of A^T A rhs.  First call: fills the cache, same sweeps as gvb_cg_solve; later calls (other tau /
+    gam2): two sweeps less, the same iteration count and the same solution up to the fixed-point error of the sweeps."""
+    N, M = 3000, 2600
+    bed = oracle.synth_bed(47, 0, M, N, miss_rate=0.01)
+    probe = oracle.bernoulli_probe(5, 0, M, M)
+    with make_ctx(C, "lut") as ctx:
+        ctx.load_host(bed, N).compute_stats(1.0)
+        rhs, mu, mu_plain, cache = ctx.vecM(probe), ctx.vecM(), ctx.vecM(), ctx.vecM()
+        state = [0]
+        for k, (tau, gam2) in enumerate(((2.0, 0.7), (1.3, 0.2), (3.1, 5.0))):
+            mu_plain.fill(0.0)
+            s0 = ctx.sweeps()
+            its_plain, log_plain = ctx.cg_solve(rhs, mu_plain, tau, gam2, 30, 0)
+            s1 = ctx.sweeps()
+            its, log, d3 = ctx.cg_solve_cached(rhs, mu, tau, gam2, 30, 0, cache, state)
+            s2 = ctx.sweeps()
+            assert state[0] == 1 and its == its_plain
+            assert (s2 - s1) == (s1 - s0) - (0 if k == 0 else 2), (k, s1 - s0, s2 - s1)
+            assert relerr(mu.download(), mu_plain.download()) < 1e-6
+            assert np.isclose(d3[1], probe @ mu.download()[:M], rtol=1e-10)
+        ata = cache.download()[:M]
+        tmpN, tmpM = ctx.vecN(), ctx.vecM()
+        ctx.dAx(rhs, tmpN)
+        ctx.dATx(tmpN, tmpM)
+        assert relerr(ata, tmpM.download()[:M]) < 1e-6

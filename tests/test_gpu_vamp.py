@@ -164,8 +164,10 @@ def test_cg_by_products_leave_the_outputs_unchanged(oracle, tmp_path, monkeypatc
     assert relerr(outs["0"][0], outs["1"][0]) < 1e-5 and np.allclose(outs["0"][1], outs["1"][1], rtol=1e-5)
     assert np.allclose(outs["0"][2], outs["1"][2], rtol=1e-5, atol=1e-9)
     saved = outs["1"][3] - outs["0"][3]
-    # 3 in the cold first iteration, 5 in the warm-started ones, and whatever the warm-started Onsager solve saves on top
-    assert saved[0] == 3 and np.all(saved[1:] >= 5), saved
+    # first iteration: the 3 by-product sweeps, minus the two Lanczos steps that the projected Onsager solve builds beyond the solve's own
+    # iteration count; later iterations: 5 (by-products + the sweep-free initial residual of the warm-started LMMSE solve) plus ALL
+    # sweeps of the Onsager solve, which runs on the cached Lanczos projection of A^T A (vamp::onsager_projected)
+    assert saved[0] >= 0 and np.all(saved[1:] >= 5 + 4), saved
 
 
 def test_test_mode_r2(oracle, tmp_path):
@@ -275,16 +277,18 @@ def _stress_prior():
     return probs, vars_
 
 
-@pytest.mark.parametrize("mode", ["default", "reference_sweeps", "onsager_warm", "cg_lag0"])
+@pytest.mark.parametrize("mode", ["default", "reference_sweeps", "onsager_sweeps", "onsager_warm", "cg_lag0"])
 def test_stress_case_matches_reference(oracle, tmp_path, mode):
     """An ill-conditioned run against the reference's files (tests/golden/make_golden.py:case_vamp_stress): M/N = 5, rho = 0.05 (the
     dnanexus damping), 30 iterations, the reference's 23-component prior shape.  The default path (CG by-products instead of the
-    three extra sweeps, zero-started Onsager solve, device-resident CG scalars) and the variants GVB_REFERENCE_SWEEPS=1 (the
-    reference's own sweeps), GVB_CG_LAG=0 (no speculative iteration) must stay within the north_star's 1e-4 over all 30 iterations
+    three extra sweeps, the Onsager solve on the Lanczos projection of A^T A - no bed sweep after the first iteration -, device-resident
+    CG scalars) and the variants GVB_REFERENCE_SWEEPS=1 (the reference's own sweeps), GVB_ONSAGER_LANCZOS=0 (the Onsager solve by bed
+    sweeps, A^T A probe cached), GVB_CG_LAG=0 (no speculative iteration) must stay within the north_star's 1e-4 over all 30 iterations
     and run the reference's number of CG iterations; GVB_ONSAGER_WARM=1 changes the solver's path on purpose (opt-in)
     and is held to a looser 5e-4."""
     g = golden("vamp_stress.npz")
-    env = {"reference_sweeps": {"GVB_REFERENCE_SWEEPS": "1"}, "onsager_warm": {"GVB_ONSAGER_WARM": "1"}, "cg_lag0": {"GVB_CG_LAG": "0"}}.get(mode, {})
+    env = {"reference_sweeps": {"GVB_REFERENCE_SWEEPS": "1"}, "onsager_warm": {"GVB_ONSAGER_WARM": "1"}, "cg_lag0": {"GVB_CG_LAG": "0"},
+           "onsager_sweeps": {"GVB_ONSAGER_LANCZOS": "0"}}.get(mode, {})
     outd, log, _ = _run_case(oracle, tmp_path, g, "lut", env)
     iters = int(g["iterations_done"])
     tol = 5e-4 if mode == "onsager_warm" else TOL_FINAL

@@ -504,7 +504,10 @@ def ours_arm(args):
                    "sweeps_per_step": res["sweeps"], "cg_iters_per_step": res["cg"], "ms_per_sweep": (prof["ax_ms"] + prof["atx_ms"]) / max(n_sw, 1),
                    "non_sweep_ms_per_step": (res["ms_dev"] - prof["ax_ms"] - prof["atx_ms"]) / K, "host_syncs_per_step": res["host_syncs"] / K,
                    "l2_policy": "inputs (>= 12 GB packed bed per sweep at the default workload) larger than the 126 MB L2",
-                   "kernels": os.environ.get("GVB_KERNELS", "tile (gen 2)"), "twin_layout": twin, "setup_s": t_setup, **res.get("extra", {})},
+                   "kernels": os.environ.get("GVB_KERNELS", "tile (gen 2)"), "twin_layout": twin, "setup_s": t_setup,
+                   "onsager_solve": "by bed sweeps" if (os.environ.get("GVB_ONSAGER_LANCZOS") == "0" or os.environ.get("GVB_REFERENCE_SWEEPS") == "1")
+                   else "the reference's CG on the cached Lanczos projection of A^T A (no bed sweep after the first iteration; DESIGN.md section 7)",
+                   **res.get("extra", {})},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
                 "ms_per_step": ms_e2e / K, "sweeps_per_step": res["e2e_sweeps"], "files_written_per_step": res.get("files", 0), "note": res["e2e_note"]},

@@ -63,7 +63,7 @@ int gvb_reduce_finish(gvb_ctx* c, int nblocks, int K, bool sync, double* res_hos
 }
 
 static inline int red_blocks(const gvb_ctx* c, long n) {
-    long b = (n + 1023) / 1024;
+    long b = (n + 511) / 512;
     return (int)std::max(1l, std::min(b, (long)GVB_RED_BLOCKS));
 }
 
@@ -390,7 +390,7 @@ extern "C" int gvb_em_stats(gvb_ctx* c, gvb_vec r1, double gam1, double lambda, 
         if (vars[k] > a.max_sigma) a.max_sigma = vars[k];
     }
     int K = 2 * L - 1;
-    int blocks = (int)std::max(1l, std::min((r1->n + 511) / 512, (long)GVB_RED_BLOCKS));
+    int blocks = (int)std::max(1l, std::min((r1->n + 255) / 256, (long)GVB_RED_BLOCKS));
     em_stats_kernel<<<blocks, 128, 0, c->stream>>>(r1->d, r1->n, a, c->red_partial);
     GVB_LAUNCHED(c);
     return gvb_reduce_finish(c, blocks, K, true, sums);

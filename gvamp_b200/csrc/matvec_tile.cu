@@ -1,4 +1,4 @@
-// matvec_tile.cu -- generation-2 main kernels of the bed mat-vecs for sm_100a.
+// matvec_tile.cu -- the main kernels of the bed mat-vecs for sm_100a (tile walks) with their pre- and post-kernels.
 //
 // Both products (reference data::Ax data.cpp:848-1011 and dot_product/ATx data.cpp:728-835) run on ONE
 // skeleton.  The unit of data movement is a TILE = 32 marker groups x 1 stripe = 32 rows of 128 B =
@@ -23,15 +23,19 @@
 //   per-lane slot byte (8 registers hold the 32 slot bytes); the table base is a link-time constant
 //   folded into the LDS immediate.  Per 4 genotypes: [LOP3 + IMAD +] PRMT + LDS + IADD/IMAD.
 //
-// A CTA = NW consumer warps + one producer warp.  The consumers walk their tiles step by step and share the table
-// tile of the step (X.v: warps = NW stripes, same marker tile; X^T.u: warps = NW marker tiles, same stripe); the
-// producer warp fetches the table tiles with 16-byte cp.async into a double buffer interleaved at 128 B.  Producer and
-// consumers meet on two pairs of mbarriers (full / empty per buffer, struct TabPipe) instead of a __syncthreads per
-// step, so a warp whose bed tile arrives late does not stall the others.  Bed tiles are per-warp, NS stages deep.
-// Persistent CTAs pull rectangular work items from an atomic counter; items are ordered so that CTAs running at the
-// same time share their table tiles in L2.
+// A CTA = NW consumer warps + one producer warp.  The consumers walk their tiles step by step and share the table tile of the step
+// (X.v: warps = NW stripes, same marker tile; X^T.u: warps = NW marker tiles, same stripe).  Two ways to stage the tables:
+//   * pair mode (ax_pair_kernel / atx_pair_kernel, the default for X^T.u and for X.v on the twin): the tables of two consecutive steps
+//     are interleaved in global memory the way they are addressed in shared memory, one 64 KB region = one pair = ONE cp.async.bulk issued
+//     by one elected thread; two regions double-buffer pairs of steps; 12 consumer warps x 2 bed stages fill the 227 KB (PairLayout);
+//   * producer warp (ax_tile_kernel / atx_tile_kernel; the gathering X.v kernel, which needs its 15 warps): 16-byte cp.async into a
+//     two-step double buffer interleaved at 128 B.
+// Producer and consumers meet on two pairs of mbarriers (full / empty per buffer or region) instead of a __syncthreads per step, so a
+// warp whose bed tile arrives late does not stall the others.  Bed tiles are per-warp, NS stages deep.  Persistent CTAs pull
+// rectangular work items from an atomic counter; items are ordered so that CTAs running at the same time share their table tiles in L2.
 //
-// Arithmetic: fixed point, exact after quantisation, see matvec_lut.cu (scales, pre- and post-kernels).
+// Arithmetic: fixed point, exact after quantisation, with one power-of-two scale class per stripe / marker tile (see "Scale classes"
+// below; pre- and post-kernels at the end of this file).
 #include "gvb_internal.cuh"
 
 namespace {

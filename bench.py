@@ -624,8 +624,11 @@ def run_linear(args, D, ctx, H, N, Mt, S, M, logf):
                     "ms_per_step_median_host_clock": float(np.median(wall)),
                     "note_on_K": "iterations/s of a run timed from its iteration 1 depends on K by construction (iteration 1 solves from zero: 4x the sweeps of a "
                                  "late iteration); ms_per_sweep and the per-step list are the K-independent figures"}
-    out["e2e_note"] = ("a fresh run of the same iterations: y re-uploaded from pinned host memory every step (A^T y recomputed: one more sweep per step), "
-                       "x1_hat / r1 / r2 / x2_hat / z1 read back every step and written to the reference's per-iteration files")
+    out["e2e_note"] = ("a fresh run of the same iterations: y re-uploaded from pinned host memory every step (the library compares it bit for bit with "
+                       "the resident copy on the device and keeps A^T y while it is unchanged, as in a real run, whose y never changes; "
+                       "GVB_ATY_CACHE=0 recomputes A^T y after every upload: one more sweep per step), "
+                       "x1_hat / r1 / r2 / x2_hat / z1 read back every step into pinned host memory, scaled and written to the reference's "
+                       "per-iteration files by a background task; the timed region ends when the last file is closed")
     return out
 
 

@@ -63,6 +63,7 @@ SIGNATURES = {
     "gvb_vec_len": (cl, [vp]),
     "gvb_vec_ptr": (vp, [vp]),
     "gvb_vec_upload": (ci, [vp, vp, c_f64p, cl]),
+    "gvb_vec_upload_changed": (ci, [vp, vp, vp, c_f64p, cl, ctypes.POINTER(ci)]),
     "gvb_vec_download": (ci, [vp, vp, c_f64p, cl]),
     "gvb_vec_copy": (ci, [vp, vp, vp]),
     "gvb_vec_fill": (ci, [vp, vp, cd]),
@@ -183,6 +184,13 @@ class Vec:
         a, p = _f64(a)
         _chk(self.ctx.L.gvb_vec_upload(self.ctx.h, self.h, p, len(a)), self.ctx.L)
         return self
+
+    def upload_changed(self, a, stage):
+        """upload + whether any bit of the vector changed (gvb_vec_upload_changed); `stage` is a scratch Vec"""
+        a, p = _f64(a)
+        changed = ci(-1)
+        _chk(self.ctx.L.gvb_vec_upload_changed(self.ctx.h, self.h, stage.h, p, len(a), ctypes.byref(changed)), self.ctx.L)
+        return bool(changed.value)
 
     def download(self, n=None):
         n = len(self) if n is None else n

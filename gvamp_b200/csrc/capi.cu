@@ -269,6 +269,34 @@ extern "C" int gvb_vec_download(gvb_ctx* c, gvb_vec src, double* dst, long n) {
     GVB_CUDA(cudaStreamSynchronize(c->stream));
     return GVB_OK;
 }
+// Upload that reports whether the vector's content changed (bitwise): host code that caches a product of the vector (A^T y of the
+// linear model) keeps it when the caller re-sends identical data.
+__global__ void upload_compare_kernel(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ stage, long n, int* __restrict__ changed) {
+    int diff = 0;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        unsigned long long a = stage[i];
+        if (a != dst[i]) {
+            dst[i] = a;
+            diff = 1;
+        }
+    }
+    if (__syncthreads_or(diff) && threadIdx.x == 0) atomicOr(changed, 1);
+}
+extern "C" int gvb_vec_upload_changed(gvb_ctx* c, gvb_vec dst, gvb_vec stage, const double* src, long n, int* changed) {
+    GVB_ARG(c && dst && stage && src && changed && dst != stage && n >= 0 && n <= dst->n && n <= stage->n, "upload length / staging vector");
+    int* flag = reinterpret_cast<int*>(c->scal + 60);
+    GVB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+    GVB_CUDA(cudaMemcpyAsync(stage->d, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (n > 0) {
+        upload_compare_kernel<<<(unsigned)std::min<long>((n + 255) / 256, 1184), 256, 0, c->stream>>>(
+            reinterpret_cast<unsigned long long*>(dst->d), reinterpret_cast<const unsigned long long*>(stage->d), n, flag);
+        GVB_LAUNCHED(c);
+    }
+    GVB_CUDA(cudaMemcpyAsync(changed, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    GVB_CUDA(cudaStreamSynchronize(c->stream));
+    c->host_syncs++;
+    return GVB_OK;
+}
 // Snapshots: the vector is copied to a staging buffer on the library stream (ordered with the kernels that produce and later
 // overwrite it), then leaves for pinned host memory on a second stream, overlapping whatever the library stream does next.
 extern "C" int gvb_snapshot_begin(gvb_ctx* c, gvb_vec src, long n, int slot) {

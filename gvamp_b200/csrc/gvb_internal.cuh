@@ -32,7 +32,7 @@
 #define GVB_GROUP 4               // markers per interleaved word
 #define GVB_GROUP_TILE 32         // marker groups per table tile (Mg_pad is a multiple of this)
 #define GVB_PAD_BYTE 0x55u
-#define GVB_SNAP_SLOTS 8
+#define GVB_SNAP_SLOTS 16
 
 struct gvb_vec_s {
     double* d;

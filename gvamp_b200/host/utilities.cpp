@@ -123,10 +123,10 @@ void store_vec_to_file(std::string filepath, std::vector<double> vec) {
 }
 
 // raw doubles, this shard at byte offset S*8; the file is created but never truncated
-void mpi_store_vec_to_file(std::string filepath, std::vector<double> vec, int S, int M) {
+void store_doubles_at(const std::string& filepath, const double* vec, int S, int M) {
     int fd = open(filepath.c_str(), O_CREAT | O_WRONLY, 0644);
     if (fd < 0) return;
-    const char* p = reinterpret_cast<const char*>(vec.data());
+    const char* p = reinterpret_cast<const char*>(vec);
     size_t total = (size_t)M * sizeof(double), done = 0;
     while (done < total) {
         ssize_t w = pwrite(fd, p + done, total - done, (off_t)S * (off_t)sizeof(double) + (off_t)done);
@@ -135,6 +135,8 @@ void mpi_store_vec_to_file(std::string filepath, std::vector<double> vec, int S,
     }
     close(fd);
 }
+
+void mpi_store_vec_to_file(std::string filepath, std::vector<double> vec, int S, int M) { store_doubles_at(filepath, vec.data(), S, M); }
 
 std::vector<double> mpi_read_vec_from_file(std::string filename, int M, int S) {
     std::vector<double> vec(M, 0.0);

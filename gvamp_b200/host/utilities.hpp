@@ -25,6 +25,7 @@ std::vector<double> read_vec_from_file(std::string filename, int M, int S);
 std::vector<double> mpi_read_vec_from_file(std::string filename, int M, int S);
 void store_vec_to_file(std::string filepath, std::vector<double> vec);
 void mpi_store_vec_to_file(std::string filepath, std::vector<double> vec, int S, int M);
+void store_doubles_at(const std::string& filepath, const double* vec, int S, int M);   // the same write without the by-value copy
 
 double inner_prod(std::vector<double> const& u, std::vector<double> const& v, int sync);
 double l2_norm2(std::vector<double> const& u, int sync);

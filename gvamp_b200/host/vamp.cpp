@@ -135,6 +135,7 @@ void vamp::dev_open(data* dataset) {
 }
 
 void vamp::dev_close() {
+    wait_writes();   // a batch in flight reads the pinned snapshot buffers of the context that is being left
     lz_started = lz_exhausted = false;   // the Lanczos vectors go with the device state
     lz_a.clear();
     lz_b.clear();
@@ -158,91 +159,86 @@ void vamp::store_scaled(gvb_vec v, const std::string& path, double div, int S) {
     sync_host(v, h, M);
     if (!files_enabled()) return;
     for (double& x : h) x = x / div;
-    mpi_store_vec_to_file(path, h, S, M);
+    store_doubles_at(path, h.data(), S, M);
 }
 
 // One output vector of the iteration (the z1 csv of vamp.cpp:435-436 and the x1_hat / r1 / r2 / x2_hat stores of
-// vamp.cpp:453,462,542,612).  Asynchronous form: a snapshot starts here and flush_outputs() finishes it.
+// vamp.cpp:453,462,542,612).  Asynchronous form: a snapshot starts here (device -> pinned host memory on the copy stream, under the
+// LMMSE sweeps) and flush_outputs() hands the landed buffers to a background task that scales and writes them.
 void vamp::emit_output(int which, gvb_vec v, size_t n, const std::string& path, double scale, int S) {
     snap_path[which] = path;
     if (async_outputs) {
-        DEV(gvb_snapshot_begin(dev.ctx, v, (long)n, which));
+        DEV(gvb_snapshot_begin(dev.ctx, v, (long)n, which + SNAP_COUNT * snap_set));
         snap_open[which] = true;
         return;
     }
     std::vector<double> h;
     sync_host(v, h, n);
-    finish_output(which, h.data(), n, scale, S);
-    start_writes();
+    finish_output(which, h.data(), n, path, scale, S);
 }
 
-void vamp::finish_output(int which, const double* h, size_t n, double scale, int S) {
-    const std::string& path = snap_path[which];
+// host mirror + file of one landed output.  Runs on the background task in the asynchronous form: until wait_writes() nothing else
+// reads z1 / x1_hat / x1_hat_stored (their readers - the association tests, linear_end() - come after the loop).
+void vamp::finish_output(int which, const double* h, size_t n, const std::string& path, double scale, int S) {
     if (which == SNAP_Z1) {
         z1.assign(h, h + n);
-        if (files_enabled() && rank == 0) pending_writes.push_back({path, z1, S, (int)n, true});
+        if (!files_enabled() || rank != 0) return;
+        // one value per line in the stream's default format (%g, 6 significant digits), like `file << v << std::endl` of the
+        // reference (vamp.cpp:435-436); std::to_chars(general, 6) is that format at a fraction of the iostream cost
+        // (400k values per iteration at biobank scale: tens of milliseconds of host time)
+        std::string buf;
+        buf.reserve(n * 14);
+        char tmp[40];
+        for (size_t i = 0; i < n; i++) {
+            auto r = std::to_chars(tmp, tmp + sizeof(tmp), h[i], std::chars_format::general, 6);
+            buf.append(tmp, r.ptr);
+            buf.push_back('\n');
+        }
+        std::ofstream f(path, std::ios::binary);
+        f.write(buf.data(), (std::streamsize)buf.size());
         return;
     }
     if (which == SNAP_X1) {
         x1_hat.assign(h, h + n);
-        for (size_t i = 0; i < n; i++) x1_hat_stored[i] = x1_hat[i] / scale;
-        if (files_enabled()) pending_writes.push_back({path, x1_hat_stored, S, M, false});
+        for (size_t i = 0; i < n; i++) x1_hat_stored[i] = h[i] / scale;
+        if (files_enabled()) store_doubles_at(path, x1_hat_stored.data(), S, M);
         return;
     }
     if (!files_enabled()) return;
-    std::vector<double> scaled(n);
-    for (size_t i = 0; i < n; i++) scaled[i] = h[i] / scale;
-    pending_writes.push_back({path, std::move(scaled), S, M, false});
+    out_scratch.resize(n);
+    for (size_t i = 0; i < n; i++) out_scratch[i] = h[i] / scale;
+    store_doubles_at(path, out_scratch.data(), S, M);
 }
 
-// The iteration's files (the z1 csv is 400k formatted doubles at biobank scale: tens of milliseconds of host time) are written by a
-// background task while the next iteration's kernels run; at most one batch is in flight, and wait_writes() is called before
-// anything reads the files or the object goes away.  GVB_ASYNC_OUT=0: written in place.
+// At most one batch of outputs is in flight: it reads one of the two sets of pinned snapshot buffers while the next iteration's
+// snapshots land in the other set, and wait_writes() is called before anything reads the files or the host mirrors, or the object
+// goes away.  GVB_ASYNC_OUT=0: everything in place, on the calling thread.
 void vamp::wait_writes() {
     if (writer.valid()) writer.get();
 }
 
-void vamp::start_writes() {
-    if (pending_writes.empty()) return;
-    wait_writes();
-    auto job = [batch = std::move(pending_writes)]() {
-        for (const OutFile& o : batch) {
-            if (o.text) {
-                // one value per line in the stream's default format (%g, 6 significant digits), like `file << v << std::endl` of the
-                // reference (vamp.cpp:435-436); std::to_chars(general, 6) is that format at a fraction of the iostream cost
-                // (400k values per iteration at biobank scale)
-                std::string buf;
-                buf.reserve(o.data.size() * 14);
-                char tmp[40];
-                for (double v : o.data) {
-                    auto r = std::to_chars(tmp, tmp + sizeof(tmp), v, std::chars_format::general, 6);
-                    buf.append(tmp, r.ptr);
-                    buf.push_back('\n');
-                }
-                std::ofstream f(o.path, std::ios::binary);
-                f.write(buf.data(), (std::streamsize)buf.size());
-            } else {
-                mpi_store_vec_to_file(o.path, o.data, o.S, o.M);
-            }
-        }
-    };
-    pending_writes.clear();
-    if (async_outputs)
-        writer = std::async(std::launch::async, std::move(job));
-    else
-        job();
-}
-
 void vamp::flush_outputs(double scale, int S) {
+    struct Landed {
+        int which;
+        const double* h;
+        size_t n;
+        std::string path;
+    };
+    std::vector<Landed> landed;
     for (int which = 0; which < SNAP_COUNT; which++) {
         if (!snap_open[which]) continue;
         const double* h = nullptr;
         long n = 0;
-        DEV(gvb_snapshot_wait(dev.ctx, which, &h, &n));
+        DEV(gvb_snapshot_wait(dev.ctx, which + SNAP_COUNT * snap_set, &h, &n));
         snap_open[which] = false;
-        finish_output(which, h, (size_t)n, scale, S);
+        landed.push_back({which, h, (size_t)n, snap_path[which]});
     }
-    start_writes();
+    if (landed.empty()) return;
+    wait_writes();     // the batch before this one: its buffer set is the one the next iteration snapshots into
+    snap_set ^= 1;
+    writer = std::async(std::launch::async, [this, landed = std::move(landed), scale, S]() {
+        for (const Landed& l : landed) finish_output(l.which, l.h, l.n, l.path, scale, S);
+    });
 }
 
 void vamp::dev_denoise(double g1_prec, double* sum_d, double* dist2) {
@@ -323,8 +319,16 @@ std::vector<double> vamp::infere_linear(data* dataset) {
 
 void vamp::upload_iteration_inputs(const double* y_host, const double* r1_host) {
     if (y_host) {
-        DEV(gvb_vec_upload(dev.ctx, dev.y, y_host, N));
-        dev.aty_valid = false;
+        // A^T y is kept while the y that arrives is bit for bit the resident one (compared on the device; tmpN is free between
+        // iterations); GVB_ATY_CACHE=0: every upload invalidates it
+        const char* e = getenv("GVB_ATY_CACHE");
+        const bool keep = !(e && e[0] == '0');
+        int changed = 1;
+        if (keep && dev.aty_valid)
+            DEV(gvb_vec_upload_changed(dev.ctx, dev.y, dev.tmpN, y_host, N, &changed));
+        else
+            DEV(gvb_vec_upload(dev.ctx, dev.y, y_host, N));
+        if (changed) dev.aty_valid = false;
     }
     if (r1_host) DEV(gvb_vec_upload(dev.ctx, dev.r1, r1_host, M));
 }

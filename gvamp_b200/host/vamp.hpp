@@ -123,24 +123,19 @@ private:
         bool bern_valid = false;    // dev.bern holds the Onsager probe of (seed, shard): the reference re-draws the SAME probe every
         long bern_key = -1;         // iteration (mt19937{seed + S}, vamp.cpp:875-882), so it is drawn and uploaded once
     } dev;
-    // the iteration's output vectors leave the device as asynchronous snapshots (gvb_snapshot_begin) while the LMMSE sweeps run
-    // and are scaled / written by flush_outputs() at the end of the iteration; GVB_ASYNC_OUT=0: synchronous, in place
+    // the iteration's output vectors leave the device as asynchronous snapshots (gvb_snapshot_begin) while the LMMSE sweeps run;
+    // flush_outputs() at the end of the iteration hands the landed pinned buffers to a background task that scales and writes
+    // them under the next iteration's kernels (two sets of snapshot slots alternate); GVB_ASYNC_OUT=0: synchronous, in place
     enum { SNAP_Z1 = 0, SNAP_X1, SNAP_R1, SNAP_R2, SNAP_X2, SNAP_COUNT };
     bool async_outputs = true;
+    int snap_set = 0;
     std::string snap_path[SNAP_COUNT];
     bool snap_open[SNAP_COUNT] = {false, false, false, false, false};
+    std::vector<double> out_scratch;   // the scaled copy of r1 / r2 / x2_hat on its way to a file
     void emit_output(int which, gvb_vec v, size_t n, const std::string& path, double scale, int S);
-    void finish_output(int which, const double* h, size_t n, double scale, int S);
+    void finish_output(int which, const double* h, size_t n, const std::string& path, double scale, int S);
     void flush_outputs(double scale, int S);
-    struct OutFile {
-        std::string path;
-        std::vector<double> data;
-        int S, M;
-        bool text;   // one formatted value per line (the z1 csv) instead of raw doubles at byte offset S*8
-    };
-    std::vector<OutFile> pending_writes;
-    std::future<void> writer;   // the previous iteration's files, written while this iteration's kernels run
-    void start_writes();
+    std::future<void> writer;   // the previous iteration's outputs, scaled and written while this iteration's kernels run
     void wait_writes();
     void dev_open(data* dataset);
     void dev_close();

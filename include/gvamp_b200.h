@@ -159,11 +159,16 @@ long gvb_vec_len(gvb_vec v);
 void* gvb_vec_ptr(gvb_vec v);                                   /* raw device pointer */
 int gvb_vec_upload(gvb_ctx* ctx, gvb_vec dst, const double* src, long n);
 int gvb_vec_download(gvb_ctx* ctx, gvb_vec src, double* dst, long n);
+/* gvb_vec_upload that also reports whether any bit of dst[0..n) changed (*changed = 0 / 1).  `stage` is a scratch vector of at
+ * least n entries (overwritten).  For host code that keeps products of an input vector: vamp::infere_linear computes A^T y in every
+ * iteration from the y it holds in host memory (vamp.cpp:588); here A^T y is kept while the y that arrives is the one already
+ * resident. */
+int gvb_vec_upload_changed(gvb_ctx* ctx, gvb_vec dst, gvb_vec stage, const double* src, long n, int* changed);
 /* Asynchronous snapshot of the first n entries of a vector into pinned host memory: the per-iteration outputs of
  * vamp::infere_linear (z1 / x1_hat / r1 / r2 / x2_hat files, vamp.cpp:435-462,542,612) leave the device while the LMMSE
  * sweeps run.  begin: ordered on the library stream like a copy kernel (the vector may be overwritten right after the
  * call); wait: blocks until that snapshot is in host memory and returns the library-owned pinned buffer, valid until
- * the next begin on the same slot (0..7) or gvb_ctx_destroy. */
+ * the next begin on the same slot (0..15) or gvb_ctx_destroy. */
 int gvb_snapshot_begin(gvb_ctx* ctx, gvb_vec src, long n, int slot);
 int gvb_snapshot_wait(gvb_ctx* ctx, int slot, const double** host, long* n);
 int gvb_vec_copy(gvb_ctx* ctx, gvb_vec dst, gvb_vec src);

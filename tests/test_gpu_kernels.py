@@ -296,7 +296,35 @@ def test_snapshot_is_ordered_with_the_stream(C, oracle):
         ctx.snapshot_begin(vb, 5, 0)               # reuse with another length
         assert np.array_equal(ctx.snapshot_wait(0), -a[:5])
         with pytest.raises(RuntimeError):
-            ctx.snapshot_begin(va, M, 8)           # slots are 0..7
+            ctx.snapshot_begin(va, M, 16)          # slots are 0..15
+
+
+def test_upload_changed_reports_bitwise_changes(C, oracle):
+    """gvb_vec_upload_changed: the vector ends up equal to the uploaded data and the flag is set exactly when a bit differs
+    (a sign of zero counts, a re-upload of the same data does not)."""
+    N, M = 512, 30011
+    bed = oracle.synth_bed(1, 0, M, N)
+    a = np.random.default_rng(5).normal(size=M)
+    with C.Context(0) as ctx:
+        ctx.load_host(bed, N)
+        v, stage = ctx.vecM(a), ctx.vecM()
+        assert v.upload_changed(a, stage) is False
+        assert np.array_equal(v.download(M), a)
+        b = a.copy()
+        b[M - 1] = np.nextafter(b[M - 1], np.inf)          # one ulp in the last entry
+        assert v.upload_changed(b, stage) is True
+        assert np.array_equal(v.download(M), b)
+        assert v.upload_changed(b, stage) is False
+        z = b.copy()
+        z[17] = 0.0
+        assert v.upload_changed(z, stage) is True
+        z2 = z.copy()
+        z2[17] = -0.0
+        assert v.upload_changed(z2, stage) is True         # bitwise, not numeric
+        assert np.signbit(v.download(M)[17])
+        assert v.upload_changed(z2[:100], stage) is False  # prefix upload
+        with pytest.raises(RuntimeError):
+            v.upload_changed(a, v)                          # the staging vector must be another vector
 
 
 def test_vector_ops(C, oracle):

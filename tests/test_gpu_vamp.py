@@ -388,3 +388,61 @@ def test_run_mode_predict_single_matches_reference(oracle, tmp_path):
     got = np.loadtxt(outd + "g_predict.csv")
     ref = g["predict_single"]
     assert got.shape == ref.shape and np.allclose(got, ref, rtol=1e-4, atol=1e-5 * np.abs(ref).max())
+
+
+def test_reuploaded_phenotype_keeps_aty_only_while_unchanged(oracle, tmp_path, monkeypatch):
+    """The stepping interface (bench.py's end-to-end leg) re-sends y before every iteration.  vamp::upload_iteration_inputs keeps the
+    cached A^T y (vamp.cpp:588 computes it every iteration) while the uploaded y is bit for bit the resident one and drops it as soon
+    as one entry differs: same results to the last bit as a run that recomputes A^T y after every upload (GVB_ATY_CACHE=0), one sweep
+    per iteration less while y is constant."""
+    import ctypes
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    from gvamp_b200 import capi as C
+    H = bench.load_host_lib()
+    N, M, iters = 2048, 6000, 6
+    bed = oracle.synth_bed(3, 0, M, N)
+    rng = np.random.default_rng(9)
+    y = rng.normal(size=N)
+    y2 = y.copy()
+    y2[5] += 1e-3
+    f64p = ctypes.POINTER(ctypes.c_double)
+    monkeypatch.setenv("GVB_NO_FILES", "1")
+    argv = ["t", "--bed-file", "in-hbm", "--N", str(N), "--Mt", str(M), "--iterations", str(iters), "--CG-max-iter", "10", "--rho", "0.5",
+            "--probs", "0.9,0.1", "--vars", "0,0.001", "--h2", "0.5", "--stop-criteria-thr", "1e-12", "--out-dir", str(tmp_path) + "/",
+            "--out-name", "t", "--model", "linear", "--run-mode", "infere"]
+    carr = (ctypes.c_char_p * len(argv))(*[a.encode() for a in argv])
+
+    def run(ctx, dat, opt, cache, uploads):
+        monkeypatch.setenv("GVB_ATY_CACHE", cache)
+        vmp = H.gvbh_vamp_create(opt, M, 1e-6, 2.0)
+        H.gvbh_vamp_linear_begin(vmp, dat)
+        s0 = ctx.sweeps()
+        for it in range(1, iters + 1):
+            u = uploads.get(it)
+            H.gvbh_vamp_linear_iteration(vmp, dat, it, u.ctypes.data_as(f64p) if u is not None else None, None)
+        x = np.zeros(M)
+        H.gvbh_vamp_linear_end(vmp, x.ctypes.data_as(f64p), M)
+        sweeps = ctx.sweeps() - s0
+        H.gvbh_vamp_destroy(vmp)
+        return x, sweeps
+
+    with C.Context(0) as ctx:
+        ctx.load_host(bed, N)
+        opt = H.gvbh_options_create(len(argv), carr)
+        dat = H.gvbh_data_create_resident(ctx.h, y.ctypes.data_as(f64p), N, M, M, 0, 1.0)
+        same = {it: y for it in range(1, iters + 1)}
+        x_none, s_none = run(ctx, dat, opt, "1", {})
+        x_keep, s_keep = run(ctx, dat, opt, "1", same)
+        x_drop, s_drop = run(ctx, dat, opt, "0", same)
+        assert np.array_equal(x_none, x_keep) and np.array_equal(x_none, x_drop)
+        assert s_keep == s_none and s_drop == s_none + (iters - 1)
+        change = dict(same)
+        for it in range(4, iters + 1):
+            change[it] = y2
+        x_c1, s_c1 = run(ctx, dat, opt, "1", change)
+        x_c0, s_c0 = run(ctx, dat, opt, "0", change)
+        assert np.array_equal(x_c1, x_c0) and not np.array_equal(x_c1, x_none)
+        assert s_c0 - s_c1 == iters - 2   # the only recomputation left is the one at the iteration that brought the new y
+        H.gvbh_data_destroy(dat)

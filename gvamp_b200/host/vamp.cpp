@@ -165,7 +165,7 @@ void vamp::store_scaled(gvb_vec v, const std::string& path, double div, int S) {
 // One output vector of the iteration (the z1 csv of vamp.cpp:435-436 and the x1_hat / r1 / r2 / x2_hat stores of
 // vamp.cpp:453,462,542,612).  Asynchronous form: a snapshot starts here (device -> pinned host memory on the copy stream, under the
 // LMMSE sweeps) and flush_outputs() hands the landed buffers to a background task that scales and writes them.
-void vamp::emit_output(int which, gvb_vec v, size_t n, const std::string& path, double scale, int S) {
+void vamp::emit_output(int which, gvb_vec v, size_t n, const std::string& path, double scale, int S, double mul) {
     snap_path[which] = path;
     if (async_outputs) {
         DEV(gvb_snapshot_begin(dev.ctx, v, (long)n, which + SNAP_COUNT * snap_set));
@@ -174,12 +174,12 @@ void vamp::emit_output(int which, gvb_vec v, size_t n, const std::string& path, 
     }
     std::vector<double> h;
     sync_host(v, h, n);
-    finish_output(which, h.data(), n, path, scale, S);
+    finish_output(which, h.data(), n, path, scale, S, mul);
 }
 
 // host mirror + file of one landed output.  Runs on the background task in the asynchronous form: until wait_writes() nothing else
 // reads z1 / x1_hat / x1_hat_stored (their readers - the association tests, linear_end() - come after the loop).
-void vamp::finish_output(int which, const double* h, size_t n, const std::string& path, double scale, int S) {
+void vamp::finish_output(int which, const double* h, size_t n, const std::string& path, double scale, int S, double mul) {
     if (which == SNAP_Z1) {
         z1.assign(h, h + n);
         if (!files_enabled() || rank != 0) return;
@@ -200,13 +200,13 @@ void vamp::finish_output(int which, const double* h, size_t n, const std::string
     }
     if (which == SNAP_X1) {
         x1_hat.assign(h, h + n);
-        for (size_t i = 0; i < n; i++) x1_hat_stored[i] = h[i] / scale;
+        for (size_t i = 0; i < n; i++) x1_hat_stored[i] = h[i] / scale * mul;
         if (files_enabled()) store_doubles_at(path, x1_hat_stored.data(), S, M);
         return;
     }
     if (!files_enabled()) return;
     out_scratch.resize(n);
-    for (size_t i = 0; i < n; i++) out_scratch[i] = h[i] / scale;
+    for (size_t i = 0; i < n; i++) out_scratch[i] = h[i] / scale * mul;
     store_doubles_at(path, out_scratch.data(), S, M);
 }
 
@@ -217,7 +217,7 @@ void vamp::wait_writes() {
     if (writer.valid()) writer.get();
 }
 
-void vamp::flush_outputs(double scale, int S) {
+void vamp::flush_outputs(double scale, int S, double mul) {
     struct Landed {
         int which;
         const double* h;
@@ -236,8 +236,8 @@ void vamp::flush_outputs(double scale, int S) {
     if (landed.empty()) return;
     wait_writes();     // the batch before this one: its buffer set is the one the next iteration snapshots into
     snap_set ^= 1;
-    writer = std::async(std::launch::async, [this, landed = std::move(landed), scale, S]() {
-        for (const Landed& l : landed) finish_output(l.which, l.h, l.n, l.path, scale, S);
+    writer = std::async(std::launch::async, [this, landed = std::move(landed), scale, S, mul]() {
+        for (const Landed& l : landed) finish_output(l.which, l.h, l.n, l.path, scale, S, mul);
     });
 }
 

@@ -132,9 +132,10 @@ private:
     std::string snap_path[SNAP_COUNT];
     bool snap_open[SNAP_COUNT] = {false, false, false, false, false};
     std::vector<double> out_scratch;   // the scaled copy of r1 / r2 / x2_hat on its way to a file
-    void emit_output(int which, gvb_vec v, size_t n, const std::string& path, double scale, int S);
-    void finish_output(int which, const double* h, size_t n, const std::string& path, double scale, int S);
-    void flush_outputs(double scale, int S);
+    // a stored value is h / scale * mul: (sqrt(N), 1) in the linear model, (1, 1/sqrt(N)) in the probit model - the reference's own arithmetic
+    void emit_output(int which, gvb_vec v, size_t n, const std::string& path, double scale, int S, double mul = 1.0);
+    void finish_output(int which, const double* h, size_t n, const std::string& path, double scale, int S, double mul);
+    void flush_outputs(double scale, int S, double mul = 1.0);
     std::future<void> writer;   // the previous iteration's outputs, scaled and written while this iteration's kernels run
     void wait_writes();
     void dev_open(data* dataset);
@@ -187,6 +188,7 @@ public:
                                  std::vector<double> eta);
     double mlogL_probit(std::vector<double> y, std::vector<double> gg, double probit_var, std::vector<std::vector<double>> Z,
                         std::vector<double> eta);
+    std::vector<double> newton_cov(const std::vector<double>& y, const std::vector<double>& gg, const std::vector<std::vector<double>>& Z, std::vector<double> eta);
     std::vector<double> Newton_method_cov(std::vector<double> y, std::vector<double> gg, std::vector<std::vector<double>> Z,
                                           std::vector<double> eta);
 

@@ -448,6 +448,11 @@ atx_tile_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
 //  steps, so a warp may run up to three steps ahead of the slowest one.  Shared memory: 128 KB of tables + NW x NS x 4 KB of bed tiles.
 // ===================================================================================================
 constexpr int PAIR_REGION = 65536;   // [256 entries][2 steps][32 slots] int32
+#ifdef GVB_EXP_TAB_COPY_BYTES            // timing experiment only (wrong results): what a smaller L2 -> shared-memory table stream would buy
+constexpr int PAIR_COPY_BYTES = GVB_EXP_TAB_COPY_BYTES;
+#else
+constexpr int PAIR_COPY_BYTES = PAIR_REGION;
+#endif
 
 // Shared memory of a pair-mode CTA, all of it dynamic so that 128 KB of tables + 24 bed tiles (12 consumer warps x 2) fit the 227 KB:
 //   [2 table regions at the start of the segment: a link-time constant base, so the lookups are LDS [R + UR]]
@@ -513,8 +518,8 @@ __device__ __forceinline__ void pair_produce_item(PairPipe& pp, uint32_t tab_sm,
         uint32_t& f = r ? pp.fills1 : pp.fills0;
         if (lane == 0) {
             mbar_wait(pp.empty + 8 * r, (f & 1) ^ 1);   // a fresh barrier passes the wait for the phase "before the first"
-            mbar_expect_tx(pp.full + 8 * r, PAIR_REGION);
-            bulk_g2s_plain(tab_sm + r * PAIR_REGION, src + (long)p * (PAIR_REGION / 4), PAIR_REGION, pp.full + 8 * r);
+            mbar_expect_tx(pp.full + 8 * r, PAIR_COPY_BYTES);
+            bulk_g2s_plain(tab_sm + r * PAIR_REGION, src + (long)p * (PAIR_REGION / 4), PAIR_COPY_BYTES, pp.full + 8 * r);
         }
         f++;
     }

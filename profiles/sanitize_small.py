@@ -48,5 +48,9 @@ for twin, stripes in (("0", None), ("1", None), (None, "30")):
                 assert np.all(np.isfinite(r))
                 x1 = ctx.vecM()
                 ctx.denoise(rhs, 3.0, [0.9, 0.06, 0.04], [0.0, 0.1, 1.0], x1)
+                stage = ctx.vecM()
+                assert rhs.upload_changed(v, stage) is False and rhs.upload_changed(-v, stage) is True
+                ctx.snapshot_begin(rhs, M, 9)
+                assert np.array_equal(ctx.snapshot_wait(9), -v)
         print(f"ok twin={twin} stripes={stripes} miss={miss}/{form}", flush=True)
 print("sanitize_small: all checks passed")

@@ -43,6 +43,9 @@ SIGNATURES = {
     "gvb_vec_reduce_batch": (ci, [vp, ci, vp, c_f64p]),
     "gvb_profile_enable": (ci, [vp, ci]),
     "gvb_profile_read": (ci, [vp, c_f64p]),
+    "gvb_profile_read_dual": (ci, [vp, c_f64p]),
+    "gvb_dual_sweep_count": (cl, [vp]),
+    "gvb_dAx2": (ci, [vp, vp, vp, vp, vp]),
     "gvb_divide_work": (None, [cl, ci, ci, ctypes.POINTER(cl), ctypes.POINTER(cl)]),
     "gvb_bed_load_file": (ci, [vp, ctypes.c_char_p, cl, cl, cl, cl]),
     "gvb_bed_load_host": (ci, [vp, c_u8p, cl, cl, cl, cl]),
@@ -364,6 +367,10 @@ class Context:
     def dATx(self, u, out):
         _chk(self.L.gvb_dATx(self.h, u.h, out.h), self.L)
 
+    def dAx2(self, v0, v1, out0, out1):
+        """out0 = X.v0, out1 = X.v1 from one pass over the bed (gvb_dAx2)"""
+        _chk(self.L.gvb_dAx2(self.h, v0.h, v1.h, out0.h, out1.h), self.L)
+
     def denoise(self, r1, gam1, probs, vars_, x1_hat):
         p, pp = _f64(probs)
         v, pv = _f64(vars_)
@@ -454,6 +461,14 @@ class Context:
         out = np.zeros(4)
         _chk(self.L.gvb_profile_read(self.h, out.ctypes.data_as(c_f64p)), self.L)
         return dict(ax_ms=out[0], ax_n=int(out[1]), atx_ms=out[2], atx_n=int(out[3]))
+
+    def profile_read_dual(self):
+        out = np.zeros(2)
+        _chk(self.L.gvb_profile_read_dual(self.h, out.ctypes.data_as(c_f64p)), self.L)
+        return dict(dual_ms=out[0], dual_n=int(out[1]))
+
+    def dual_sweeps(self) -> int:
+        return self.L.gvb_dual_sweep_count(self.h)
 
     def launches(self) -> int:
         return self.L.gvb_launch_count(self.h)

@@ -99,6 +99,10 @@ struct gvb_ctx {
     size_t tab_v_cap = 0;
     int* shift_u = nullptr;         // per stripe: left shift of its table's int32 windows (scale classes, matvec_tile.cu)
     int* shift_v = nullptr;         // per marker tile, likewise
+    int32_t* tab_v2 = nullptr;      // dual X.v (two right-hand sides per bed read): interleaved tables, the second product's shifts / accumulators
+    size_t tab_v2_cap = 0;
+    int* shift_v2 = nullptr;
+    unsigned long long* acc_dual = nullptr;
     size_t shift_cap = 0;
     unsigned long long* acc_i64 = nullptr;  // fixed-point accumulators
     size_t acc_i64_cap = 0;
@@ -125,11 +129,11 @@ struct gvb_ctx {
 
     // timers and counters
     cudaEvent_t ev_start[8], ev_stop[8];
-    long launches = 0, sweeps = 0;
+    long launches = 0, sweeps = 0, dual_sweeps = 0;   // a dual sweep (two products, one bed read) counts once in `sweeps`
     long host_syncs = 0;            // stream synchronisations that return a reduction to the host (bench.py reports them per iteration)
     bool profile = false;
-    std::vector<cudaEvent_t> prof_ev[2];   // [0] X.v, [1] X^T.u : start/stop pairs
-    size_t prof_used[2] = {0, 0};
+    std::vector<cudaEvent_t> prof_ev[3];   // [0] X.v, [1] X^T.u, [2] dual X.v : start/stop pairs
+    size_t prof_used[3] = {0, 0, 0};
     std::vector<gvb_vec_s*> vecs;
     gvb_vec_s* cg_ws[3] = {nullptr, nullptr, nullptr};   // r, p, d of the CG solver (allocated once: no cudaMalloc in the loop)
     // device-resident scalars of the CG solver (cg.cu): the iteration never returns to the host for alpha / beta / the exit tests
@@ -220,6 +224,7 @@ int gvb_atx_simple(gvb_ctx* c, const double* u, double* out);
 int gvb_ax_lut(gvb_ctx* c, const double* v, double* out);
 int gvb_atx_lut(gvb_ctx* c, const double* u, double* out);
 int gvb_ax_tile(gvb_ctx* c, const double* v, double* out, int mode = 0);     // gen-2 sweeps (matvec_tile.cu); mode: ax_code_values
+int gvb_ax_tile_dual(gvb_ctx* c, const double* v0, const double* v1, double* out0, double* out1);   // two products, one bed read
 int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB = nullptr);   // outB[j] = sum_i b_ij u_i (optional)
 int gvb_count_tile_main(gvb_ctx* c, const int* tab, unsigned long long* acc);
 void gvb_twin_reset(gvb_ctx* c);                                       // twin.cu

@@ -760,6 +760,147 @@ atx_pair_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab, l
 }
 #undef PAIR_STEP
 
+// ===================================================================================================
+//  Two right-hand sides per bed read ("dual" X.v): out0 = X.v0 and out1 = X.v1 from ONE pass over the shard.  The tables of the two
+//  products are interleaved entry by entry, [step][256 entries][32 slots][2 rhs] int32, so that one LDS.64 returns both summands of a
+//  lookup and the index arithmetic (the gather of the 2-bit codes, the PRMT) is shared.  A 64 KB region now holds ONE step; the two
+//  regions double-buffer single steps.  Every int32 window, shift and int64 sum is the one the single-product kernel forms for that
+//  right-hand side: the results are bit-identical to two gvb_ax_tile calls (test_dual_ax_equals_two_sweeps).
+// ===================================================================================================
+__device__ __forceinline__ void make_spack_dual(unsigned (&sp)[11], int lane) {
+#pragma unroll
+    for (int j = 0; j < 11; j++) {
+        unsigned x = 0;
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+            if (3 * j + b < 32) x |= ((unsigned)((((3 * j + b) ^ lane) & 31) * 8)) << (8 * b);
+        sp[j] = x;
+    }
+}
+
+template <bool TW>
+__device__ __forceinline__ void ax_consume_dual(const char* __restrict__ tabc, uint32_t bb, const unsigned (&sp)[11], int (&a0)[4], int (&a1)[4]) {
+#pragma unroll
+    for (int tau = 0; tau < 32; tau++) {
+        const uint32_t w = lds32(bb ^ (uint32_t)(tau << 7));   // row tau ^ lane, column lane
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned prod = TW ? w : (w & (0x03030303u << (2 * k))) * (0x01041040u >> (2 * k));
+            const unsigned a = prmt(prod, sp[tau / 3], (TW ? (0xF700u | (k << 4)) : 0xF730u) | (4 + (tau % 3)));
+            const int2 val = *reinterpret_cast<const int2*>(tabc + a);
+            a0[k] += val.x;
+            a1[k] += val.y;
+        }
+    }
+}
+
+template <int NW, int NS, bool TW>
+__global__ void __launch_bounds__(NW * 32 + 32, 1)
+ax_dual_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv2, long Mg_pad, long stripe0, long n_stripes, int n_sblocks, int n_gchunks,
+               int tiles_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out0, unsigned long long* __restrict__ acc_out1,
+               const int* __restrict__ skip, const int* __restrict__ shifts0, const int* __restrict__ shifts1) {
+    if (skip && *skip) return;
+    extern __shared__ __align__(1024) char smem[];
+    const PairLayout lay = pair_layout<NW, NS>(smem);
+    volatile int* s_item_p = reinterpret_cast<volatile int*>(smem + lay.ctrl_off);
+    const char* tabs = smem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool producer = warp == NW;
+    const uint32_t tab_sm = lay.tab;
+    const uint32_t bed_sm = lay.bed + (producer ? 0 : warp) * (NS * TILE_BYTES);
+    const uint32_t bar0 = lay.ctrl + 64 + 8 * ((producer ? 0 : warp) * NS);
+    if (lane == 0 && !producer) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    PairPipe pp;
+    pair_pipe_init(pp, lay.ctrl + 8, NW);
+    const uint64_t pol = policy_evict_first();
+    unsigned sp[11];
+    const uint32_t lane_off = lane * 132;
+    uint32_t n_fill = 0, n_use = 0;
+    const int n_items = n_sblocks * n_gchunks;
+    const long n_tiles = Mg_pad / 32;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) *s_item_p = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int item = *s_item_p;
+        if (item >= n_items) break;
+        const int gc = item / n_sblocks, sb = item % n_sblocks;
+        const long step_lo = (long)gc * tiles_per_chunk;
+        const int nt = (int)min((long)tiles_per_chunk, n_tiles - step_lo);
+        if (producer) {   // one 64 KB region per step, regions alternating from 0
+            const int* src = tabv2 + step_lo * (PAIR_REGION / 4);
+            for (int i = 0; i < nt; i++) {
+                const int r = i & 1;
+                uint32_t& f = r ? pp.fills1 : pp.fills0;
+                if (lane == 0) {
+                    mbar_wait(pp.empty + 8 * r, (f & 1) ^ 1);
+                    mbar_expect_tx(pp.full + 8 * r, PAIR_REGION);
+                    bulk_g2s_plain(tab_sm + r * PAIR_REGION, src + (long)i * (PAIR_REGION / 4), PAIR_REGION, pp.full + 8 * r);
+                }
+                f++;
+            }
+            continue;
+        }
+        const long t = stripe0 + (long)sb * NW + warp;
+        const bool active = (long)sb * NW + warp < n_stripes;
+        const uint32_t* bsrc = bed + ((active ? t : stripe0) * Mg_pad + step_lo * 32) * 32;
+        auto issue_bed = [&](int i) {
+            if (active && i < nt) {
+                if (lane == 0) {
+                    const uint32_t s = n_fill % NS;
+                    mbar_expect_tx(bar0 + 8 * s, TILE_BYTES);
+                    bulk_g2s(bed_sm + s * TILE_BYTES, bsrc + (long)i * TILE_WORDS, TILE_BYTES, bar0 + 8 * s, pol);
+                }
+                n_fill++;
+            }
+        };
+#pragma unroll
+        for (int s = 0; s < NS - 1; s++) issue_bed(s);
+        long long acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+        make_spack_dual(sp, lane);   // region 0
+#pragma unroll 1
+        for (int i = 0; i < nt; i++) {
+            const int rgn = i & 1;
+            issue_bed(i + NS - 1);
+            {
+                const uint32_t f = rgn ? pp.fills1 : pp.fills0;
+                mbar_wait(pp.full + 8 * rgn, f & 1);
+                if (rgn) pp.fills1++; else pp.fills0++;
+            }
+            const int sh0 = __ldg(shifts0 + step_lo + i), sh1 = __ldg(shifts1 + step_lo + i);
+            if (active) {
+                const uint32_t s = n_use % NS;
+                mbar_wait(bar0 + 8 * s, (n_use / NS) & 1);
+                n_use++;
+                int a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+                ax_consume_dual<TW>(tabs, bed_sm + s * TILE_BYTES + lane_off, sp, a0, a1);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    acc0[k] += (long long)a0[k] << sh0;
+                    acc1[k] += (long long)a1[k] << sh1;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 11; j++) sp[j] ^= 0x01000000u;   // the other region
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pp.empty + 8 * rgn);
+        }
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (acc0[k] != 0) atomicAdd(acc_out0 + (t * 32 + lane) * 4 + k, (unsigned long long)acc0[k]);
+                if (acc1[k] != 0) atomicAdd(acc_out1 + (t * 32 + lane) * 4 + k, (unsigned long long)acc1[k]);
+            }
+        }
+    }
+    release_work_counter(work_counter);
+}
+
 // measured defaults (profiles/r02_sweep_tuning.txt)
 #define GVB_DEFAULT_TMA_WALK 1
 #define GVB_DEFAULT_TMA_GATHER 0
@@ -836,6 +977,27 @@ int launch_ax_pair(gvb_ctx* c, unsigned long long* accN, long stripe0, long n_st
     int grid = std::min(n_sblocks * n_gchunks, c->sm_count);
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(TW ? c->bed_twin : c->bed, c->tab_v, c->Mg_pad, stripe0, n_stripes, n_sblocks, n_gchunks, tpc, c->work_counter,
                                                        accN, 1, c->skip, c->shift_v);
+    GVB_LAUNCHED(c);
+    return GVB_OK;
+}
+
+template <int NW, int NS, bool TW>
+int launch_ax_dual(gvb_ctx* c, unsigned long long* acc0, unsigned long long* acc1, long stripe0, long n_stripes) {
+    using Cfg = PairCfg<NW, NS>;
+    auto kern = ax_dual_kernel<NW, NS, TW>;
+    static unsigned long long attr_done = 0;
+    if (!(attr_done >> (c->device & 63) & 1ull)) {
+        GVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        attr_done |= 1ull << (c->device & 63);
+    }
+    if (n_stripes <= 0) return GVB_OK;
+    const long n_tiles = c->Mg_pad / 32;
+    int n_sblocks = (int)((n_stripes + NW - 1) / NW);
+    const int tpc = pick_chunk(tune().ax_tiles_per_chunk, n_sblocks, n_tiles, c->sm_count);
+    int n_gchunks = (int)((n_tiles + tpc - 1) / tpc);
+    int grid = std::min(n_sblocks * n_gchunks, c->sm_count);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(TW ? c->bed_twin : c->bed, c->tab_v2, c->Mg_pad, stripe0, n_stripes, n_sblocks, n_gchunks, tpc, c->work_counter,
+                                                       acc0, acc1, c->skip, c->shift_v, c->shift_v2);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }
@@ -970,7 +1132,7 @@ __global__ void __launch_bounds__(128) ax_prep_kernel(const double* __restrict__
 // Q_j(c) = rint(val_j(c) * scale), val_j(00) = (2-mu) w, val_j(10) = (1-mu) w, val_j(11) = -mu w, val_j(missing) = 0
 __global__ void __launch_bounds__(256) ax_build_kernel(const double* __restrict__ v, const double* __restrict__ mave, const double* __restrict__ msig,
                                                        double* __restrict__ scal, int* __restrict__ tabv, int mode, const int* __restrict__ skip,
-                                                       int* __restrict__ shifts, int pairs) {
+                                                       int* __restrict__ shifts, int pairs, int dual_rhs) {
     if (skip && *skip) return;
     __shared__ int Qs[4][4][32];   // [q][code][slot]: a warp reads one (q, code) row -> conflict free
     __shared__ double s_scale;
@@ -1013,7 +1175,8 @@ __global__ void __launch_bounds__(256) ax_build_kernel(const double* __restrict_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll 4
     for (int e = warp; e < 256; e += 8)
-        tabv[gvb_tab_index(T, e, lane, pairs)] = Qs[0][e & 3][lane] + Qs[1][(e >> 2) & 3][lane] + Qs[2][(e >> 4) & 3][lane] + Qs[3][e >> 6][lane];
+        tabv[dual_rhs < 0 ? gvb_tab_index(T, e, lane, pairs) : (size_t)(T * 256 + e) * 64 + lane * 2 + dual_rhs] =
+            Qs[0][e & 3][lane] + Qs[1][(e >> 2) & 3][lane] + Qs[2][(e >> 4) & 3][lane] + Qs[3][e >> 6][lane];
 }
 
 // out[i] = present_i ? acc_i / scale / sqrt(N) : 0   (the mask m_i of data.cpp:972; pads are never present)
@@ -1231,11 +1394,53 @@ int gvb_ax_tile(gvb_ctx* c, const double* v, double* out, int mode) {
     unsigned long long* accN = c->acc_i64 + 2 * (size_t)c->Mg_pad * 4;
     ax_prep_kernel<<<(unsigned)n_tiles, 128, 0, c->stream>>>(v, c->mave, c->msig, c->scal, accN, c->Npad, mode, c->skip);
     GVB_LAUNCHED(c);
-    ax_build_kernel<<<(unsigned)n_tiles, 256, 0, c->stream>>>(v, c->mave, c->msig, c->scal, c->tab_v, mode, c->skip, c->shift_v, c->tab_pairs);
+    ax_build_kernel<<<(unsigned)n_tiles, 256, 0, c->stream>>>(v, c->mave, c->msig, c->scal, c->tab_v, mode, c->skip, c->shift_v, c->tab_pairs, -1);
     GVB_LAUNCHED(c);
     GVB_CHECK(ax_main(c, accN));
     ax_finish_kernel<<<(unsigned)((c->Npad + 255) / 256), 256, 0, c->stream>>>(accN, c->scal, c->maskw, c->Npad,
                                                                                mode == 0 ? 1.0 / sqrt((double)c->N) : 1.0, out, c->skip);
+    GVB_LAUNCHED(c);
+    return GVB_OK;
+}
+
+// out0 = X.v0 and out1 = X.v1 of the local shard from one pass over the bed (ax_dual_kernel); bit-identical to two gvb_ax_tile calls.
+// The second product keeps its scales in scal[32..], its shifts in shift_v2 and its accumulators in acc_dual.
+int gvb_ax_tile_dual(gvb_ctx* c, const double* v0, const double* v1, double* out0, double* out1) {
+    GVB_CHECK(ensure_scratch(c, false, true, false));
+    const long n_tiles = c->Mg_pad / 32;
+    const size_t tab2_ints = (size_t)n_tiles * 16384;
+    if (c->tab_v2_cap < tab2_ints) {
+        if (c->tab_v2) cudaFree(c->tab_v2);
+        if (c->shift_v2) cudaFree(c->shift_v2);
+        if (c->acc_dual) cudaFree(c->acc_dual);
+        c->tab_v2 = nullptr; c->shift_v2 = nullptr; c->acc_dual = nullptr;
+        c->tab_v2_cap = 0;
+        GVB_CUDA(gvb_malloc(c, &c->tab_v2, tab2_ints * sizeof(int)));
+        GVB_CUDA(gvb_malloc(c, &c->shift_v2, (size_t)n_tiles * sizeof(int)));
+        GVB_CUDA(gvb_malloc(c, &c->acc_dual, (size_t)c->Npad * sizeof(unsigned long long)));
+        c->tab_v2_cap = tab2_ints;
+    }
+    unsigned long long* accN0 = c->acc_i64 + 2 * (size_t)c->Mg_pad * 4;
+    unsigned long long* accN1 = c->acc_dual;
+    double* scal1 = c->scal + 32;
+    ax_prep_kernel<<<(unsigned)n_tiles, 128, 0, c->stream>>>(v0, c->mave, c->msig, c->scal, accN0, c->Npad, 0, c->skip);
+    GVB_LAUNCHED(c);
+    ax_prep_kernel<<<(unsigned)n_tiles, 128, 0, c->stream>>>(v1, c->mave, c->msig, scal1, accN1, c->Npad, 0, c->skip);
+    GVB_LAUNCHED(c);
+    ax_build_kernel<<<(unsigned)n_tiles, 256, 0, c->stream>>>(v0, c->mave, c->msig, c->scal, c->tab_v2, 0, c->skip, c->shift_v, c->tab_pairs, 0);
+    GVB_LAUNCHED(c);
+    ax_build_kernel<<<(unsigned)n_tiles, 256, 0, c->stream>>>(v1, c->mave, c->msig, scal1, c->tab_v2, 0, c->skip, c->shift_v2, c->tab_pairs, 1);
+    GVB_LAUNCHED(c);
+    const char* tw = getenv("GVB_TWIN");
+    const bool want_twin = !(tw && !strcmp(tw, "0"));
+    if (want_twin && c->twin_state == 0) GVB_CHECK(gvb_twin_build(c));
+    const long T = (want_twin && c->twin_state > 0) ? c->twin_stripes : 0;
+    GVB_CHECK((launch_ax_dual<12, 2, true>(c, accN0, accN1, 0, T)));
+    GVB_CHECK((launch_ax_dual<12, 2, false>(c, accN0, accN1, T, c->n_stripes - T)));
+    const double isn = 1.0 / sqrt((double)c->N);
+    ax_finish_kernel<<<(unsigned)((c->Npad + 255) / 256), 256, 0, c->stream>>>(accN0, c->scal, c->maskw, c->Npad, isn, out0, c->skip);
+    GVB_LAUNCHED(c);
+    ax_finish_kernel<<<(unsigned)((c->Npad + 255) / 256), 256, 0, c->stream>>>(accN1, scal1, c->maskw, c->Npad, isn, out1, c->skip);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }

@@ -79,6 +79,9 @@ long gvb_layout_generation(gvb_ctx* ctx);
  * X^T.u total ms, X^T.u sweeps} since the last read and resets the counters. */
 int gvb_profile_enable(gvb_ctx* ctx, int on);
 int gvb_profile_read(gvb_ctx* ctx, double* out4);
+/* the same for the dual sweeps (gvb_dAx2): out[0..1] = {total ms, sweeps} since the last read */
+int gvb_profile_read_dual(gvb_ctx* ctx, double* out2);
+long gvb_dual_sweep_count(gvb_ctx* ctx); /* dual sweeps so far; each also counts once in gvb_sweep_count */
 
 /* ---- partition ------------------------------------------------------------------------------ */
 /* divide_work, utilities.cpp:259-291: first Mt%nranks ranks own Mt/nranks+1 contiguous markers */
@@ -199,6 +202,10 @@ int gvb_vec_dist2(gvb_ctx* ctx, gvb_vec x, gvb_vec y, int sync, double* res);
 /* device-resident matvecs used by the fused loop (same math as gvb_Ax / gvb_ATx, full range) */
 int gvb_dAx(gvb_ctx* ctx, gvb_vec v, gvb_vec out);
 int gvb_dATx(gvb_ctx* ctx, gvb_vec u, gvb_vec out);
+/* Two products from ONE pass over the bed: out0 = X.v0, out1 = X.v1 (both all-reduced like gvb_dAx).  Where the reference calls
+ * data::Ax twice on independent vectors (z1 = A x1_hat, vamp.cpp:430, and the first operator application of the LMMSE solve,
+ * vamp.cpp:1146) the bed is read once.  Bit-identical to two gvb_dAx calls. */
+int gvb_dAx2(gvb_ctx* ctx, gvb_vec v0, gvb_vec v1, gvb_vec out0, gvb_vec out1);
 
 /* ---- denoiser and EM prior update ---------------------------------------------------------------- */
 /* x1_hat = g1(r1), sums[0] = sum_i g1d(r1_i) over ALL ranks, sums[1] = ||x1_hat - r1||^2 over all

@@ -246,6 +246,49 @@ def test_twin_layout_is_bit_identical(C, oracle, N, M, miss, monkeypatch):
     assert relerr(res["1"][0], ds.Ax(v)) < TOL_MATVEC
 
 
+@pytest.mark.parametrize("N,M,miss", [(70_001, 301, 0.02), (4099, 1030, 0.0), (2500, 333, 0.05), (1200, 9000, 0.0)])
+def test_dual_ax_equals_two_sweeps(C, oracle, N, M, miss, monkeypatch):
+    """gvb_dAx2: two products from one pass over the bed (tables interleaved [entry][slot][rhs], one LDS.64 per lookup).  Every int32
+    window, shift and int64 sum is the one the single-product kernel forms, so both outputs must equal two gvb_dAx calls BIT FOR BIT -
+    on the twin, on the one matrix (gathered indices), on a partial twin, with vectors of very different magnitude (separate scale
+    classes per right-hand side), a zero vector and a non-finite entry (NaN stays with its own product)."""
+    bed = oracle.synth_bed(41, 0, M, N, miss_rate=miss)
+    present = np.ones(N, bool)
+    present[np.random.default_rng(6).choice(N, N // 40, replace=False)] = False
+    mask4 = oracle.make_mask4(N, present)
+    rng = np.random.default_rng(8)
+    v0 = rng.normal(size=M)
+    v1 = rng.normal(size=M) * np.where(rng.random(M) < 0.01, 1e6, 1e-3)     # outliers: other scale classes than v0
+    n_stripes = ((N + 3) // 4 + 31) // 32
+    for mode in ("0", "1", "partial"):
+        if mode == "partial":
+            monkeypatch.delenv("GVB_TWIN")
+            monkeypatch.setenv("GVB_TWIN_STRIPES", str(max(1, n_stripes // 3)))
+        else:
+            monkeypatch.setenv("GVB_TWIN", mode)
+        with C.Context(0) as ctx:
+            ctx.load_host(bed, N).set_mask(mask4, int(present.sum())).compute_stats(1.0)
+            a, b, oa, ob, pa, pb = ctx.vecM(v0), ctx.vecM(v1), ctx.vecN(), ctx.vecN(), ctx.vecN(), ctx.vecN()
+            for x, y in ((v0, v1), (v1, v0), (v0, np.zeros(M)), (v0, v0)):
+                a.upload(x), b.upload(y)
+                ctx.dAx(a, oa), ctx.dAx(b, ob)
+                s0, d0 = ctx.sweeps(), ctx.dual_sweeps()
+                ctx.dAx2(a, b, pa, pb)
+                assert ctx.sweeps() == s0 + 1 and ctx.dual_sweeps() == d0 + 1
+                assert np.array_equal(oa.download(), pa.download()) and np.array_equal(ob.download(), pb.download())
+            bad = v1.copy()
+            bad[M // 2] = np.nan
+            a.upload(v0), b.upload(bad)
+            ctx.dAx(a, oa)
+            ctx.dAx2(a, b, pa, pb)
+            assert np.array_equal(oa.download(), pa.download())
+            assert np.all(np.isnan(pb.download()[:N][present]))
+            ctx.dAx2(a, b, pa, pb)                                         # and the flags re-arm
+            assert np.array_equal(oa.download(), pa.download())
+            assert ctx.twin_state() == {"0": 0, "1": 1, "partial": 2}[mode]
+    monkeypatch.delenv("GVB_TWIN_STRIPES")
+
+
 def test_nonfinite_inputs_turn_the_outputs_into_nan(C, oracle):
     """A NaN / infinity in the input vector: the reference's FP64 LUT products (0 * NaN, data.cpp:766 / :975) turn EVERY
     output into NaN.  The fixed-point sweeps cannot carry a NaN through their integer sums, so they flag it (bound kernel ->

@@ -82,6 +82,8 @@ SIGNATURES = {
     "gvb_cg_solve": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p]),
     "gvb_cg_solve_ex": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, c_f64p]),
     "gvb_cg_solve_warm": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, vp, ci, c_f64p]),
+    "gvb_cg_prepare": (ci, [vp, vp, vp, cd, cd, ci, vp, vp, ci, vp, vp]),
+    "gvb_cg_solve_prepared": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, vp, ci, c_f64p]),
     "gvb_cg_solve_cached": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, ctypes.POINTER(ci), c_f64p]),
     "gvb_people_stats": (ci, [vp, vp, vp, vp]),
     "gvb_cg_solve_aat": (ci, [vp, vp, vp, cd, cd, vp, vp, vp, ci, ctypes.POINTER(ci), c_f64p]),
@@ -409,6 +411,20 @@ class Context:
         dots3 = np.zeros(3)
         _chk(self.L.gvb_cg_solve_warm(self.h, rhs.h, mu.h, tau, gam2, max_iter, denoiser, ctypes.byref(it), log.ctypes.data_as(c_f64p),
                                       ax_mu.h, ata_mu.h, int(have_start), dots3.ctypes.data_as(c_f64p)))
+        return it.value, log.reshape(max_iter, 4)[: it.value], dots3
+
+    def cg_prepare(self, rhs, mu, tau, gam2, max_iter, ax_mu, ata_mu, have_start, extra_v, extra_out):
+        """start of a solve + one dual sweep {A p0, extra_out = A extra_v} (gvb_cg_prepare)"""
+        _chk(self.L.gvb_cg_prepare(self.h, rhs.h, mu.h, tau, gam2, max_iter, ax_mu.h if ax_mu is not None else None,
+                                   ata_mu.h if ata_mu is not None else None, int(have_start), extra_v.h, extra_out.h), self.L)
+
+    def cg_solve_prepared(self, rhs, mu, tau, gam2, max_iter, denoiser, ax_mu, ata_mu, have_start):
+        it = ci(0)
+        log = np.zeros(4 * max_iter)
+        dots3 = np.zeros(3)
+        _chk(self.L.gvb_cg_solve_prepared(self.h, rhs.h, mu.h, tau, gam2, max_iter, denoiser, ctypes.byref(it), log.ctypes.data_as(c_f64p),
+                                          ax_mu.h if ax_mu is not None else None, ata_mu.h if ata_mu is not None else None, int(have_start),
+                                          dots3.ctypes.data_as(c_f64p)), self.L)
         return it.value, log.reshape(max_iter, 4)[: it.value], dots3
 
     def cg_solve_cached(self, rhs, mu, tau, gam2, max_iter, denoiser, ata_rhs, state):

@@ -163,7 +163,7 @@ extern "C" void gvb_ctx_destroy(gvb_ctx* c) {
     fr(c->tmpN); fr(c->tmpN2); fr(c->tmpM); fr(c->tmpM2); fr(c->wv); fr(c->cv); fr(c->ax_partial);
     gvb_misslist_reset(c);
     gvb_twin_reset(c);
-    fr(c->tab_u); fr(c->tab_v); fr(c->tab_v2); fr(c->shift_v2); fr(c->acc_dual); fr(c->shift_u); fr(c->shift_v); fr(c->acc_i64); fr(c->red_partial); fr(c->red_result); fr(c->scal); fr(c->work_counter);
+    fr(c->tab_u); fr(c->tab_v); fr(c->tab_v2); fr(c->shift_v2); fr(c->acc_dual); fr(c->cg_ap); fr(c->shift_u); fr(c->shift_v); fr(c->acc_i64); fr(c->red_partial); fr(c->red_result); fr(c->scal); fr(c->work_counter);
     if (c->h_red) cudaFreeHost(c->h_red);
     fr(c->cg_dev); fr(c->cg_flags);
     if (c->cg_host) cudaFreeHost(c->cg_host);
@@ -438,30 +438,33 @@ extern "C" int gvb_dAx(gvb_ctx* c, gvb_vec v, gvb_vec out) {
     return gvb_ax_dev(c, v->d, out->d, true);
 }
 // out0 = X.v0, out1 = X.v1 from one pass over the bed; the two N-vectors are all-reduced like gvb_dAx's
-extern "C" int gvb_dAx2(gvb_ctx* c, gvb_vec v0, gvb_vec v1, gvb_vec out0, gvb_vec out1) {
-    GVB_ARG(c && v0 && v1 && out0 && out1 && v0->cap >= c->Mg_pad * 4 && v1->cap >= c->Mg_pad * 4 && out0->cap >= c->Npad && out1->cap >= c->Npad,
-            "Ax2 needs two M-vectors and two N-vectors from gvb_vec_alloc_M/_N");
-    GVB_ARG(out0 != out1, "the two products need two output vectors");
+int gvb_ax2_dev(gvb_ctx* c, const double* v0, const double* v1, double* out0, double* out1) {
     GVB_ARG(c->have_stats, "compute_stats must run before Ax");
 #ifdef GVB_LEGACY_KERNELS
     if (c->kernel_gen < 2) {
-        GVB_CHECK(gvb_ax_dev(c, v0->d, out0->d, true));
-        return gvb_ax_dev(c, v1->d, out1->d, true);
+        GVB_CHECK(gvb_ax_dev(c, v0, out0, true));
+        return gvb_ax_dev(c, v1, out1, true);
     }
 #endif
     prof_mark(c, 2);
-    int rc_mv = gvb_ax_tile_dual(c, v0->d, v1->d, out0->d, out1->d);
+    int rc_mv = gvb_ax_tile_dual(c, v0, v1, out0, out1);
     prof_mark(c, 2);
     GVB_CHECK(rc_mv);
     c->sweeps++;
     c->dual_sweeps++;
     if (c->nranks > 1) {
         GVB_NCCL(ncclGroupStart());
-        GVB_NCCL(ncclAllReduce(out0->d, out0->d, (size_t)(4 * c->mbytes), ncclDouble, ncclSum, c->comm, c->stream));
-        GVB_NCCL(ncclAllReduce(out1->d, out1->d, (size_t)(4 * c->mbytes), ncclDouble, ncclSum, c->comm, c->stream));
+        GVB_NCCL(ncclAllReduce(out0, out0, (size_t)(4 * c->mbytes), ncclDouble, ncclSum, c->comm, c->stream));
+        GVB_NCCL(ncclAllReduce(out1, out1, (size_t)(4 * c->mbytes), ncclDouble, ncclSum, c->comm, c->stream));
         GVB_NCCL(ncclGroupEnd());
     }
     return GVB_OK;
+}
+extern "C" int gvb_dAx2(gvb_ctx* c, gvb_vec v0, gvb_vec v1, gvb_vec out0, gvb_vec out1) {
+    GVB_ARG(c && v0 && v1 && out0 && out1 && v0->cap >= c->Mg_pad * 4 && v1->cap >= c->Mg_pad * 4 && out0->cap >= c->Npad && out1->cap >= c->Npad,
+            "Ax2 needs two M-vectors and two N-vectors from gvb_vec_alloc_M/_N");
+    GVB_ARG(out0 != out1, "the two products need two output vectors");
+    return gvb_ax2_dev(c, v0->d, v1->d, out0->d, out1->d);
 }
 extern "C" int gvb_dATx(gvb_ctx* c, gvb_vec u, gvb_vec out) {
     GVB_ARG(c && u && out && u->cap >= c->Npad && out->cap >= c->Mg_pad * 4, "ATx needs an N-vector and an M-vector from gvb_vec_alloc_N/_M");

@@ -264,9 +264,19 @@ extern "C" int gvb_lmmse_mult(gvb_ctx* c, gvb_vec v, double tau, double gam2, gv
 // (tau A^T A rhs + gam2 rhs) / diag and needs no sweep once A^T A rhs is known.  *state == 0: iteration 0 sweeps and fills the cache
 // (*state becomes 1); *state == 1: iteration 0 takes it from the cache.  Like the by-products this is an identity of exact arithmetic;
 // in FP64 it differs from the sweeps by their own fixed-point error (linearity of the sweeps holds to ~1e-7).
+//
+// phase (the prepared solve, gvb_cg_prepare / gvb_cg_solve_prepared): 0 = the whole solve; 1 = only its start - initial residual, first
+// search direction p0 - followed by ONE dual sweep that forms A p0 (kept in c->cg_ap) together with extra_out = A extra_v, a product the
+// caller needs anyway (z1 = A x1_hat of the VAMP iteration): one bed read instead of two; 2 = the rest of a solve prepared that way:
+// iteration 0 takes A p0 from c->cg_ap.  Same kernels in the same order on the same data as phase 0: the results are bit-identical.
 static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
-                         gvb_vec ax_mu, double* dots3, gvb_vec ata_mu, int have_start, gvb_vec ata_rhs = nullptr, int* ata_rhs_state = nullptr) {
+                         gvb_vec ax_mu, double* dots3, gvb_vec ata_mu, int have_start, gvb_vec ata_rhs = nullptr, int* ata_rhs_state = nullptr,
+                         int phase = 0, gvb_vec extra_v = nullptr, gvb_vec extra_out = nullptr) {
     GVB_ARG(c && rhs && mu && rhs != mu, "vectors");
+    GVB_ARG(phase == 0 || (have_start != 0 && !ata_rhs), "a prepared solve starts from zero or from a vector with known by-products");
+    GVB_ARG(phase != 1 || (extra_v && extra_out && extra_v->cap >= c->Mg_pad * 4 && extra_out->cap >= c->Npad), "the companion product needs an M- and an N-vector");
+    GVB_ARG(phase != 2 || c->cg_prepared, "gvb_cg_solve_prepared without gvb_cg_prepare");
+    if (phase != 2) c->cg_prepared = false;
     GVB_ARG(max_iter >= 0, "max_iter");
     GVB_ARG(rhs->cap >= c->Mg_pad * 4 && mu->cap >= c->Mg_pad * 4, "M-vectors from gvb_vec_alloc_M");
     GVB_ARG(!ax_mu || ax_mu->cap >= c->Npad, "ax_mu must be an N-vector from gvb_vec_alloc_N");
@@ -296,9 +306,12 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
     // an Onsager solve that does not start from zero stops on the residual only (see cg_scal_update_kernel)
     const int residual_only = (denoiser == 0 && have_start == 1) ? 1 : 0;
 
+    if (phase == 1 && !c->cg_ap) GVB_CUDA(gvb_malloc(c, &c->cg_ap, (size_t)c->Npad * sizeof(double)));
     // ---- initial residual r = rhs - Q mu_start ; p = r/diag
     const double* q = d->d;
-    if (have_start == 1) {
+    if (phase == 2) {
+        // done by gvb_cg_prepare
+    } else if (have_start == 1) {
         cg_d_from_ata_kernel<<<nbm, 256, 0, c->stream>>>(d->d, ata_mu->d, mu->d, gam2, tau, n);
         GVB_LAUNCHED(c);
     } else if (have_start == 2) {
@@ -314,11 +327,19 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
             GVB_LAUNCHED(c);
         }
     }
-    cg_init_kernel<<<nb, 256, 0, c->stream>>>(r->d, p->d, rhs->d, q, mu->d, diag, n, c->red_partial);
-    GVB_LAUNCHED(c);
-    GVB_CHECK(gvb_reduce_device(c, nb, 3, true));
-    cg_scal_init_kernel<<<1, 1, 0, c->stream>>>(S, flags, c->red_result);
-    GVB_LAUNCHED(c);
+    if (phase != 2) {
+        cg_init_kernel<<<nb, 256, 0, c->stream>>>(r->d, p->d, rhs->d, q, mu->d, diag, n, c->red_partial);
+        GVB_LAUNCHED(c);
+        GVB_CHECK(gvb_reduce_device(c, nb, 3, true));
+        cg_scal_init_kernel<<<1, 1, 0, c->stream>>>(S, flags, c->red_result);
+        GVB_LAUNCHED(c);
+    }
+    if (phase == 1) {
+        GVB_CHECK(gvb_ax2_dev(c, p->d, extra_v->d, c->cg_ap, extra_out->d));
+        c->cg_prepared = true;
+        return GVB_OK;
+    }
+    c->cg_prepared = false;
 
     // ---- iterations: enqueue i, then look at the flag of iteration i - lag
     int enqueued = 0;
@@ -327,12 +348,16 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
         SkipGuard guard(c);
         c->skip = flags;
         for (int i = 0; i < max_iter && !stopped; i++) {
+            double* ap = c->tmpN2;
             if (i == 0 && ata_rhs && *ata_rhs_state == 1) {       // p0 = rhs / diag: A^T A p0 from the cache, no sweep
                 cg_d_from_cached_kernel<<<nbm, 256, 0, c->stream>>>(d->d, ata_rhs->d, diag, n);
                 GVB_LAUNCHED(c);
             } else {
-                GVB_CHECK(gvb_ax_dev(c, p->d, c->tmpN2, true));   // d = Q p
-                GVB_CHECK(gvb_atx_dev(c, c->tmpN2, d->d));
+                if (phase == 2 && i == 0)
+                    ap = c->cg_ap;                                     // A p0 came with the dual sweep of gvb_cg_prepare
+                else
+                    GVB_CHECK(gvb_ax_dev(c, p->d, ap, true));      // d = Q p
+                GVB_CHECK(gvb_atx_dev(c, ap, d->d));
                 if (i == 0 && ata_rhs) {
                     cg_cache_from_d_kernel<<<nbm, 256, 0, c->stream>>>(ata_rhs->d, d->d, diag, n);
                     GVB_LAUNCHED(c);
@@ -344,8 +369,8 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
             GVB_CHECK(gvb_reduce_device(c, nb, 1, true));
             cg_scal_alpha_kernel<<<1, 1, 0, c->stream>>>(S, flags, c->red_result);
             GVB_LAUNCHED(c);
-            if (ax_mu) {   // c->tmpN2 still holds A p of this iteration
-                cg_axpy_n_kernel<<<nbn, 256, 0, c->stream>>>(ax_mu->d, c->tmpN2, S, c->Npad, flags);
+            if (ax_mu) {   // ap still holds A p of this iteration
+                cg_axpy_n_kernel<<<nbn, 256, 0, c->stream>>>(ax_mu->d, ap, S, c->Npad, flags);
                 GVB_LAUNCHED(c);
             }
             cg_update_mu_r_kernel<<<nb, 256, 0, c->stream>>>(mu->d, r->d, p->d, d->d, rhs->d, ata_mu ? ata_mu->d : nullptr, S, diag, gam2, tau, n,
@@ -439,4 +464,19 @@ extern "C" int gvb_cg_solve_warm(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau
     int mode = 0;
     GVB_CHECK(start_mode(c, mu, have_start, &mode));
     return cg_solve_impl(c, rhs, mu, tau, gam2, max_iter, denoiser, iters, log4, ax_mu, dots3, ata_mu, mode);
+}
+
+// The LMMSE solve of a VAMP iteration in two calls, so that its first product A p0 shares a bed read with a product the caller needs
+// anyway: gvb_cg_prepare forms the initial residual and p0 (have_start 1 or 2 as in gvb_cg_solve_warm) and runs one dual sweep
+// {A p0, extra_out = A extra_v}; gvb_cg_solve_prepared runs the iterations.  Anything may be enqueued between the two calls except
+// another solve.  Results are bit-identical to gvb_dAx(extra_v) followed by gvb_cg_solve_warm.
+extern "C" int gvb_cg_prepare(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, gvb_vec ax_mu, gvb_vec ata_mu, int have_start,
+                              gvb_vec extra_v, gvb_vec extra_out) {
+    GVB_ARG(have_start == 1 || have_start == 2, "have_start is 1 or 2");
+    return cg_solve_impl(c, rhs, mu, tau, gam2, max_iter, 1, nullptr, nullptr, ax_mu, nullptr, ata_mu, have_start, nullptr, nullptr, 1, extra_v, extra_out);
+}
+extern "C" int gvb_cg_solve_prepared(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
+                                     gvb_vec ax_mu, gvb_vec ata_mu, int have_start, double* dots3) {
+    GVB_ARG(have_start == 1 || have_start == 2, "have_start is 1 or 2");
+    return cg_solve_impl(c, rhs, mu, tau, gam2, max_iter, denoiser, iters, log4, ax_mu, dots3, ata_mu, have_start, nullptr, nullptr, 2);
 }

@@ -135,6 +135,8 @@ struct gvb_ctx {
     std::vector<cudaEvent_t> prof_ev[3];   // [0] X.v, [1] X^T.u, [2] dual X.v : start/stop pairs
     size_t prof_used[3] = {0, 0, 0};
     std::vector<gvb_vec_s*> vecs;
+    double* cg_ap = nullptr;        // A p0 of a prepared solve (gvb_cg_prepare), consumed by iteration 0 of gvb_cg_solve_prepared
+    bool cg_prepared = false;
     gvb_vec_s* cg_ws[3] = {nullptr, nullptr, nullptr};   // r, p, d of the CG solver (allocated once: no cudaMalloc in the loop)
     // device-resident scalars of the CG solver (cg.cu): the iteration never returns to the host for alpha / beta / the exit tests
     double* cg_dev = nullptr;       // [GVB_CG_NSCAL scalars][4 log doubles per iteration]
@@ -224,6 +226,7 @@ int gvb_atx_simple(gvb_ctx* c, const double* u, double* out);
 int gvb_ax_lut(gvb_ctx* c, const double* v, double* out);
 int gvb_atx_lut(gvb_ctx* c, const double* u, double* out);
 int gvb_ax_tile(gvb_ctx* c, const double* v, double* out, int mode = 0);     // gen-2 sweeps (matvec_tile.cu); mode: ax_code_values
+int gvb_ax2_dev(gvb_ctx* c, const double* v0, const double* v1, double* out0, double* out1);   // dual sweep + all-reduce (capi.cu)
 int gvb_ax_tile_dual(gvb_ctx* c, const double* v0, const double* v1, double* out0, double* out1);   // two products, one bed read
 int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB = nullptr);   // outB[j] = sum_i b_ij u_i (optional)
 int gvb_count_tile_main(gvb_ctx* c, const int* tab, unsigned long long* acc);

@@ -77,6 +77,8 @@ vamp::vamp(int N, int M, int Mt, double gam1, double gamw, int max_iter, double 
     onsager_warm = (ow && ow[0] == '1') && !reference_sweeps;   // opt-in: the default is the reference's zero start
     const char* ao = getenv("GVB_ASYNC_OUT");
     async_outputs = !(ao && ao[0] == '0');
+    const char* ds = getenv("GVB_DUAL_SWEEP");
+    dual_sweep = !(ds && ds[0] == '0');
     const char* ol = getenv("GVB_ONSAGER_LANCZOS");
     onsager_lanczos = !(ol && ol[0] == '0') && !reference_sweeps && !onsager_warm;
 }
@@ -110,6 +112,8 @@ vamp::vamp(int M, double gam1, double gamw, std::vector<double> true_signal, int
     onsager_warm = (ow && ow[0] == '1') && !reference_sweeps;   // opt-in: the default is the reference's zero start
     const char* ao = getenv("GVB_ASYNC_OUT");
     async_outputs = !(ao && ao[0] == '0');
+    const char* ds = getenv("GVB_DUAL_SWEEP");
+    dual_sweep = !(ds && ds[0] == '0');
     const char* ol = getenv("GVB_ONSAGER_LANCZOS");
     onsager_lanczos = !(ol && ol[0] == '0') && !reference_sweeps && !onsager_warm;
 }
@@ -416,7 +420,34 @@ bool vamp::linear_iteration(data* dataset, int it) {
 
         nvtxRangePop();
         double start_z1 = wtime();
-        {
+        // The LMMSE solve's inputs depend on nothing that happens between here and the solve, so they are formed now and the solve's first
+        // product A p0 shares ONE bed read with z1 = A x1_hat (gvb_cg_prepare: a dual sweep); the iterations run at the reference's place
+        // (gvb_cg_solve_prepared).  Not when the solve re-seeds its by-products from real sweeps, in the N-space form, or with
+        // GVB_DUAL_SWEEP=0 / GVB_REFERENCE_SWEEPS=1: then z1 is a sweep of its own.
+        gam_before = gam2;
+        gam2 = clampd(eta1 - gam1, gamma_min, gamma_max);
+        const double gam2_print = gam2;
+        DEV(gvb_vec_copy(ctx, dev.r2_prev, dev.r2));
+        DEV(gvb_vec_axpby_div(ctx, dev.r2, eta1, dev.x1, -gam1, dev.r1, gam2));   // r2 = (eta1 x1 - gam1 r1)/gam2
+        if (use_lmmse_damp == 1) {
+            double xi = std::min(2 * rho, 1.0);
+            if (it > 1) gam2 = 1.0 / pow(xi / sqrt(gam2) + (1 - xi) / sqrt(gam_before), 2);
+        }
+        const int warm = (it == 1) ? 2 : ((dev.warm_age >= 0 && dev.warm_age < 8) ? 1 : 0);
+        const bool prepared = dual_sweep && !reference_sweeps && reverse != 1 && CG_max_iter > 0 && warm != 0;
+        if (prepared) {
+            Phase ph("vamp.z1 = X.x1 + first product of the LMMSE solve (dual sweep)");
+            if (!dev.aty_valid) {
+                DEV(gvb_dATx(ctx, dev.y, dev.aty));
+                dev.aty_valid = true;
+            }
+            DEV(gvb_vec_axpby(ctx, dev.rhs, gamw, dev.aty, gam2, dev.r2));   // v = gamw * A^T y + gam2 * r2
+            if (it == 1)
+                DEV(gvb_vec_fill(ctx, dev.x2, 0.0));
+            else
+                DEV(gvb_vec_copy(ctx, dev.x2, dev.mu_last));
+            DEV(gvb_cg_prepare(ctx, dev.rhs, dev.x2, gamw, gam2, CG_max_iter, dev.tmpN2, dev.ata_x2, warm, dev.x1, dev.z1));
+        } else {
             Phase ph("vamp.z1 = X.x1");
             DEV(gvb_dAx(ctx, dev.x1, dev.z1));
         }
@@ -436,17 +467,9 @@ bool vamp::linear_iteration(data* dataset, int it) {
         if (rank == 0) std::cout << "r1 filepath_out is " << filepath_out_r1 << std::endl;
         if (rank == 0) std::cout << "time needed to save beta1 to an external file = " << wtime() - start_saving << " seconds" << std::endl;
 
-        gam_before = gam2;
-        gam2 = clampd(eta1 - gam1, gamma_min, gamma_max);
         if (rank == 0) {
             std::cout << "eta1 = " << eta1 << std::endl;
-            std::cout << "gam2 = " << gam2 << std::endl;
-        }
-        DEV(gvb_vec_copy(ctx, dev.r2_prev, dev.r2));
-        DEV(gvb_vec_axpby_div(ctx, dev.r2, eta1, dev.x1, -gam1, dev.r1, gam2));   // r2 = (eta1 x1 - gam1 r1)/gam2
-        if (use_lmmse_damp == 1) {
-            double xi = std::min(2 * rho, 1.0);
-            if (it > 1) gam2 = 1.0 / pow(xi / sqrt(gam2) + (1 - xi) / sqrt(gam_before), 2);
+            std::cout << "gam2 = " << gam2_print << std::endl;
         }
         // larger damping factors if the Onsager terms allow it (vamp.cpp:501-502)
         double xi = std::min(2 * std::min(alpha1, alpha2), 1.0);
@@ -491,24 +514,33 @@ bool vamp::linear_iteration(data* dataset, int it) {
             last_cg_iters[0] = 0;
         } else {
         // v = gamw * A^T y + gam2 * r2
-        if (!dev.aty_valid) {
-            DEV(gvb_dATx(ctx, dev.y, dev.aty));
-            dev.aty_valid = true;
+        if (!prepared) {
+            if (!dev.aty_valid) {
+                DEV(gvb_dATx(ctx, dev.y, dev.aty));
+                dev.aty_valid = true;
+            }
+            DEV(gvb_vec_axpby(ctx, dev.rhs, gamw, dev.aty, gam2, dev.r2));
+            if (it == 1)
+                DEV(gvb_vec_fill(ctx, dev.x2, 0.0));
+            else
+                DEV(gvb_vec_copy(ctx, dev.x2, dev.mu_last));   // warm start from the previous LMMSE estimate
         }
-        DEV(gvb_vec_axpby(ctx, dev.rhs, gamw, dev.aty, gam2, dev.r2));
-        if (it == 1)
-            DEV(gvb_vec_fill(ctx, dev.x2, 0.0));
-        else
-            DEV(gvb_vec_copy(ctx, dev.x2, dev.mu_last));   // warm start from the previous LMMSE estimate
         // A x2_hat falls out of the CG (sum of alpha_k A p_k): updateNoisePrec and err_measures(2) need no sweep of their own.
         // A^T A x2_hat falls out the same way, and since the next solve starts from this x2_hat, its initial residual needs no
         // sweep either; every 8th solve re-seeds both from real sweeps so that rounding cannot accumulate over a long run.
         if (reference_sweeps) {
             last_cg_iters[0] = dev_cg(dev.rhs, dev.x2, gamw, 1, nullptr, nullptr, nullptr, it == 1 ? 2 : 0);
         } else {
-            // 2: zero start (iteration 1), 1: by-products of the previous solve describe the start vector, 0: re-seed by real sweeps
-            const int warm = (it == 1) ? 2 : ((dev.warm_age >= 0 && dev.warm_age < 8) ? 1 : 0);
-            last_cg_iters[0] = dev_cg(dev.rhs, dev.x2, gamw, 1, dev.tmpN2, nullptr, dev.ata_x2, warm);
+            // warm = 2: zero start (iteration 1), 1: by-products of the previous solve describe the start vector, 0: re-seed by real sweeps
+            if (prepared) {
+                std::vector<double> log(4 * (size_t)CG_max_iter, 0.0);
+                int iters = 0;
+                DEV(gvb_cg_solve_prepared(ctx, dev.rhs, dev.x2, gamw, gam2, CG_max_iter, 1, &iters, log.data(), dev.tmpN2, dev.ata_x2, warm, nullptr));
+                print_cg_log(log, iters, 1);
+                last_cg_iters[0] = iters;
+            } else {
+                last_cg_iters[0] = dev_cg(dev.rhs, dev.x2, gamw, 1, dev.tmpN2, nullptr, dev.ata_x2, warm);
+            }
             dev.warm_age = warm == 1 ? dev.warm_age + 1 : 0;
         }
         DEV(gvb_vec_copy(ctx, dev.mu_last, dev.x2));

@@ -128,6 +128,7 @@ private:
     // them under the next iteration's kernels (two sets of snapshot slots alternate); GVB_ASYNC_OUT=0: synchronous, in place
     enum { SNAP_Z1 = 0, SNAP_X1, SNAP_R1, SNAP_R2, SNAP_X2, SNAP_COUNT };
     bool async_outputs = true;
+    bool dual_sweep = true;   // z1 = A x1_hat shares a bed read with the first product of the LMMSE solve (GVB_DUAL_SWEEP=0: two sweeps)
     int snap_set = 0;
     std::string snap_path[SNAP_COUNT];
     bool snap_open[SNAP_COUNT] = {false, false, false, false, false};

@@ -254,6 +254,15 @@ int gvb_cg_solve_ex(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double ga
  * The solver's scalars (alpha, beta, the exit tests) live on the device: the stream does not drain inside a solve. */
 int gvb_cg_solve_warm(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters,
                       double* rel_res, gvb_vec ax_mu, gvb_vec ata_mu, int have_start, double* dots3);
+/* The same solve in two calls, so that its first product A p0 shares ONE bed read with a product the caller needs anyway (z1 = A x1_hat
+ * of the VAMP iteration, vamp.cpp:430): gvb_cg_prepare forms the initial residual and the first search direction (have_start 1 or 2 as
+ * above) and runs one dual sweep {A p0, extra_out = A extra_v}; gvb_cg_solve_prepared, called with the same vectors and scalars, runs
+ * the iterations.  Anything may be enqueued between the two calls except another solve.  Bit-identical to gvb_dAx(extra_v, extra_out)
+ * followed by gvb_cg_solve_warm. */
+int gvb_cg_prepare(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, gvb_vec ax_mu, gvb_vec ata_mu, int have_start,
+                   gvb_vec extra_v, gvb_vec extra_out);
+int gvb_cg_solve_prepared(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
+                          gvb_vec ax_mu, gvb_vec ata_mu, int have_start, double* dots3);
 
 /* Zero-start solve against a right-hand side that recurs (the Onsager probe: the same Rademacher vector in every VAMP iteration,
  * vamp.cpp:875-882).  mu is cleared.  ata_rhs (M-vector) caches A^T A rhs: with a zero start the first search direction is rhs / diag,

@@ -535,6 +535,42 @@ def test_cg_by_products(C, oracle, denoiser, warm):
     assert abs((d3[0] - gam2 * d3[1] - d3[2]) / tau - explicit) < 1e-6 * abs(explicit)
 
 
+@pytest.mark.parametrize("start", [2, 1])
+def test_prepared_solve_is_bit_identical(C, oracle, start):
+    """gvb_cg_prepare + gvb_cg_solve_prepared: the solve's first product A p0 shares one bed read with a companion product (dual sweep).
+    Solution, iteration count, log, by-products and the companion product are the bits of gvb_dAx + gvb_cg_solve_warm; the pair of
+    calls costs one sweep less; other work may be enqueued between the two calls; a second solve_prepared without prepare is refused."""
+    N, M = 3000, 2600
+    bed = oracle.synth_bed(43, 0, M, N, miss_rate=0.01)
+    rng = np.random.default_rng(10)
+    rhs1, rhs2, x = rng.normal(size=M), rng.normal(size=M), rng.normal(size=M)
+    with C.Context(0) as ctx:
+        ctx.load_host(bed, N).compute_stats(1.0)
+        res = {}
+        for mode in ("plain", "prepared"):
+            r1, r2, mu, ax, ata, xv, z = ctx.vecM(rhs1), ctx.vecM(rhs2), ctx.vecM(), ctx.vecN(), ctx.vecM(), ctx.vecM(x), ctx.vecN()
+            if start == 1:                                     # a first solve leaves a start vector with its by-products
+                ctx.cg_solve_warm(r1, mu, 2.0, 0.7, 30, 1, ax, ata, 2)
+            s0 = ctx.sweeps()
+            if mode == "plain":
+                ctx.dAx(xv, z)
+                its, log, d3 = ctx.cg_solve_warm(r2, mu, 1.5, 0.9, 30, 1, ax, ata, start)
+            else:
+                ctx.cg_prepare(r2, mu, 1.5, 0.9, 30, ax, ata, start, xv, z)
+                tmp = ctx.vecM(rhs1)                            # unrelated work between the two calls
+                ctx.axpby(tmp, 2.0, tmp)
+                assert np.isfinite(ctx.reduce_batch([(C.RED_DOT, tmp, None, 0, 0, 1)])[0])
+                its, log, d3 = ctx.cg_solve_prepared(r2, mu, 1.5, 0.9, 30, 1, ax, ata, start)
+                with pytest.raises(RuntimeError):
+                    ctx.cg_solve_prepared(r2, mu, 1.5, 0.9, 30, 1, ax, ata, start)
+            res[mode] = (its, log.copy(), d3.copy(), mu.download(), ax.download(), ata.download(), z.download(), ctx.sweeps() - s0)
+        a, b = res["plain"], res["prepared"]
+        assert a[0] == b[0] and a[0] > 3
+        for k in range(1, 7):
+            assert np.array_equal(a[k], b[k]), k
+        assert b[7] == a[7] - 1
+
+
 def test_cg_warm_start_products(C, oracle):
     """gvb_cg_solve_warm: a second solve (other rhs, tau, gam2) started from the first solve's solution with its A.mu / A^T A.mu
     by-products forms its initial residual without a sweep, runs the same iterations as gvb_cg_solve from the same start and

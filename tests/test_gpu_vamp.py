@@ -83,6 +83,27 @@ def test_async_outputs_write_the_same_files(oracle, tmp_path):
         assert open(outs["1"] + fn, "rb").read() == open(outs["0"] + fn, "rb").read(), fn
 
 
+def test_dual_sweep_writes_the_same_files(oracle, tmp_path):
+    """z1 = A x1_hat shares a bed read with the first product of the LMMSE solve (gvb_cg_prepare, a dual sweep; the solve's inputs
+    are formed before z1 instead of after it).  Same integer sums, same kernels on the same data: every output file and every
+    value line of the log must be identical to a run with GVB_DUAL_SWEEP=0, which costs one sweep more per iteration."""
+    g = golden("vamp_linear.npz")
+    outs, logs = {}, {}
+    for mode in ("1", "0"):
+        (tmp_path / mode).mkdir()
+        outs[mode], logs[mode], iters = _run_case(oracle, tmp_path / mode, g, "lut", {"GVB_DUAL_SWEEP": mode, "GVB_LOG_SWEEPS": "1"})
+    names = sorted(os.listdir(outs["1"]))
+    assert names == sorted(os.listdir(outs["0"])) and len(names) >= 5 * iters
+    for fn in names:
+        assert open(outs["1"] + fn, "rb").read() == open(outs["0"] + fn, "rb").read(), fn
+    def keep(mode):    # the log without its wall-clock lines and without the run's own directory in the paths it prints
+        lines = [l.replace(str(tmp_path / mode), "") for l in logs[mode].splitlines()]
+        return [l for l in lines if not any(w in l for w in ("seconds", "took", "time", "bed sweeps"))]
+    assert keep("1") == keep("0")
+    sw = {m: [int(l.split("=")[1]) for l in logs[m].splitlines() if l.startswith("bed sweeps this iteration")] for m in ("0", "1")}
+    assert len(sw["1"]) == iters and all(a <= b for a, b in zip(sw["1"], sw["0"])) and sum(sw["0"]) - sum(sw["1"]) >= iters - 2
+
+
 def test_config1_matches_reference(oracle, tmp_path):
     """BASELINE.json configs[0] end to end: N=10,000 x M=20,000, h2=0.5, CV=2,000, linear, 10 iterations, against the output of
     the reference's own main_real.exe (MANVECT build, tests/golden/config1.npz): signal estimate of the first, a middle and the

@@ -485,12 +485,18 @@ def ours_arm(args):
     kname = {"X.v": "ax_pair_kernel<twin>" if twin == 1 else ("ax_pair_kernel<twin>+ax_tile_kernel<gather>" if twin == 2 else "ax_tile_kernel<gather>"),
              "X^T.u": "atx_pair_kernel" + ("+miss_sum_kernel" if miss > 0 else "")}[dom]
     traffic, traffic_src = ncu_traffic(f"{kname}@{bed_bytes_local}")
-    n_sw = prof["ax_n"] + prof["atx_n"]
+    dual_ms, dual_n = prof.get("dual_ms", 0.0), prof.get("dual_n", 0)
+    sweep_ms_all = prof["ax_ms"] + prof["atx_ms"] + dual_ms
+    n_sw = prof["ax_n"] + prof["atx_n"] + dual_n
     roofline = {"bound": "hbm", "kernel": f"{dom}: {kname}", "achieved": gbs[dom], "peak": peak, "unit": "GB/s",
                 "frac": gbs[dom] / peak if gbs[dom] else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bed_bytes_local, "per_kernel_GBps": gbs,
                 "sweep_ms": {k: (ms / n if n else None) for k, (ms, n) in per.items()},
-                "sweep_share_of_step": (prof["ax_ms"] + prof["atx_ms"]) / res["ms_dev"],
+                "sweep_share_of_step": sweep_ms_all / res["ms_dev"],
+                "dual_sweeps": {"n": dual_n, "ms_each": dual_ms / dual_n if dual_n else None,
+                                "bed_GBps": (bed_bytes_local / 1e9) / (dual_ms / dual_n / 1e3) if dual_n else None,
+                                "note": "X.v for two right-hand sides from ONE bed read (z1 = A x1_hat + the first product of the LMMSE solve); "
+                                        "not part of `achieved`, which is the single-product X.v / X^T.u sweeps"},
                 "note": "achieved = packed bed bytes of the local shard / mean CUDA-event time of all launches of one sweep (scale, table build, main kernel, "
                         "finish), measured inside the timed region on this rank"}
     line = {
@@ -501,8 +507,8 @@ def ours_arm(args):
                    "protocol": f"{W} warm-up iterations of a throw-away run, then iterations 1..{K} of a fresh run (device-timed), then the same "
                                f"iterations 1..{K} of another fresh run end to end (host y upload, output read-back, files written)",
                    "iter_per_s_unscaled": K / (ms_dev / 1e3), "config4_scale_factor": work,
-                   "sweeps_per_step": res["sweeps"], "cg_iters_per_step": res["cg"], "ms_per_sweep": (prof["ax_ms"] + prof["atx_ms"]) / max(n_sw, 1),
-                   "non_sweep_ms_per_step": (res["ms_dev"] - prof["ax_ms"] - prof["atx_ms"]) / K, "host_syncs_per_step": res["host_syncs"] / K,
+                   "sweeps_per_step": res["sweeps"], "cg_iters_per_step": res["cg"], "ms_per_sweep": sweep_ms_all / max(n_sw, 1),
+                   "non_sweep_ms_per_step": (res["ms_dev"] - sweep_ms_all) / K, "host_syncs_per_step": res["host_syncs"] / K,
                    "l2_policy": "inputs (>= 12 GB packed bed per sweep at the default workload) larger than the 126 MB L2",
                    "kernels": os.environ.get("GVB_KERNELS", "tile (gen 2)"), "twin_layout": twin, "setup_s": t_setup,
                    "onsager_solve": "by bed sweeps" if (os.environ.get("GVB_ONSAGER_LANCZOS") == "0" or os.environ.get("GVB_REFERENCE_SWEEPS") == "1")
@@ -607,7 +613,7 @@ def run_linear(args, D, ctx, H, N, Mt, S, M, logf):
         out["sweeps"], out["cg"], out["ms_dev"], gamw, wall = fresh_run(K, False, False, 0)
         out["launches"] = ctx.launches() - launches0
         out["host_syncs"] = ctx.host_syncs() - syncs0
-        out["prof"] = ctx.profile_read()
+        out["prof"] = {**ctx.profile_read(), **ctx.profile_read_dual()}
         ctx.profile(False)
         out["clocks"] = sampler.stop() if sampler else None
         # ---- timed region 2: the same iterations end to end

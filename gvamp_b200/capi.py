@@ -82,6 +82,7 @@ SIGNATURES = {
     "gvb_cg_solve": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p]),
     "gvb_cg_solve_ex": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, c_f64p]),
     "gvb_cg_solve_warm": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, vp, ci, c_f64p]),
+    "gvb_cg_set_companion": (ci, [vp, vp, vp]),
     "gvb_cg_prepare": (ci, [vp, vp, vp, cd, cd, ci, vp, vp, ci, vp, vp]),
     "gvb_cg_solve_prepared": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, vp, ci, c_f64p]),
     "gvb_cg_solve_cached": (ci, [vp, vp, vp, cd, cd, ci, ci, ctypes.POINTER(ci), c_f64p, vp, ctypes.POINTER(ci), c_f64p]),

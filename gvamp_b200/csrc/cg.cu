@@ -344,6 +344,12 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
     // ---- iterations: enqueue i, then look at the flag of iteration i - lag
     int enqueued = 0;
     bool stopped = false;
+    gvb_cg_companion_fn companion = (phase != 1) ? c->cg_companion : nullptr;   // serves this solve only
+    void* companion_user = c->cg_companion_user;
+    if (phase != 1) c->cg_companion = nullptr;
+    bool last_had_companion = false;
+    long companion_sweeps = 0;
+    (void)companion_sweeps;
     {
         SkipGuard guard(c);
         c->skip = flags;
@@ -353,11 +359,37 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
                 cg_d_from_cached_kernel<<<nbm, 256, 0, c->stream>>>(d->d, ata_rhs->d, diag, n);
                 GVB_LAUNCHED(c);
             } else {
-                if (phase == 2 && i == 0)
+                gvb_vec cv = nullptr, cav = nullptr;
+                bool with_companion = false;
+                if (phase == 2 && i == 0) {
                     ap = c->cg_ap;                                     // A p0 came with the dual sweep of gvb_cg_prepare
-                else
-                    GVB_CHECK(gvb_ax_dev(c, p->d, ap, true));      // d = Q p
+                } else {
+                    // a companion (gvb_cg_set_companion) may ride on this iteration's A p: one dual sweep {A p, av = A v}.  That sweep is
+                    // not predicated on the solver's exit flag - the companion's product must exist even when this iteration turns out
+                    // to be a speculative one (A p is then simply not used)
+                    if (companion && companion(companion_user, 0, i, &cv, &cav) == 1) {
+                        GVB_ARG(cv && cav && cv->cap >= c->Mg_pad * 4 && cav->cap >= c->Npad, "the companion product needs an M- and an N-vector");
+                        with_companion = true;
+                        c->skip = nullptr;
+                        int rc2 = gvb_ax2_dev(c, p->d, cv->d, ap, cav->d);
+                        c->skip = flags;
+                        GVB_CHECK(rc2);
+                        companion_sweeps++;
+                    } else {
+                        GVB_CHECK(gvb_ax_dev(c, p->d, ap, true));      // d = Q p
+                    }
+                }
+                last_had_companion = with_companion;
                 GVB_CHECK(gvb_atx_dev(c, ap, d->d));
+                if (with_companion) {   // the companion finishes its own step (its sweeps and host-visible sums are not the solver's)
+                    c->skip = nullptr;
+                    int rc2 = companion(companion_user, 1, i, &cv, &cav);
+                    c->skip = flags;
+                    if (rc2 < 0) {
+                        gvb_set_error("the companion of the solve failed in iteration %d", i);
+                        return GVB_ERR_ARG;
+                    }
+                }
                 if (i == 0 && ata_rhs) {
                     cg_cache_from_d_kernel<<<nbm, 256, 0, c->stream>>>(ata_rhs->d, d->d, diag, n);
                     GVB_LAUNCHED(c);
@@ -409,7 +441,7 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
     // iterations enqueued after the solver had stopped ran as empty launches: they are not sweeps and carry no timing
     const int spec = enqueued - it_done;
     if (spec > 0) {
-        c->sweeps -= 2l * spec;
+        c->sweeps -= 2l * spec - ((last_had_companion && spec >= 1) ? 1 : 0);   // a companion's dual sweep ran in full
         for (int w = 0; w < 2; w++)
             if (c->profile && c->prof_used[w] >= (size_t)(2 * spec)) c->prof_used[w] -= (size_t)(2 * spec);
     }
@@ -479,4 +511,16 @@ extern "C" int gvb_cg_solve_prepared(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double
                                      gvb_vec ax_mu, gvb_vec ata_mu, int have_start, double* dots3) {
     GVB_ARG(have_start == 1 || have_start == 2, "have_start is 1 or 2");
     return cg_solve_impl(c, rhs, mu, tau, gam2, max_iter, denoiser, iters, log4, ax_mu, dots3, ata_mu, have_start, nullptr, nullptr, 2);
+}
+
+// A companion for the NEXT solve of this context (consumed by it; NULL clears): before the product A p of an iteration the solver calls
+// fn(user, 0, i, &v, &av); when that returns 1 with an M-vector v and an N-vector av, the iteration's X.v becomes one dual sweep
+// {A p, av = A v}, and after the iteration's X^T.u the solver calls fn(user, 1, i, ...) so that the companion can finish its own step
+// (it may enqueue sweeps and synchronise; a negative return aborts the solve).  vamp::infere_linear lets the Lanczos steps of the
+// Onsager projection ride on the LMMSE solve of iteration 1 this way.
+extern "C" int gvb_cg_set_companion(gvb_ctx* c, gvb_cg_companion_fn fn, void* user) {
+    GVB_ARG(c, "ctx");
+    c->cg_companion = fn;
+    c->cg_companion_user = user;
+    return GVB_OK;
 }

@@ -137,6 +137,8 @@ struct gvb_ctx {
     std::vector<gvb_vec_s*> vecs;
     double* cg_ap = nullptr;        // A p0 of a prepared solve (gvb_cg_prepare), consumed by iteration 0 of gvb_cg_solve_prepared
     bool cg_prepared = false;
+    gvb_cg_companion_fn cg_companion = nullptr;   // gvb_cg_set_companion: consumed by the next solve
+    void* cg_companion_user = nullptr;
     gvb_vec_s* cg_ws[3] = {nullptr, nullptr, nullptr};   // r, p, d of the CG solver (allocated once: no cudaMalloc in the loop)
     // device-resident scalars of the CG solver (cg.cu): the iteration never returns to the host for alpha / beta / the exit tests
     double* cg_dev = nullptr;       // [GVB_CG_NSCAL scalars][4 log doubles per iteration]

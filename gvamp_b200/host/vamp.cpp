@@ -532,6 +532,7 @@ bool vamp::linear_iteration(data* dataset, int it) {
             last_cg_iters[0] = dev_cg(dev.rhs, dev.x2, gamw, 1, nullptr, nullptr, nullptr, it == 1 ? 2 : 0);
         } else {
             // warm = 2: zero start (iteration 1), 1: by-products of the previous solve describe the start vector, 0: re-seed by real sweeps
+            lanczos_ride(dataset);
             if (prepared) {
                 std::vector<double> log(4 * (size_t)CG_max_iter, 0.0);
                 int iters = 0;
@@ -687,8 +688,7 @@ double vamp::g1d(double x, double gam1) {
 // ---------------------------------------------------------------------------------------------------
 // Onsager correction by a Hutchinson probe (vamp.cpp:871-889)
 // ---------------------------------------------------------------------------------------------------
-double vamp::g2d_onsager(double gam2, double tau, data* dataset) {
-    dev_open(dataset);
+void vamp::onsager_probe(data* dataset) {
     // Rademacher probe +-1/sqrt(Mt) from mt19937{seed + S}: identical stream to the reference on every shard
     // (the reference re-draws it every iteration from the same seed, vamp.cpp:875-882: drawn and uploaded once here)
     const long bern_key = (long)seed + (long)dataset->get_S();
@@ -702,15 +702,20 @@ double vamp::g2d_onsager(double gam2, double tau, data* dataset) {
         dev.bern_key = bern_key;
         dev.ata_bern_state = 0;   // another probe: its A^T A product is not cached yet
     }
+    if (onsager_lanczos && lz_key != bern_key) {   // another probe (or another shard): its Krylov space starts over
+        lz_started = lz_exhausted = false;
+        lz_a.clear();
+        lz_b.clear();
+        lz_key = bern_key;
+    }
+}
+
+double vamp::g2d_onsager(double gam2, double tau, data* dataset) {
+    dev_open(dataset);
+    onsager_probe(dataset);
     this->gam2 = gam2;
     double d3[3] = {0, 0, 0};
     if (onsager_lanczos) {
-        if (lz_key != bern_key) {   // another probe (or another shard): its Krylov space starts over
-            lz_started = lz_exhausted = false;
-            lz_a.clear();
-            lz_b.clear();
-            lz_key = bern_key;
-        }
         last_cg_iters[1] = onsager_projected(gam2, tau, d3);
     } else if (onsager_warm) {   // GVB_ONSAGER_WARM=1: start from the previous iteration's Q^-1 u (same probe); the solve then stops on the residual only
         const int warm = (dev.onsager_age >= 0 && dev.onsager_age < 8) ? 1 : 2;
@@ -732,39 +737,69 @@ double vamp::g2d_onsager(double gam2, double tau, data* dataset) {
 //   w = B v_K ; a_K = <w, v_K> ; w -= a_K v_K + b_{K-1} v_{K-1} ; b_K = ||w|| ; v_{K+1} = w / b_K          (two bed sweeps per step)
 // All dots are rank sums, so every rank holds the same T.
 // ---------------------------------------------------------------------------------------------------
-void vamp::lanczos_extend(int K_needed) {
+void vamp::lanczos_begin() {
+    if (lz_started) return;
     gvb_ctx* ctx = dev.ctx;
-    if (!lz_started) {
-        gvb_vec xs[1] = {dev.bern};
-        double uu = 0;
-        DEV(gvb_vec_dots(ctx, 1, xs, nullptr, 1, &uu));
-        lz_unorm = sqrt(uu);
-        DEV(gvb_vec_axpby(ctx, dev.lz_cur, 1.0 / lz_unorm, dev.bern, 0.0, nullptr));
-        DEV(gvb_vec_fill(ctx, dev.lz_prev, 0.0));
-        lz_started = true;
+    gvb_vec xs[1] = {dev.bern};
+    double uu = 0;
+    DEV(gvb_vec_dots(ctx, 1, xs, nullptr, 1, &uu));
+    lz_unorm = sqrt(uu);
+    DEV(gvb_vec_axpby(ctx, dev.lz_cur, 1.0 / lz_unorm, dev.bern, 0.0, nullptr));
+    DEV(gvb_vec_fill(ctx, dev.lz_prev, 0.0));
+    lz_started = true;
+}
+
+void vamp::lanczos_finish_step() {
+    gvb_ctx* ctx = dev.ctx;
+    const int K = (int)lz_a.size();
+    DEV(gvb_dATx(ctx, dev.tmpN, dev.lz_w));
+    gvb_vec xs[1] = {dev.lz_w}, ys[1] = {dev.lz_cur};
+    double a = 0;
+    DEV(gvb_vec_dots(ctx, 1, xs, ys, 1, &a));
+    DEV(gvb_vec_axpby(ctx, dev.lz_w, 1.0, dev.lz_w, -a, dev.lz_cur));
+    if (K > 0) DEV(gvb_vec_axpby(ctx, dev.lz_w, 1.0, dev.lz_w, -lz_b[K - 1], dev.lz_prev));
+    double ww = 0;
+    DEV(gvb_vec_dots(ctx, 1, xs, nullptr, 1, &ww));
+    const double b = sqrt(ww);
+    lz_a.push_back(a);
+    lz_b.push_back(b);
+    if (!(b > 1e-13 * std::fabs(a))) {   // the Krylov space is exhausted (tiny shards): T is complete
+        lz_b.back() = 0.0;
+        lz_exhausted = true;
+        return;
     }
+    std::swap(dev.lz_prev, dev.lz_cur);                                               // v_{K-1} <- v_K
+    DEV(gvb_vec_axpby(ctx, dev.lz_cur, 1.0 / b, dev.lz_w, 0.0, nullptr));     // v_K <- w / b
+}
+
+void vamp::lanczos_extend(int K_needed) {
+    lanczos_begin();
     while ((int)lz_a.size() < K_needed && !lz_exhausted) {
-        const int K = (int)lz_a.size();
-        DEV(gvb_dAx(ctx, dev.lz_cur, dev.tmpN));
-        DEV(gvb_dATx(ctx, dev.tmpN, dev.lz_w));
-        gvb_vec xs[1] = {dev.lz_w}, ys[1] = {dev.lz_cur};
-        double a = 0;
-        DEV(gvb_vec_dots(ctx, 1, xs, ys, 1, &a));
-        DEV(gvb_vec_axpby(ctx, dev.lz_w, 1.0, dev.lz_w, -a, dev.lz_cur));
-        if (K > 0) DEV(gvb_vec_axpby(ctx, dev.lz_w, 1.0, dev.lz_w, -lz_b[K - 1], dev.lz_prev));
-        double ww = 0;
-        DEV(gvb_vec_dots(ctx, 1, xs, nullptr, 1, &ww));
-        const double b = sqrt(ww);
-        lz_a.push_back(a);
-        lz_b.push_back(b);
-        if (!(b > 1e-13 * std::fabs(a))) {   // the Krylov space is exhausted (tiny shards): T is complete
-            lz_b.back() = 0.0;
-            lz_exhausted = true;
-            break;
-        }
-        std::swap(dev.lz_prev, dev.lz_cur);                                               // v_{K-1} <- v_K
-        DEV(gvb_vec_axpby(ctx, dev.lz_cur, 1.0 / b, dev.lz_w, 0.0, nullptr));     // v_K <- w / b
+        DEV(gvb_dAx(dev.ctx, dev.lz_cur, dev.tmpN));
+        lanczos_finish_step();
     }
+}
+
+// stage 0: does the Krylov space want another step?  then its A v_K rides on this iteration's A p; stage 1: the step's tail
+int vamp::lanczos_companion(void* self, int stage, int iteration, gvb_vec* v, gvb_vec* av) {
+    (void)iteration;
+    vamp* me = static_cast<vamp*>(self);
+    if (stage == 0) {
+        if (me->lz_exhausted || (int)me->lz_a.size() >= me->CG_max_iter + 1) return 0;   // onsager_projected never asks for more
+        *v = me->dev.lz_cur;
+        *av = me->dev.tmpN;
+        return 1;
+    }
+    me->lanczos_finish_step();
+    return 0;
+}
+
+void vamp::lanczos_ride(data* dataset) {
+    if (!onsager_lanczos || !dual_sweep) return;
+    onsager_probe(dataset);
+    if (!lz_a.empty() || lz_exhausted) return;   // only the solve that meets an empty Krylov space carries its construction
+    lanczos_begin();
+    DEV(gvb_cg_set_companion(dev.ctx, &vamp::lanczos_companion, this));
 }
 
 // vamp::precondCG_solver(u, 0, tau, denoiser = 0) (vamp.cpp:1130-1229) in the coordinates of the Lanczos basis: u = ||u|| e_0, the operator is

@@ -263,6 +263,13 @@ int gvb_cg_prepare(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam
                    gvb_vec extra_v, gvb_vec extra_out);
 int gvb_cg_solve_prepared(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
                           gvb_vec ax_mu, gvb_vec ata_mu, int have_start, double* dots3);
+/* A companion product for the NEXT solve of this context (consumed by it; fn = NULL clears).  Before the product A p of iteration i the
+ * solver calls fn(user, 0, i, &v, &av); when that returns 1 and sets an M-vector v and an N-vector av, the iteration's X.v is ONE dual
+ * sweep {A p, av = A v}; after the iteration's X^T.u the solver calls fn(user, 1, i, &v, &av), where the companion finishes its own
+ * step (it may enqueue sweeps and synchronise; a negative return aborts the solve).  The solver's own results do not change by a bit.
+ * Used by vamp::infere_linear to let the Lanczos steps of the Onsager projection ride on the LMMSE solve of the first iteration. */
+typedef int (*gvb_cg_companion_fn)(void* user, int stage, int iteration, gvb_vec* v, gvb_vec* av);
+int gvb_cg_set_companion(gvb_ctx* ctx, gvb_cg_companion_fn fn, void* user);
 
 /* Zero-start solve against a right-hand side that recurs (the Onsager probe: the same Rademacher vector in every VAMP iteration,
  * vamp.cpp:875-882).  mu is cleared.  ata_rhs (M-vector) caches A^T A rhs: with a zero start the first search direction is rhs / diag,

@@ -571,6 +571,50 @@ def test_prepared_solve_is_bit_identical(C, oracle, start):
         assert b[7] == a[7] - 1
 
 
+def test_solve_with_a_companion_product(C, oracle):
+    """gvb_cg_set_companion: a companion's product A v rides on the A p of the solver's iterations (one dual sweep each).  The solver's
+    solution, log and iteration count do not change by a bit, the companion receives exactly gvb_dAx(v) every time it asks, the hook is
+    consumed by one solve, and an iteration enqueued speculatively after the exit still delivers the companion's product."""
+    import ctypes
+    N, M = 3000, 2600
+    bed = oracle.synth_bed(47, 0, M, N, miss_rate=0.01)
+    rng = np.random.default_rng(12)
+    rhs_h = rng.normal(size=M)
+    vs = [rng.normal(size=M) for _ in range(3)]
+    with C.Context(0) as ctx:
+        ctx.load_host(bed, N).compute_stats(1.0)
+        rhs, mu, mu_c = ctx.vecM(rhs_h), ctx.vecM(), ctx.vecM()
+        its, log = ctx.cg_solve(rhs, mu, 2.0, 0.7, 30, 1)
+        v, av, ref = ctx.vecM(), ctx.vecN(), ctx.vecN()
+        seen = []
+        FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p))
+
+        def companion(user, stage, i, pv, pav):
+            if stage == 0:
+                if i % 2 == 1:                          # every other iteration goes without
+                    return 0
+                v.upload(vs[i % 3])
+                pv[0], pav[0] = v.h, av.h
+                return 1
+            got = av.download()                         # stage 1: the product is there (the download synchronises)
+            ctx.dAx(v, ref)                             # ... and sweeps of the companion's own are allowed here
+            seen.append((i, np.array_equal(got, ref.download())))
+            return 0
+
+        cb = FN(companion)
+        assert ctx.L.gvb_cg_set_companion(ctx.h, ctypes.cast(cb, ctypes.c_void_p), None) == 0
+        s0, d0 = ctx.sweeps(), ctx.dual_sweeps()
+        its_c, log_c = ctx.cg_solve(rhs, mu_c, 2.0, 0.7, 30, 1)
+        n_dual = ctx.dual_sweeps() - d0
+        assert its_c == its and np.array_equal(log_c, log) and np.array_equal(mu.download(), mu_c.download())
+        assert [i for i, _ in seen] == [i for i in range(its + 1) if i % 2 == 0][:len(seen)] and len(seen) >= (its + 1) // 2
+        assert all(ok for _, ok in seen) and n_dual == len(seen)
+        assert ctx.sweeps() - s0 == 2 * its + len(seen) + (1 if len(seen) > (its + 1) // 2 else 0)   # the solver's own sweeps + the companion's dAx; a speculative dual counts
+        seen.clear()
+        its_d, _ = ctx.cg_solve(rhs, mu_c, 2.0, 0.7, 30, 1)   # the hook served one solve only
+        assert seen == [] and its_d <= 1                       # (mu_c is the solution: the solve stops at once)
+
+
 def test_cg_warm_start_products(C, oracle):
     """gvb_cg_solve_warm: a second solve (other rhs, tau, gam2) started from the first solve's solution with its A.mu / A^T A.mu
     by-products forms its initial residual without a sweep, runs the same iterations as gvb_cg_solve from the same start and

@@ -306,7 +306,13 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
     // an Onsager solve that does not start from zero stops on the residual only (see cg_scal_update_kernel)
     const int residual_only = (denoiser == 0 && have_start == 1) ? 1 : 0;
 
-    if (phase == 1 && !c->cg_ap) GVB_CUDA(gvb_malloc(c, &c->cg_ap, (size_t)c->Npad * sizeof(double)));
+    if (phase == 1 && c->cg_ap_cap < (size_t)c->Npad) {
+        if (c->cg_ap) cudaFree(c->cg_ap);
+        c->cg_ap = nullptr;
+        c->cg_ap_cap = 0;
+        GVB_CUDA(gvb_malloc(c, &c->cg_ap, (size_t)c->Npad * sizeof(double)));
+        c->cg_ap_cap = (size_t)c->Npad;
+    }
     // ---- initial residual r = rhs - Q mu_start ; p = r/diag
     const double* q = d->d;
     if (phase == 2) {

@@ -103,6 +103,7 @@ struct gvb_ctx {
     size_t tab_v2_cap = 0;
     int* shift_v2 = nullptr;
     unsigned long long* acc_dual = nullptr;
+    size_t acc_dual_cap = 0;
     size_t shift_cap = 0;
     unsigned long long* acc_i64 = nullptr;  // fixed-point accumulators
     size_t acc_i64_cap = 0;
@@ -135,6 +136,7 @@ struct gvb_ctx {
     std::vector<cudaEvent_t> prof_ev[3];   // [0] X.v, [1] X^T.u, [2] dual X.v : start/stop pairs
     size_t prof_used[3] = {0, 0, 0};
     std::vector<gvb_vec_s*> vecs;
+    size_t cg_ap_cap = 0;
     double* cg_ap = nullptr;        // A p0 of a prepared solve (gvb_cg_prepare), consumed by iteration 0 of gvb_cg_solve_prepared
     bool cg_prepared = false;
     gvb_cg_companion_fn cg_companion = nullptr;   // gvb_cg_set_companion: consumed by the next solve

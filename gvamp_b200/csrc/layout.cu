@@ -297,5 +297,7 @@ extern "C" int gvb_set_mask(gvb_ctx* c, const uint8_t* mask4, int nonas) {
     c->have_mask = true;
     c->have_stats = false;
     c->layout_gen++;   // by-products of earlier solves (A mu, A^T A mu, A^T y) describe another operator now
+    c->cg_prepared = false;   // ... and so does a prepared solve or a companion that was waiting for one
+    c->cg_companion = nullptr;
     return GVB_OK;
 }

@@ -1409,16 +1409,21 @@ int gvb_ax_tile_dual(gvb_ctx* c, const double* v0, const double* v1, double* out
     GVB_CHECK(ensure_scratch(c, false, true, false));
     const long n_tiles = c->Mg_pad / 32;
     const size_t tab2_ints = (size_t)n_tiles * 16384;
-    if (c->tab_v2_cap < tab2_ints) {
+    if (c->tab_v2_cap < tab2_ints) {   // tables and shifts of the second product: sized by the marker tiles
         if (c->tab_v2) cudaFree(c->tab_v2);
         if (c->shift_v2) cudaFree(c->shift_v2);
-        if (c->acc_dual) cudaFree(c->acc_dual);
-        c->tab_v2 = nullptr; c->shift_v2 = nullptr; c->acc_dual = nullptr;
+        c->tab_v2 = nullptr; c->shift_v2 = nullptr;
         c->tab_v2_cap = 0;
         GVB_CUDA(gvb_malloc(c, &c->tab_v2, tab2_ints * sizeof(int)));
         GVB_CUDA(gvb_malloc(c, &c->shift_v2, (size_t)n_tiles * sizeof(int)));
-        GVB_CUDA(gvb_malloc(c, &c->acc_dual, (size_t)c->Npad * sizeof(unsigned long long)));
         c->tab_v2_cap = tab2_ints;
+    }
+    if (c->acc_dual_cap < (size_t)c->Npad) {   // its accumulators: sized by the individuals (a reload may change either)
+        if (c->acc_dual) cudaFree(c->acc_dual);
+        c->acc_dual = nullptr;
+        c->acc_dual_cap = 0;
+        GVB_CUDA(gvb_malloc(c, &c->acc_dual, (size_t)c->Npad * sizeof(unsigned long long)));
+        c->acc_dual_cap = (size_t)c->Npad;
     }
     unsigned long long* accN0 = c->acc_i64 + 2 * (size_t)c->Mg_pad * 4;
     unsigned long long* accN1 = c->acc_dual;

@@ -289,6 +289,24 @@ def test_dual_ax_equals_two_sweeps(C, oracle, N, M, miss, monkeypatch):
     monkeypatch.delenv("GVB_TWIN_STRIPES")
 
 
+def test_dual_buffers_follow_a_reload(C, oracle):
+    """The second product's tables are sized by the marker tiles, its accumulators by the individuals: a context that reloads a
+    matrix with fewer markers but more individuals (and the other way round) must resize both."""
+    rng = np.random.default_rng(3)
+    with C.Context(0) as ctx:
+        for N, M in ((1200, 9000), (9000, 1200), (20_000, 700)):
+            bed = oracle.synth_bed(5, 0, M, N)
+            ctx.load_host(bed, N).compute_stats(1.0)
+            a, b, oa, ob, pa, pb = ctx.vecM(rng.normal(size=M)), ctx.vecM(rng.normal(size=M)), ctx.vecN(), ctx.vecN(), ctx.vecN(), ctx.vecN()
+            ctx.dAx(a, oa), ctx.dAx(b, ob)
+            ctx.dAx2(a, b, pa, pb)
+            assert np.array_equal(oa.download(), pa.download()) and np.array_equal(ob.download(), pb.download())
+            mu, ax, ata, z = ctx.vecM(), ctx.vecN(), ctx.vecM(), ctx.vecN()
+            ctx.cg_prepare(a, mu, 1.5, 0.9, 5, ax, ata, 2, b, z)
+            its, _, _ = ctx.cg_solve_prepared(a, mu, 1.5, 0.9, 5, 1, ax, ata, 2)
+            assert its >= 1 and np.array_equal(z.download(), ob.download())
+
+
 def test_nonfinite_inputs_turn_the_outputs_into_nan(C, oracle):
     """A NaN / infinity in the input vector: the reference's FP64 LUT products (0 * NaN, data.cpp:766 / :975) turn EVERY
     output into NaN.  The fixed-point sweeps cannot carry a NaN through their integer sums, so they flag it (bound kernel ->

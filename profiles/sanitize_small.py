@@ -48,6 +48,13 @@ for twin, stripes in (("0", None), ("1", None), (None, "30")):
                 assert np.all(np.isfinite(r))
                 x1 = ctx.vecM()
                 ctx.denoise(rhs, 3.0, [0.9, 0.06, 0.04], [0.0, 0.1, 1.0], x1)
+                v2, o1, o2, p1, p2 = ctx.vecM(0.5 * v + 1.0), ctx.vecN(), ctx.vecN(), ctx.vecN(), ctx.vecN()     # dual sweep, prepared solve
+                ctx.dAx(rhs, o1), ctx.dAx(v2, o2), ctx.dAx2(rhs, v2, p1, p2)
+                assert np.array_equal(o1.download(), p1.download()) and np.array_equal(o2.download(), p2.download())
+                mu2, ata = ctx.vecM(), ctx.vecM()
+                ctx.cg_prepare(rhs, mu2, 2.0, 0.7, 6, ax, ata, 2, v2, p2)
+                its2, _, _ = ctx.cg_solve_prepared(rhs, mu2, 2.0, 0.7, 6, 1, ax, ata, 2)
+                assert its2 == its_ref and np.array_equal(p2.download(), o2.download())
                 stage = ctx.vecM()
                 assert rhs.upload_changed(v, stage) is False and rhs.upload_changed(-v, stage) is True
                 ctx.snapshot_begin(rhs, M, 9)

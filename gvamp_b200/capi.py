@@ -46,6 +46,7 @@ SIGNATURES = {
     "gvb_profile_read_dual": (ci, [vp, c_f64p]),
     "gvb_dual_sweep_count": (cl, [vp]),
     "gvb_dAx2": (ci, [vp, vp, vp, vp, vp]),
+    "gvb_dATx2": (ci, [vp, vp, vp, vp, vp]),
     "gvb_divide_work": (None, [cl, ci, ci, ctypes.POINTER(cl), ctypes.POINTER(cl)]),
     "gvb_bed_load_file": (ci, [vp, ctypes.c_char_p, cl, cl, cl, cl]),
     "gvb_bed_load_host": (ci, [vp, c_u8p, cl, cl, cl, cl]),
@@ -478,6 +479,10 @@ class Context:
         out = np.zeros(4)
         _chk(self.L.gvb_profile_read(self.h, out.ctypes.data_as(c_f64p)), self.L)
         return dict(ax_ms=out[0], ax_n=int(out[1]), atx_ms=out[2], atx_n=int(out[3]))
+
+    def dATx2(self, u0, u1, out0, out1):
+        """out0 = X^T.u0, out1 = X^T.u1 from one pass over the bed (gvb_dATx2)"""
+        _chk(self.L.gvb_dATx2(self.h, u0.h, u1.h, out0.h, out1.h), self.L)
 
     def profile_read_dual(self):
         out = np.zeros(2)

@@ -163,7 +163,7 @@ extern "C" void gvb_ctx_destroy(gvb_ctx* c) {
     fr(c->tmpN); fr(c->tmpN2); fr(c->tmpM); fr(c->tmpM2); fr(c->wv); fr(c->cv); fr(c->ax_partial);
     gvb_misslist_reset(c);
     gvb_twin_reset(c);
-    fr(c->tab_u); fr(c->tab_v); fr(c->tab_v2); fr(c->shift_v2); fr(c->acc_dual); fr(c->cg_ap); fr(c->shift_u); fr(c->shift_v); fr(c->acc_i64); fr(c->red_partial); fr(c->red_result); fr(c->scal); fr(c->work_counter);
+    fr(c->tab_u); fr(c->tab_v); fr(c->tab_v2); fr(c->shift_v2); fr(c->acc_dual); fr(c->tab_u2); fr(c->shift_u2); fr(c->cg_ap); fr(c->shift_u); fr(c->shift_v); fr(c->acc_i64); fr(c->red_partial); fr(c->red_result); fr(c->scal); fr(c->work_counter);
     if (c->h_red) cudaFreeHost(c->h_red);
     fr(c->cg_dev); fr(c->cg_flags);
     if (c->cg_host) cudaFreeHost(c->cg_host);
@@ -465,6 +465,33 @@ extern "C" int gvb_dAx2(gvb_ctx* c, gvb_vec v0, gvb_vec v1, gvb_vec out0, gvb_ve
             "Ax2 needs two M-vectors and two N-vectors from gvb_vec_alloc_M/_N");
     GVB_ARG(out0 != out1, "the two products need two output vectors");
     return gvb_ax2_dev(c, v0->d, v1->d, out0->d, out1->d);
+}
+// out0 = X^T.u0, out1 = X^T.u1 from one pass over the bed (local products: nothing to all-reduce)
+int gvb_atx2_dev(gvb_ctx* c, const double* u0, const double* u1, double* out0, double* out1) {
+    GVB_ARG(c->have_stats, "compute_stats must run before ATx");
+#ifdef GVB_LEGACY_KERNELS
+    if (c->kernel_gen < 2) {
+        GVB_CHECK(gvb_atx_dev(c, u0, out0));
+        return gvb_atx_dev(c, u1, out1);
+    }
+#endif
+    if (c->total_missing > 0) {   // shards with missing genotypes: two single sweeps (gvb_atx_tile_dual)
+        GVB_CHECK(gvb_atx_dev(c, u0, out0));
+        return gvb_atx_dev(c, u1, out1);
+    }
+    prof_mark(c, 2);
+    int rc_mv = gvb_atx_tile_dual(c, u0, u1, out0, out1);
+    prof_mark(c, 2);
+    GVB_CHECK(rc_mv);
+    c->sweeps++;
+    c->dual_sweeps++;
+    return GVB_OK;
+}
+extern "C" int gvb_dATx2(gvb_ctx* c, gvb_vec u0, gvb_vec u1, gvb_vec out0, gvb_vec out1) {
+    GVB_ARG(c && u0 && u1 && out0 && out1 && u0->cap >= c->Npad && u1->cap >= c->Npad && out0->cap >= c->Mg_pad * 4 && out1->cap >= c->Mg_pad * 4,
+            "ATx2 needs two N-vectors and two M-vectors from gvb_vec_alloc_N/_M");
+    GVB_ARG(out0 != out1, "the two products need two output vectors");
+    return gvb_atx2_dev(c, u0->d, u1->d, out0->d, out1->d);
 }
 extern "C" int gvb_dATx(gvb_ctx* c, gvb_vec u, gvb_vec out) {
     GVB_ARG(c && u && out && u->cap >= c->Npad && out->cap >= c->Mg_pad * 4, "ATx needs an N-vector and an M-vector from gvb_vec_alloc_N/_M");

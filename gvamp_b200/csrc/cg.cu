@@ -353,7 +353,7 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
     gvb_cg_companion_fn companion = (phase != 1) ? c->cg_companion : nullptr;   // serves this solve only
     void* companion_user = c->cg_companion_user;
     if (phase != 1) c->cg_companion = nullptr;
-    bool last_had_companion = false;
+    bool last_had_companion = false, last_companion_atx = false;
     long companion_sweeps = 0;
     (void)companion_sweeps;
     {
@@ -365,7 +365,7 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
                 cg_d_from_cached_kernel<<<nbm, 256, 0, c->stream>>>(d->d, ata_rhs->d, diag, n);
                 GVB_LAUNCHED(c);
             } else {
-                gvb_vec cv = nullptr, cav = nullptr;
+                gvb_vec cv = nullptr, cav = nullptr, cw = nullptr;
                 bool with_companion = false;
                 if (phase == 2 && i == 0) {
                     ap = c->cg_ap;                                     // A p0 came with the dual sweep of gvb_cg_prepare
@@ -373,7 +373,7 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
                     // a companion (gvb_cg_set_companion) may ride on this iteration's A p: one dual sweep {A p, av = A v}.  That sweep is
                     // not predicated on the solver's exit flag - the companion's product must exist even when this iteration turns out
                     // to be a speculative one (A p is then simply not used)
-                    if (companion && companion(companion_user, 0, i, &cv, &cav) == 1) {
+                    if (companion && companion(companion_user, 0, i, &cv, &cav, &cw) == 1) {
                         GVB_ARG(cv && cav && cv->cap >= c->Mg_pad * 4 && cav->cap >= c->Npad, "the companion product needs an M- and an N-vector");
                         with_companion = true;
                         c->skip = nullptr;
@@ -386,10 +386,20 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
                     }
                 }
                 last_had_companion = with_companion;
-                GVB_CHECK(gvb_atx_dev(c, ap, d->d));
+                last_companion_atx = false;
+                if (with_companion && cw) {   // ... and its w = A^T av on this iteration's A^T (A p), the same way
+                    GVB_ARG(cw->cap >= c->Mg_pad * 4, "the companion's A^T product needs an M-vector");
+                    c->skip = nullptr;
+                    int rc2 = gvb_atx2_dev(c, ap, cav->d, d->d, cw->d);
+                    c->skip = flags;
+                    GVB_CHECK(rc2);
+                    last_companion_atx = true;
+                } else {
+                    GVB_CHECK(gvb_atx_dev(c, ap, d->d));
+                }
                 if (with_companion) {   // the companion finishes its own step (its sweeps and host-visible sums are not the solver's)
                     c->skip = nullptr;
-                    int rc2 = companion(companion_user, 1, i, &cv, &cav);
+                    int rc2 = companion(companion_user, 1, i, &cv, &cav, &cw);
                     c->skip = flags;
                     if (rc2 < 0) {
                         gvb_set_error("the companion of the solve failed in iteration %d", i);
@@ -447,7 +457,7 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
     // iterations enqueued after the solver had stopped ran as empty launches: they are not sweeps and carry no timing
     const int spec = enqueued - it_done;
     if (spec > 0) {
-        c->sweeps -= 2l * spec - ((last_had_companion && spec >= 1) ? 1 : 0);   // a companion's dual sweep ran in full
+        c->sweeps -= 2l * spec - ((last_had_companion && spec >= 1) ? (last_companion_atx ? 2 : 1) : 0);   // a companion's dual sweeps ran in full
         for (int w = 0; w < 2; w++)
             if (c->profile && c->prof_used[w] >= (size_t)(2 * spec)) c->prof_used[w] -= (size_t)(2 * spec);
     }
@@ -520,8 +530,9 @@ extern "C" int gvb_cg_solve_prepared(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double
 }
 
 // A companion for the NEXT solve of this context (consumed by it; NULL clears): before the product A p of an iteration the solver calls
-// fn(user, 0, i, &v, &av); when that returns 1 with an M-vector v and an N-vector av, the iteration's X.v becomes one dual sweep
-// {A p, av = A v}, and after the iteration's X^T.u the solver calls fn(user, 1, i, ...) so that the companion can finish its own step
+// fn(user, 0, i, &v, &av, &w); when that returns 1 with an M-vector v and an N-vector av, the iteration's X.v becomes one dual sweep
+// {A p, av = A v}; when it also sets an M-vector w, the iteration's X^T.u becomes a dual sweep too, {A^T (A p), w = A^T av}.  After
+// that the solver calls fn(user, 1, i, ...) so that the companion can finish its own step
 // (it may enqueue sweeps and synchronise; a negative return aborts the solve).  vamp::infere_linear lets the Lanczos steps of the
 // Onsager projection ride on the LMMSE solve of iteration 1 this way.
 extern "C" int gvb_cg_set_companion(gvb_ctx* c, gvb_cg_companion_fn fn, void* user) {

@@ -103,6 +103,9 @@ struct gvb_ctx {
     size_t tab_v2_cap = 0;
     int* shift_v2 = nullptr;
     unsigned long long* acc_dual = nullptr;
+    int32_t* tab_u2 = nullptr;      // dual X^T.u: interleaved per-stripe tables and the second product's shifts
+    size_t tab_u2_cap = 0;
+    int* shift_u2 = nullptr;
     size_t acc_dual_cap = 0;
     size_t shift_cap = 0;
     unsigned long long* acc_i64 = nullptr;  // fixed-point accumulators
@@ -231,6 +234,8 @@ int gvb_ax_lut(gvb_ctx* c, const double* v, double* out);
 int gvb_atx_lut(gvb_ctx* c, const double* u, double* out);
 int gvb_ax_tile(gvb_ctx* c, const double* v, double* out, int mode = 0);     // gen-2 sweeps (matvec_tile.cu); mode: ax_code_values
 int gvb_ax2_dev(gvb_ctx* c, const double* v0, const double* v1, double* out0, double* out1);   // dual sweep + all-reduce (capi.cu)
+int gvb_atx2_dev(gvb_ctx* c, const double* u0, const double* u1, double* out0, double* out1);   // dual X^T.u (capi.cu)
+int gvb_atx_tile_dual(gvb_ctx* c, const double* u0, const double* u1, double* out0, double* out1);
 int gvb_ax_tile_dual(gvb_ctx* c, const double* v0, const double* v1, double* out0, double* out1);   // two products, one bed read
 int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB = nullptr);   // outB[j] = sum_i b_ij u_i (optional)
 int gvb_count_tile_main(gvb_ctx* c, const int* tab, unsigned long long* acc);

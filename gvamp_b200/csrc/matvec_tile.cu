@@ -901,6 +901,129 @@ ax_dual_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tabv2, 
     release_work_counter(work_counter);
 }
 
+// The dual X^T.u: out0 = X^T.u0 and out1 = X^T.u1 from one pass over the shard, the per-stripe tables interleaved like those of the dual
+// X.v ([stripe][256 entries][32 slots][2 rhs]).  Bit-identical to two gvb_atx_tile calls on a shard without missing genotypes.
+__device__ __forceinline__ void atx_consume_dual(const char* __restrict__ tabc, uint32_t bb, const unsigned (&sp)[11], int (&a0)[4], int (&a1)[4]) {
+#pragma unroll
+    for (int tau = 0; tau < 32; tau++) {
+        const uint32_t w = lds32(bb ^ (uint32_t)(tau << 2));   // row lane, column tau ^ lane
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const unsigned a = prmt(w, sp[tau / 3], 0xF700u | (q << 4) | (4 + (tau % 3)));
+            const int2 val = *reinterpret_cast<const int2*>(tabc + a);
+            a0[q] += val.x;
+            a1[q] += val.y;
+        }
+    }
+}
+
+template <int NW, int NS>
+__global__ void __launch_bounds__(NW * 32 + 32, 1)
+atx_dual_kernel(const uint32_t* __restrict__ bed, const int* __restrict__ tab2, long Mg_pad, long n_stripes, int n_gblocks, int n_schunks,
+                int stripes_per_chunk, int* __restrict__ work_counter, unsigned long long* __restrict__ acc_out0, unsigned long long* __restrict__ acc_out1,
+                const int* __restrict__ skip, const int* __restrict__ shifts0, const int* __restrict__ shifts1) {
+    if (skip && *skip) return;
+    extern __shared__ __align__(1024) char smem[];
+    const PairLayout lay = pair_layout<NW, NS>(smem);
+    volatile int* s_item_p = reinterpret_cast<volatile int*>(smem + lay.ctrl_off);
+    const char* tabs = smem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool producer = warp == NW;
+    const uint32_t tab_sm = lay.tab;
+    const uint32_t bed_sm = lay.bed + (producer ? 0 : warp) * (NS * TILE_BYTES);
+    const uint32_t bar0 = lay.ctrl + 64 + 8 * ((producer ? 0 : warp) * NS);
+    if (lane == 0 && !producer) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    PairPipe pp;
+    pair_pipe_init(pp, lay.ctrl + 8, NW);
+    const uint64_t pol = policy_evict_first();
+    unsigned sp[11];
+    const uint32_t lane_off = lane * 132;
+    uint32_t n_fill = 0, n_use = 0;
+    const int n_items = n_gblocks * n_schunks;
+    const long n_tiles = Mg_pad / 32;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) *s_item_p = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int item = *s_item_p;
+        if (item >= n_items) break;
+        const int sc = item / n_gblocks, gb = item % n_gblocks;
+        const long step_lo = (long)sc * stripes_per_chunk;
+        const int ns = (int)min((long)stripes_per_chunk, n_stripes - step_lo);
+        if (producer) {   // one 64 KB region per stripe, regions alternating from 0
+            const int* src = tab2 + step_lo * (PAIR_REGION / 4);
+            for (int i = 0; i < ns; i++) {
+                const int r = i & 1;
+                uint32_t& f = r ? pp.fills1 : pp.fills0;
+                if (lane == 0) {
+                    mbar_wait(pp.empty + 8 * r, (f & 1) ^ 1);
+                    mbar_expect_tx(pp.full + 8 * r, PAIR_REGION);
+                    bulk_g2s_plain(tab_sm + r * PAIR_REGION, src + (long)i * (PAIR_REGION / 4), PAIR_REGION, pp.full + 8 * r);
+                }
+                f++;
+            }
+            continue;
+        }
+        const long T = (long)gb * NW + warp;
+        const bool active = T < n_tiles;
+        const uint32_t* bsrc = bed + (step_lo * Mg_pad + (active ? T : 0) * 32) * 32;   // + i * Mg_pad * 32 words per stripe
+        auto issue_bed = [&](int i) {
+            if (active && i < ns) {
+                if (lane == 0) {
+                    const uint32_t s = n_fill % NS;
+                    mbar_expect_tx(bar0 + 8 * s, TILE_BYTES);
+                    bulk_g2s(bed_sm + s * TILE_BYTES, bsrc + (long)i * Mg_pad * 32, TILE_BYTES, bar0 + 8 * s, pol);
+                }
+                n_fill++;
+            }
+        };
+#pragma unroll
+        for (int s = 0; s < NS - 1; s++) issue_bed(s);
+        long long acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+        make_spack_dual(sp, lane);   // region 0
+#pragma unroll 1
+        for (int i = 0; i < ns; i++) {
+            const int rgn = i & 1;
+            issue_bed(i + NS - 1);
+            {
+                const uint32_t f = rgn ? pp.fills1 : pp.fills0;
+                mbar_wait(pp.full + 8 * rgn, f & 1);
+                if (rgn) pp.fills1++; else pp.fills0++;
+            }
+            const int sh0 = __ldg(shifts0 + step_lo + i), sh1 = __ldg(shifts1 + step_lo + i);
+            if (active) {
+                const uint32_t s = n_use % NS;
+                mbar_wait(bar0 + 8 * s, (n_use / NS) & 1);
+                n_use++;
+                int a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+                atx_consume_dual(tabs, bed_sm + s * TILE_BYTES + lane_off, sp, a0, a1);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    acc0[q] += (long long)a0[q] << sh0;
+                    acc1[q] += (long long)a1[q] << sh1;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 11; j++) sp[j] ^= 0x01000000u;   // the other region
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pp.empty + 8 * rgn);
+        }
+        if (active) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (acc0[q] != 0) atomicAdd(acc_out0 + (T * 32 + lane) * 4 + q, (unsigned long long)acc0[q]);
+                if (acc1[q] != 0) atomicAdd(acc_out1 + (T * 32 + lane) * 4 + q, (unsigned long long)acc1[q]);
+            }
+        }
+    }
+    release_work_counter(work_counter);
+}
+
 // measured defaults (profiles/r02_sweep_tuning.txt)
 #define GVB_DEFAULT_TMA_WALK 1
 #define GVB_DEFAULT_TMA_GATHER 0
@@ -998,6 +1121,26 @@ int launch_ax_dual(gvb_ctx* c, unsigned long long* acc0, unsigned long long* acc
     int grid = std::min(n_sblocks * n_gchunks, c->sm_count);
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(TW ? c->bed_twin : c->bed, c->tab_v2, c->Mg_pad, stripe0, n_stripes, n_sblocks, n_gchunks, tpc, c->work_counter,
                                                        acc0, acc1, c->skip, c->shift_v, c->shift_v2);
+    GVB_LAUNCHED(c);
+    return GVB_OK;
+}
+
+template <int NW, int NS>
+int launch_atx_dual(gvb_ctx* c, unsigned long long* acc0, unsigned long long* acc1) {
+    using Cfg = PairCfg<NW, NS>;
+    auto kern = atx_dual_kernel<NW, NS>;
+    static unsigned long long attr_done = 0;
+    if (!(attr_done >> (c->device & 63) & 1ull)) {
+        GVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        attr_done |= 1ull << (c->device & 63);
+    }
+    const long n_tiles = c->Mg_pad / 32;
+    int n_gblocks = (int)((n_tiles + NW - 1) / NW);
+    const int spc = pick_chunk(tune().atx_stripes_per_chunk, n_gblocks, c->n_stripes, c->sm_count);
+    int n_schunks = (int)((c->n_stripes + spc - 1) / spc);
+    int grid = std::min(n_gblocks * n_schunks, c->sm_count);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, c->stream>>>(c->bed, c->tab_u2, c->Mg_pad, c->n_stripes, n_gblocks, n_schunks, spc, c->work_counter, acc0, acc1, c->skip,
+                                                       c->shift_u, c->shift_u2);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }
@@ -1217,7 +1360,7 @@ __global__ void __launch_bounds__(256) atx_prep_kernel(const double* __restrict_
 // tabm (shards with missing genotypes) holds the same sum over the MISSING codes with weight 1; accumulates sum_i U_i
 __global__ void __launch_bounds__(256) atx_build_kernel(const double* __restrict__ u, double window, double* __restrict__ scal, int* __restrict__ tab,
                                                         int* __restrict__ tabm, long long* __restrict__ usum, int* __restrict__ uq, const int* __restrict__ skip,
-                                                        int* __restrict__ shifts, int pairs) {
+                                                        int* __restrict__ shifts, int pairs, int dual_rhs) {
     if (skip && *skip) return;
     __shared__ int Us[4][32];   // [k][position]
     __shared__ double s_scale, s_scale0;
@@ -1265,7 +1408,7 @@ __global__ void __launch_bounds__(256) atx_build_kernel(const double* __restrict
 #pragma unroll 4
     for (int B = warp; B < 256; B += 8) {
         const unsigned c0 = B & 3, c1 = (B >> 2) & 3, c2 = (B >> 4) & 3, c3 = B >> 6;
-        const size_t at = gvb_tab_index(t, B, lane, pairs);
+        const size_t at = dual_rhs < 0 ? gvb_tab_index(t, B, lane, pairs) : (size_t)(t * 256 + B) * 64 + lane * 2 + dual_rhs;
         tab[at] = dosage_of(c0) * U0 + dosage_of(c1) * U1 + dosage_of(c2) * U2 + dosage_of(c3) * U3;
         if (tabm) tabm[at] = (c0 == 1u ? U0 : 0) + (c1 == 1u ? U1 : 0) + (c2 == 1u ? U2 : 0) + (c3 == 1u ? U3 : 0);
     }
@@ -1467,7 +1610,7 @@ int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB) {
     atx_prep_kernel<<<nb, 256, 0, c->stream>>>(u, npos, c->scal, acc, (long)((miss ? 2 : 1) * Mpad), usum, c->skip);
     GVB_LAUNCHED(c);
     atx_build_kernel<<<(unsigned)c->n_stripes, 256, 0, c->stream>>>(u, 32.0, c->scal, c->tab_u, (miss && !list) ? c->tab_u + total : nullptr, usum,
-                                                                    list ? c->uq : nullptr, c->skip, c->shift_u, c->tab_pairs);
+                                                                    list ? c->uq : nullptr, c->skip, c->shift_u, c->tab_pairs, -1);
     GVB_LAUNCHED(c);
     GVB_CHECK(atx_main(c, c->tab_u, acc));
     if (list)
@@ -1476,6 +1619,49 @@ int gvb_atx_tile(gvb_ctx* c, const double* u, double* out, double* outB) {
         GVB_CHECK(atx_main(c, c->tab_u + total, accm));
     atx_finish_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, c->stream>>>(acc, miss ? accm : nullptr, usum, c->scal, c->mave, c->msig, (long)Mpad, c->M,
                                                                              1.0 / sqrt((double)c->N), out, outB, c->skip, list ? GVB_CLASS_BITS * GVB_CLASS_MAX : 0);
+    GVB_LAUNCHED(c);
+    return GVB_OK;
+}
+
+// out0 = X^T.u0 and out1 = X^T.u1 of the local shard from one pass over the bed (atx_dual_kernel); bit-identical to two gvb_atx_tile
+// calls.  Shards with missing genotypes keep two single sweeps (their second term comes from one list / one quantised copy of u).
+int gvb_atx_tile_dual(gvb_ctx* c, const double* u0, const double* u1, double* out0, double* out1) {
+    if (c->total_missing > 0) {
+        GVB_CHECK(gvb_atx_tile(c, u0, out0, nullptr));
+        return gvb_atx_tile(c, u1, out1, nullptr);
+    }
+    GVB_CHECK(ensure_scratch(c, true, false, false));
+    const size_t tab2_ints = (size_t)c->n_stripes * 16384;
+    if (c->tab_u2_cap < tab2_ints) {
+        if (c->tab_u2) cudaFree(c->tab_u2);
+        if (c->shift_u2) cudaFree(c->shift_u2);
+        c->tab_u2 = nullptr; c->shift_u2 = nullptr;
+        c->tab_u2_cap = 0;
+        GVB_CUDA(gvb_malloc(c, &c->tab_u2, tab2_ints * sizeof(int)));
+        GVB_CUDA(gvb_malloc(c, &c->shift_u2, (size_t)c->n_stripes * sizeof(int)));
+        c->tab_u2_cap = tab2_ints;
+    }
+    const size_t Mpad = (size_t)c->Mg_pad * 4;
+    const long npos = c->n_stripes * 32;
+    unsigned long long* acc0 = c->acc_i64;
+    unsigned long long* acc1 = c->acc_i64 + Mpad;   // the accumulators of the missing-genotype term: unused on this shard
+    long long* usum0 = reinterpret_cast<long long*>(c->acc_i64 + 2 * Mpad + c->Npad);
+    long long* usum1 = usum0 + 1;
+    double* scal1 = c->scal + 32;
+    int nb = (int)std::max(1l, std::min((npos + 255) / 256, 2l * c->sm_count));
+    atx_prep_kernel<<<nb, 256, 0, c->stream>>>(u0, npos, c->scal, acc0, (long)Mpad, usum0, c->skip);
+    GVB_LAUNCHED(c);
+    atx_prep_kernel<<<nb, 256, 0, c->stream>>>(u1, npos, scal1, acc1, (long)Mpad, usum1, c->skip);
+    GVB_LAUNCHED(c);
+    atx_build_kernel<<<(unsigned)c->n_stripes, 256, 0, c->stream>>>(u0, 32.0, c->scal, c->tab_u2, nullptr, usum0, nullptr, c->skip, c->shift_u, c->tab_pairs, 0);
+    GVB_LAUNCHED(c);
+    atx_build_kernel<<<(unsigned)c->n_stripes, 256, 0, c->stream>>>(u1, 32.0, scal1, c->tab_u2, nullptr, usum1, nullptr, c->skip, c->shift_u2, c->tab_pairs, 1);
+    GVB_LAUNCHED(c);
+    GVB_CHECK((launch_atx_dual<12, 2>(c, acc0, acc1)));
+    const double isn = 1.0 / sqrt((double)c->N);
+    atx_finish_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, c->stream>>>(acc0, nullptr, usum0, c->scal, c->mave, c->msig, (long)Mpad, c->M, isn, out0, nullptr, c->skip, 0);
+    GVB_LAUNCHED(c);
+    atx_finish_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, c->stream>>>(acc1, nullptr, usum1, scal1, c->mave, c->msig, (long)Mpad, c->M, isn, out1, nullptr, c->skip, 0);
     GVB_LAUNCHED(c);
     return GVB_OK;
 }

@@ -749,10 +749,10 @@ void vamp::lanczos_begin() {
     lz_started = true;
 }
 
-void vamp::lanczos_finish_step() {
+void vamp::lanczos_finish_step(bool have_w) {
     gvb_ctx* ctx = dev.ctx;
     const int K = (int)lz_a.size();
-    DEV(gvb_dATx(ctx, dev.tmpN, dev.lz_w));
+    if (!have_w) DEV(gvb_dATx(ctx, dev.tmpN, dev.lz_w));
     gvb_vec xs[1] = {dev.lz_w}, ys[1] = {dev.lz_cur};
     double a = 0;
     DEV(gvb_vec_dots(ctx, 1, xs, ys, 1, &a));
@@ -781,16 +781,17 @@ void vamp::lanczos_extend(int K_needed) {
 }
 
 // stage 0: does the Krylov space want another step?  then its A v_K rides on this iteration's A p; stage 1: the step's tail
-int vamp::lanczos_companion(void* self, int stage, int iteration, gvb_vec* v, gvb_vec* av) {
+int vamp::lanczos_companion(void* self, int stage, int iteration, gvb_vec* v, gvb_vec* av, gvb_vec* w) {
     (void)iteration;
     vamp* me = static_cast<vamp*>(self);
     if (stage == 0) {
         if (me->lz_exhausted || (int)me->lz_a.size() >= me->CG_max_iter + 1) return 0;   // onsager_projected never asks for more
         *v = me->dev.lz_cur;
         *av = me->dev.tmpN;
+        *w = me->dev.lz_w;        // both halves of the step's A^T A v_K come with the solver's sweeps
         return 1;
     }
-    me->lanczos_finish_step();
+    me->lanczos_finish_step(*w != nullptr);
     return 0;
 }
 

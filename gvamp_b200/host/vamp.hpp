@@ -92,10 +92,10 @@ private:
     void lanczos_extend(int K_needed);
     void onsager_probe(data* dataset);   // draws / uploads the probe of (seed, shard) once and restarts the Krylov space when it changed
     void lanczos_begin();                // v_0 = u / ||u||
-    void lanczos_finish_step();          // the tail of a step whose A v_K sits in dev.tmpN: w = A^T (A v_K), the recurrence, v_{K+1}
+    void lanczos_finish_step(bool have_w = false);   // the tail of a step whose A v_K sits in dev.tmpN: w = A^T (A v_K) unless it came with a dual sweep, the recurrence, v_{K+1}
     // In the first LMMSE solve after the Krylov space was started the Lanczos steps ride on the solver's iterations: each iteration's A p
     // and the step's A v_K come from one dual sweep (gvb_cg_set_companion); GVB_DUAL_SWEEP=0: every step sweeps for itself
-    static int lanczos_companion(void* self, int stage, int iteration, gvb_vec* v, gvb_vec* av);
+    static int lanczos_companion(void* self, int stage, int iteration, gvb_vec* v, gvb_vec* av, gvb_vec* w);
     void lanczos_ride(data* dataset);    // registers the companion for the next solve when there is a Krylov space to build
     int onsager_projected(double gam2, double tau, double* d3);
     void print_cg_log(const std::vector<double>& log, int iters, int denoiser);

@@ -206,6 +206,8 @@ int gvb_dATx(gvb_ctx* ctx, gvb_vec u, gvb_vec out);
  * data::Ax twice on independent vectors (z1 = A x1_hat, vamp.cpp:430, and the first operator application of the LMMSE solve,
  * vamp.cpp:1146) the bed is read once.  Bit-identical to two gvb_dAx calls. */
 int gvb_dAx2(gvb_ctx* ctx, gvb_vec v0, gvb_vec v1, gvb_vec out0, gvb_vec out1);
+/* ... and the same for X^T.u: out0 = X^T.u0, out1 = X^T.u1 from one pass (shards with missing genotypes: two single sweeps). */
+int gvb_dATx2(gvb_ctx* ctx, gvb_vec u0, gvb_vec u1, gvb_vec out0, gvb_vec out1);
 
 /* ---- denoiser and EM prior update ---------------------------------------------------------------- */
 /* x1_hat = g1(r1), sums[0] = sum_i g1d(r1_i) over ALL ranks, sums[1] = ||x1_hat - r1||^2 over all
@@ -263,12 +265,14 @@ int gvb_cg_prepare(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam
                    gvb_vec extra_v, gvb_vec extra_out);
 int gvb_cg_solve_prepared(gvb_ctx* ctx, gvb_vec rhs, gvb_vec mu, double tau, double gam2, int max_iter, int denoiser, int* iters, double* log4,
                           gvb_vec ax_mu, gvb_vec ata_mu, int have_start, double* dots3);
-/* A companion product for the NEXT solve of this context (consumed by it; fn = NULL clears).  Before the product A p of iteration i the
- * solver calls fn(user, 0, i, &v, &av); when that returns 1 and sets an M-vector v and an N-vector av, the iteration's X.v is ONE dual
- * sweep {A p, av = A v}; after the iteration's X^T.u the solver calls fn(user, 1, i, &v, &av), where the companion finishes its own
- * step (it may enqueue sweeps and synchronise; a negative return aborts the solve).  The solver's own results do not change by a bit.
- * Used by vamp::infere_linear to let the Lanczos steps of the Onsager projection ride on the LMMSE solve of the first iteration. */
-typedef int (*gvb_cg_companion_fn)(void* user, int stage, int iteration, gvb_vec* v, gvb_vec* av);
+/* A companion for the NEXT solve of this context (consumed by it; fn = NULL clears).  Before the product A p of iteration i the solver
+ * calls fn(user, 0, i, &v, &av, &w); when that returns 1 and sets an M-vector v and an N-vector av, the iteration's X.v is ONE dual
+ * sweep {A p, av = A v}; when it also sets an M-vector w, the iteration's X^T.u is a dual sweep too, {A^T (A p), w = A^T av} (w = NULL:
+ * the companion sweeps for it itself).  Then the solver calls fn(user, 1, i, &v, &av, &w), where the companion finishes its own step (it
+ * may enqueue sweeps and synchronise; a negative return aborts the solve).  The solver's own results do not change by a bit.  Used by
+ * vamp::infere_linear to let the Lanczos steps of the Onsager projection (the reference's second solve with the same operator,
+ * vamp.cpp:884) ride on the LMMSE solve of the first iteration (vamp.cpp:594-599). */
+typedef int (*gvb_cg_companion_fn)(void* user, int stage, int iteration, gvb_vec* v, gvb_vec* av, gvb_vec* w);
 int gvb_cg_set_companion(gvb_ctx* ctx, gvb_cg_companion_fn fn, void* user);
 
 /* Zero-start solve against a right-hand side that recurs (the Onsager probe: the same Rademacher vector in every VAMP iteration,

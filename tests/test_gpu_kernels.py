@@ -289,6 +289,38 @@ def test_dual_ax_equals_two_sweeps(C, oracle, N, M, miss, monkeypatch):
     monkeypatch.delenv("GVB_TWIN_STRIPES")
 
 
+@pytest.mark.parametrize("N,M,miss", [(70_001, 301, 0.0), (4099, 1030, 0.0), (1200, 9000, 0.0), (2500, 333, 0.05)])
+def test_dual_atx_equals_two_sweeps(C, oracle, N, M, miss):
+    """gvb_dATx2: X^T.u0 and X^T.u1 from one pass over the bed, bit for bit two gvb_dATx calls - with phenotype NAs, ragged shapes,
+    vectors in different scale classes, a zero vector, a non-finite entry; on a shard with missing genotypes the call is two single
+    sweeps (and says so in its counters)."""
+    bed = oracle.synth_bed(43, 0, M, N, miss_rate=miss)
+    present = np.ones(N, bool)
+    present[np.random.default_rng(6).choice(N, N // 40, replace=False)] = False
+    mask4 = oracle.make_mask4(N, present)
+    rng = np.random.default_rng(9)
+    u0 = rng.normal(size=N) * present
+    u1 = rng.normal(size=N) * np.where(rng.random(N) < 0.01, 1e6, 1e-3) * present
+    with C.Context(0) as ctx:
+        ctx.load_host(bed, N).set_mask(mask4, int(present.sum())).compute_stats(1.0)
+        a, b, oa, ob, pa, pb = ctx.vecN(u0), ctx.vecN(u1), ctx.vecM(), ctx.vecM(), ctx.vecM(), ctx.vecM()
+        for x, y in ((u0, u1), (u1, u0), (u0, np.zeros(N)), (u0, u0)):
+            a.upload(x), b.upload(y)
+            ctx.dATx(a, oa), ctx.dATx(b, ob)
+            s0, d0 = ctx.sweeps(), ctx.dual_sweeps()
+            ctx.dATx2(a, b, pa, pb)
+            assert (ctx.sweeps() - s0, ctx.dual_sweeps() - d0) == ((1, 1) if miss == 0.0 else (2, 0))
+            assert np.array_equal(oa.download(), pa.download()) and np.array_equal(ob.download(), pb.download())
+        bad = u1.copy()
+        bad[N // 2] = np.inf
+        a.upload(u0), b.upload(bad)
+        ctx.dATx(a, oa)
+        ctx.dATx2(a, b, pa, pb)
+        assert np.array_equal(oa.download(), pa.download()) and np.all(np.isnan(pb.download()[:M]))
+        ctx.dATx2(a, b, pa, pb)
+        assert np.array_equal(oa.download(), pa.download())
+
+
 def test_dual_buffers_follow_a_reload(C, oracle):
     """The second product's tables are sized by the marker tiles, its accumulators by the individuals: a context that reloads a
     matrix with fewer markers but more individuals (and the other way round) must resize both."""
@@ -595,7 +627,7 @@ def test_solve_with_a_companion_product(C, oracle):
     consumed by one solve, and an iteration enqueued speculatively after the exit still delivers the companion's product."""
     import ctypes
     N, M = 3000, 2600
-    bed = oracle.synth_bed(47, 0, M, N, miss_rate=0.01)
+    bed = oracle.synth_bed(47, 0, M, N)          # no missing genotypes: the dual X^T.u is a real dual sweep
     rng = np.random.default_rng(12)
     rhs_h = rng.normal(size=M)
     vs = [rng.normal(size=M) for _ in range(3)]
@@ -603,20 +635,27 @@ def test_solve_with_a_companion_product(C, oracle):
         ctx.load_host(bed, N).compute_stats(1.0)
         rhs, mu, mu_c = ctx.vecM(rhs_h), ctx.vecM(), ctx.vecM()
         its, log = ctx.cg_solve(rhs, mu, 2.0, 0.7, 30, 1)
-        v, av, ref = ctx.vecM(), ctx.vecN(), ctx.vecN()
+        v, av, ref, w, wref = ctx.vecM(), ctx.vecN(), ctx.vecN(), ctx.vecM(), ctx.vecM()
         seen = []
-        FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p))
+        PV = ctypes.POINTER(ctypes.c_void_p)
+        FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, PV, PV, PV)
 
-        def companion(user, stage, i, pv, pav):
+        def companion(user, stage, i, pv, pav, pw):
             if stage == 0:
                 if i % 2 == 1:                          # every other iteration goes without
                     return 0
                 v.upload(vs[i % 3])
                 pv[0], pav[0] = v.h, av.h
+                if i % 4 == 0:                          # ... and every other companion iteration also wants w = A^T av
+                    pw[0] = w.h
                 return 1
-            got = av.download()                         # stage 1: the product is there (the download synchronises)
+            got = av.download()                         # stage 1: the products are there (the download synchronises)
             ctx.dAx(v, ref)                             # ... and sweeps of the companion's own are allowed here
-            seen.append((i, np.array_equal(got, ref.download())))
+            ok = np.array_equal(got, ref.download())
+            if pw[0]:
+                ctx.dATx(ref, wref)
+                ok = ok and np.array_equal(w.download(), wref.download())
+            seen.append((i, ok))
             return 0
 
         cb = FN(companion)
@@ -626,8 +665,10 @@ def test_solve_with_a_companion_product(C, oracle):
         n_dual = ctx.dual_sweeps() - d0
         assert its_c == its and np.array_equal(log_c, log) and np.array_equal(mu.download(), mu_c.download())
         assert [i for i, _ in seen] == [i for i in range(its + 1) if i % 2 == 0][:len(seen)] and len(seen) >= (its + 1) // 2
-        assert all(ok for _, ok in seen) and n_dual == len(seen)
-        assert ctx.sweeps() - s0 == 2 * its + len(seen) + (1 if len(seen) > (its + 1) // 2 else 0)   # the solver's own sweeps + the companion's dAx; a speculative dual counts
+        assert all(ok for _, ok in seen)
+        n_w = sum(1 for i, _ in seen if i % 4 == 0)
+        assert n_dual == len(seen) + n_w                                       # one dual X.v per companion iteration, a dual X^T.u where w was asked for
+        assert ctx.sweeps() - s0 >= 2 * its + len(seen) + n_w                  # the solver's own sweeps + the sweeps of the companion's checks
         seen.clear()
         its_d, _ = ctx.cg_solve(rhs, mu_c, 2.0, 0.7, 30, 1)   # the hook served one solve only
         assert seen == [] and its_d <= 1                       # (mu_c is the solution: the solve stops at once)

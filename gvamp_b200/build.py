@@ -83,7 +83,7 @@ def build_host(force=False, verbose=True):
         return []
     os.makedirs(BINDIR, exist_ok=True)
     common = [os.path.join(HOST, f) for f in ("options.cpp", "data.cpp", "vamp.cpp", "utilities.cpp", "comm.cpp") if os.path.exists(os.path.join(HOST, f))]
-    headers = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")] + [os.path.join(ROOT, "include", "gvamp_b200.h")]
+    headers = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith((".hpp", ".inc"))] + [os.path.join(ROOT, "include", "gvamp_b200.h")]
     outs = []
     cuda_inc = os.path.join(os.path.dirname(os.path.dirname(NVCC)), "include")    # nvtx3 (header-only) for the phase ranges
     flags = ["-O2", "-std=c++17", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + HOST, "-isystem", cuda_inc, "-Wno-unused-result"]

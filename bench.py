@@ -701,7 +701,7 @@ def run_probit(args, D, ctx, H, N, Mt, S, M, logf):
         out["ms_dev"], sw = run(K, False, 0)
         out["launches"] = ctx.launches() - launches0
         out["host_syncs"] = ctx.host_syncs() - syncs0
-        out["prof"] = ctx.profile_read()
+        out["prof"] = {**ctx.profile_read(), **ctx.profile_read_dual()}
         ctx.profile(False)
         out["clocks"] = sampler.stop() if sampler else None
         out["ms_e2e"], sw2 = run(K, True, 1)
@@ -746,7 +746,7 @@ def run_sweeps(args, D, ctx, H, N, Mt, S, M, logf):
     out["ms_dev"] = ctx.timer_ms(0) * (K / max(its, 1))
     out["launches"] = ctx.launches() - launches0
     out["host_syncs"] = ctx.host_syncs() - syncs0
-    out["prof"] = ctx.profile_read()
+    out["prof"] = {**ctx.profile_read(), **ctx.profile_read_dual()}
     ctx.profile(False)
     out["clocks"] = sampler.stop() if sampler else None
     out["sweeps"] = [ctx.sweeps() - s0]

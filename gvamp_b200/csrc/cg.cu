@@ -354,8 +354,6 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
     void* companion_user = c->cg_companion_user;
     if (phase != 1) c->cg_companion = nullptr;
     bool last_had_companion = false, last_companion_atx = false;
-    long companion_sweeps = 0;
-    (void)companion_sweeps;
     {
         SkipGuard guard(c);
         c->skip = flags;
@@ -380,7 +378,6 @@ static int cg_solve_impl(gvb_ctx* c, gvb_vec rhs, gvb_vec mu, double tau, double
                         int rc2 = gvb_ax2_dev(c, p->d, cv->d, ap, cav->d);
                         c->skip = flags;
                         GVB_CHECK(rc2);
-                        companion_sweeps++;
                     } else {
                         GVB_CHECK(gvb_ax_dev(c, p->d, ap, true));      // d = Q p
                     }
